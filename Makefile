@@ -1,0 +1,23 @@
+# Builds the C-ABI shared library (sm_100a only) and the oracle helpers.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+SRC_DIR   := tricolo_b200/csrc
+SRCS      := $(wildcard $(SRC_DIR)/*.cu)
+OBJS      := $(patsubst $(SRC_DIR)/%.cu,build/%.o,$(SRCS))
+LIB       := tricolo_b200/lib/libtricolo_b200.so
+
+all: $(LIB)
+
+build/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.h) $(wildcard $(SRC_DIR)/*.cuh) include/tricolo_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	@mkdir -p tricolo_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart shared
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean

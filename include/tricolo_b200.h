@@ -1,0 +1,191 @@
+/*
+ * tricolo_b200 — C ABI of the sm_100a embedding-similarity hot path.
+ *
+ * This is the drop-in boundary for the two reference entry points
+ *   tricolo/loss/nt_xent.py:24        NTXentLoss.forward(zis, zjs, norm=True)
+ *   tricolo/evaluation/eval_retrieval.py:249  compute_metrics(dataset, embeddings_dict)
+ * (and the callers tricolo/model/tricolo_net.py:56-65 / :90-97).  The reference has no
+ * FFI of its own (pure PyTorch / NumPy); the Python host in
+ * tricolo_b200/ binds these symbols with ctypes, INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name says host; the caller allocates every buffer, including
+ *     workspaces (query the *_workspace_bytes functions); the library never
+ *     allocates, frees or retains device memory.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *     (no hidden synchronisation).
+ *   - return value: 0 = OK, otherwise one of TCL_ERR_* (>= 1000: 1000 +
+ *     cudaError_t); tcl_last_error_string() gives the text (thread-local).
+ *   - sm_100 only: any other device returns TCL_ERR_BAD_ARCH.  There is no
+ *     fallback path of any kind.
+ */
+#ifndef TRICOLO_B200_H_
+#define TRICOLO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCL_ABI_VERSION 1
+
+enum {
+  TCL_OK = 0,
+  TCL_ERR_BAD_SHAPE = 1,
+  TCL_ERR_BAD_ALIGN = 2,
+  TCL_ERR_BAD_ARCH = 3,
+  TCL_ERR_BAD_ARG = 4,
+  TCL_ERR_DRIVER = 5,
+  TCL_ERR_WORKSPACE = 6,
+  TCL_ERR_CUDA_BASE = 1000
+};
+
+/* 16-bit tensor-core operand formats (tcgen05 kind::f16 takes either). */
+enum { TCL_OP_F16 = 0, TCL_OP_BF16 = 1 };
+/* element types of user tensors */
+enum { TCL_DT_F32 = 0, TCL_DT_F16 = 1, TCL_DT_BF16 = 2, TCL_DT_F64 = 3 };
+
+#define TCL_MAX_TENSORS 3 /* text, image, voxel */
+#define TCL_MAX_PAIRS 3   /* (text,image) (text,voxel) (image,voxel): tricolo_net.py:59-63 */
+
+int tcl_version(void);
+const char* tcl_last_error_string(void);
+
+/* ---------------------------------------------------------------------------
+ * K1 — L2-normalise prologue.           replaces nt_xent.py:56-57 (F.normalize)
+ * For each of n_tensors row-major [rows, dim] inputs: inv_norm[r] = 1/max(||x_r||, eps),
+ * z[r,:] = x[r,:] * inv_norm[r] rounded to the 16-bit operand format.
+ * x_row_stride in elements.  dim % 8 == 0.
+ * ------------------------------------------------------------------------- */
+int tcl_l2norm_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t rows,
+                   int64_t dim, int64_t x_row_stride, void* const* z_host_ptrs, int op_format,
+                   float* const* inv_norm_host_ptrs, float eps, void* stream);
+
+/* 16-bit cast without normalisation (retrieval uses the raw dot product,
+ * eval_retrieval.py:74).  Accepts f32/f64/f16/bf16 input. */
+int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t x_row_stride,
+                   void* y, int op_format, void* stream);
+
+/* [rows, dim] 16-bit -> [dim, ld_t] 16-bit (ld_t >= rows, ld_t % 8 == 0); operand
+ * layout of the gradient GEMM in tcl_ntxent_bwd. */
+int tcl_transpose_16bit(int n_tensors, const void* const* z_host_ptrs, int64_t rows, int64_t dim,
+                        void* const* zt_host_ptrs, int64_t ld_t, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2 — similarity GEMM + fused sum-exp epilogue.   replaces nt_xent.py:62-72 forward
+ * For each pair p: S = Zrow_p [n_rows, dim] · Zcol_p [n_cols, dim]^T on tcgen05 (fp32
+ * accumulate in TMEM); the logits never leave the SM.  With c1 = log2(e)/tau:
+ *   row_sumexp[p][i] = sum_j 2^(c1*S_ij - c1)      (complete for the given rows)
+ *   col_sumexp[p][j] = sum_i 2^(c1*S_ij - c1)      (partial: only the given rows)
+ *   diag2[p][i]      = c1 * S_{i, row_offset+i}    (log2-domain logit of the positive)
+ * The fixed shift c1 is exact for normalised inputs (|S| <= 1); requires
+ * 2/tau*log2(e) < 120, i.e. tau >= 0.025 (checked).
+ * n_rows = rows held locally (global index row_offset + i), n_cols = global batch.
+ * dim % 64 == 0, dim <= 512.
+ * ------------------------------------------------------------------------- */
+size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, int64_t n_cols);
+int tcl_ntxent_fwd(int n_pairs, const void* const* zrow_host_ptrs,
+                   const void* const* zcol_host_ptrs, int64_t n_rows, int64_t n_cols, int64_t dim,
+                   int64_t row_offset, int op_format, float inv_tau, float* row_sumexp,
+                   float* col_sumexp, float* diag2, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* Finalise: log2-domain LSEs and the per-pair loss.     nt_xent.py:20-21,71-74
+ *   lse2_row[p][i] = log2(row_sumexp) + c1,  lse2_col[p][j] likewise (needs the
+ *   all-reduced col_sumexp when rows are sharded over ranks)
+ *   loss_parts[p][0] = ln2 * sum_i (lse2_row_i - diag2_i)
+ *   loss_parts[p][1] = ln2 * sum_i (lse2_col_{row_offset+i} - diag2_i)
+ *   loss[p] = (alpha*parts0 + (1-alpha)*parts1) / n_cols     (only meaningful when the
+ *             call holds all rows; sharded callers all-reduce loss_parts instead) */
+int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row_offset,
+                        float inv_tau, float alpha, const float* row_sumexp,
+                        const float* col_sumexp, const float* diag2, float* lse2_row,
+                        float* lse2_col, float* loss_parts, float* loss, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K3 — recompute-based backward.       replaces autograd of nt_xent.py:55-74
+ * One "job" per tensor that needs a gradient; a job has 1-2 "segments", one per
+ * pair the tensor takes part in.  For a segment the kernel re-forms the logit
+ * tile S = Zself · Zother^T, builds
+ *   G_ij = w_self * 2^(c1 S_ij - lse2_self_i) + w_other * 2^(c1 S_ij - lse2_other_j) - [i==j]
+ * in registers, writes it as a 16-bit operand tile to shared memory and
+ * accumulates  dZself += G · Zother  in TMEM.  Then (second kernel) the
+ * normalise backward  dx = (g - (g·z) z) * inv_norm,  g = grad_scale/(tau*n_other) * acc.
+ * w_self / lse2_self belong to the softmax taken along the OTHER index for a fixed
+ * self row (row softmax when self is the pair's first argument: w = alpha).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const void* z_other;     /* [n_other, dim] 16-bit */
+  const void* z_other_t;   /* [dim, ld_t]   16-bit (tcl_transpose_16bit) */
+  const float* lse2_self;  /* [n_self]  */
+  const float* lse2_other; /* [n_other] */
+  const float* grad_scale; /* device scalar dL/d(loss of this pair); NULL = 1 */
+  float w_self;
+  float w_other;
+} tcl_bwd_segment;
+
+typedef struct {
+  const void* z_self;    /* [n_self, dim] 16-bit */
+  const void* x_self;    /* original input rows [n_self, dim], x_dtype */
+  const float* inv_norm; /* [n_self] from tcl_l2norm_fwd */
+  void* dx;              /* [n_self, dim] output, x_dtype */
+  int32_t n_segments;
+  int32_t reserved;
+  tcl_bwd_segment seg[2];
+} tcl_bwd_job;
+
+size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int64_t dim);
+int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int64_t n_other,
+                   int64_t dim, int64_t self_offset, int64_t ld_t, int x_dtype,
+                   int64_t x_row_stride, int op_format, float inv_tau, float eps,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2' — similarity GEMM for retrieval.           replaces eval_retrieval.py:74 (np.dot)
+ * S[q, g] = Q[q,:] · G[g,:] (raw dot product, no normalisation), 16-bit operands,
+ * fp32 accumulate, fp32 output with leading dimension ld_s (ld_s % 4 == 0).
+ * dim % 8 == 0.
+ * ------------------------------------------------------------------------- */
+int tcl_sim_gemm(const void* q, const void* g, int64_t n_q, int64_t n_g, int64_t dim,
+                 int op_format, float* s, int64_t ld_s, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K4 — per-query top-k + rank of the ground truth.  replaces eval_retrieval.py:75-82,184-186
+ * Order: (similarity descending, gallery index ascending) — the stated tie-break.
+ * For each query row of S [n_q, n_g] (ld_s):
+ *   topk_val/topk_idx[q][0..k)  best k entries, idx = idx_base + column
+ *   gt_sim[q]   = S[q, label[q]-idx_base]         (only written when gt_sim_in == NULL)
+ *   n_before[q] = #{ j : S_qj > s_gt  or (S_qj == s_gt and idx_base+j < label[q]) }
+ * so that rank = 1 + n_before (summed over gallery shards).  When the gallery is
+ * sharded, pass the all-reduced ground-truth similarity in gt_sim_in.
+ * k <= 16.  labels are global gallery indices.
+ * ------------------------------------------------------------------------- */
+int tcl_topk_rank(const float* s, int64_t ld_s, int64_t n_q, int64_t n_g, int k,
+                  const int64_t* labels, int64_t idx_base, const float* gt_sim_in,
+                  float* topk_val, int32_t* topk_idx, float* gt_sim_out, int32_t* n_before,
+                  void* stream);
+
+/* gt_sim[q] = S[q, label[q]-idx_base] if the label falls in [idx_base, idx_base+n_g) else 0
+ * (shard owner contributes, the others add zero in the all-reduce). */
+int tcl_gather_gt_sim(const float* s, int64_t ld_s, int64_t n_q, int64_t n_g,
+                      const int64_t* labels, int64_t idx_base, float* gt_sim, void* stream);
+
+/* Merge n_shards sorted candidate lists per query (layout [n_shards][n_q][k]) into one
+ * top-k under the same order. */
+int tcl_topk_merge(const float* cand_val, const int32_t* cand_idx, int n_shards, int64_t n_q,
+                   int k, float* topk_val, int32_t* topk_idx, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Bring-up / test hooks (not part of the product path).
+ * tcl_debug_tmem_probe: writes lane*64+col into a 128x32 TMEM block and reads it back
+ * through the 16x256b load shape; out[(warp*2+half)*32*16 + thread*16 + reg].
+ * ------------------------------------------------------------------------- */
+int tcl_debug_tmem_probe(uint32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRICOLO_B200_H_ */

@@ -1,0 +1,149 @@
+"""ctypes binding of the C-ABI library ``libtricolo_b200.so`` (include/tricolo_b200.h).
+
+The library is the only compute path of this package: if it cannot be loaded
+the import fails loudly — there is no PyTorch / CPU fallback (BASELINE.json
+north_star: "no Triton, no multi-backend dispatch and no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtricolo_b200.so"
+
+TCL_OP_F16, TCL_OP_BF16 = 0, 1
+TCL_DT_F32, TCL_DT_F16, TCL_DT_BF16, TCL_DT_F64 = 0, 1, 2, 3
+
+_DTYPE_CODE = {
+    torch.float32: TCL_DT_F32,
+    torch.float16: TCL_DT_F16,
+    torch.bfloat16: TCL_DT_BF16,
+    torch.float64: TCL_DT_F64,
+}
+_OP_TORCH = {TCL_OP_F16: torch.float16, TCL_OP_BF16: torch.bfloat16}
+
+
+class TricoloB200Error(RuntimeError):
+    """Non-zero return code from the C ABI."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tricolo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class BwdSegment(C.Structure):
+    _fields_ = [
+        ("z_other", C.c_void_p),
+        ("z_other_t", C.c_void_p),
+        ("lse2_self", C.c_void_p),
+        ("lse2_other", C.c_void_p),
+        ("grad_scale", C.c_void_p),
+        ("w_self", C.c_float),
+        ("w_other", C.c_float),
+    ]
+
+
+class BwdJob(C.Structure):
+    _fields_ = [
+        ("z_self", C.c_void_p),
+        ("x_self", C.c_void_p),
+        ("inv_norm", C.c_void_p),
+        ("dx", C.c_void_p),
+        ("n_segments", C.c_int32),
+        ("reserved", C.c_int32),
+        ("seg", BwdSegment * 2),
+    ]
+
+
+# symbol -> (restype, argtypes); the single source for the loader and for the
+# CPU test that checks every declared symbol is exported.
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "tcl_version": (_i, []),
+    "tcl_last_error_string": (C.c_char_p, []),
+    "tcl_l2norm_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _pp, _i, _pp, _f, _vp]),
+    "tcl_cast_16bit": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp]),
+    "tcl_transpose_16bit": (_i, [_i, _pp, _i64, _i64, _pp, _i64, _vp]),
+    "tcl_ntxent_fwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
+    "tcl_ntxent_fwd": (_i, [_i, _pp, _pp, _i64, _i64, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tcl_ntxent_finalize": (_i, [_i, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tcl_ntxent_bwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
+    "tcl_ntxent_bwd": (_i, [_i, C.POINTER(BwdJob), _i64, _i64, _i64, _i64, _i64, _i, _i64, _i, _f, _f, _vp, _sz, _vp]),
+    "tcl_sim_gemm": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _i64, _vp]),
+    "tcl_topk_rank": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tcl_gather_gt_sim": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "tcl_topk_merge": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "tcl_debug_tmem_probe": (_i, [_vp, _vp]),
+}
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("TRICOLO_B200_LIB", str(_LIB_PATH)))
+
+
+def _load() -> C.CDLL:
+    path = lib_path()
+    if not path.exists():
+        raise ImportError(
+            f"tricolo_b200: {path} not found. Build it with `make` (or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`) — there is no fallback path."
+        )
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+LIB = _load()
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise TricoloB200Error(code, LIB.tcl_last_error_string().decode("utf-8", "replace"))
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f"tricolo_b200: unsupported dtype {t.dtype}") from None
+
+
+def op_torch_dtype(op_format: int) -> torch.dtype:
+    return _OP_TORCH[op_format]
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def ptr_array(tensors) -> "C.Array":
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def stream_ptr(device=None) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "tricolo_b200 runs on sm_100a only: got a tensor on "
+                f"{t.device}; there is no CPU path in this package"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tricolo_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev

@@ -1,0 +1,59 @@
+// Host-side helpers shared by the C-ABI entry points: error plumbing, device
+// check, TMA tensor-map encoding through the driver entry point (no link-time
+// dependency on libcuda).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tcl {
+
+// thread-local last error text, read back through tcl_last_error_string()
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define TCL_CHECK_CUDA(expr)                                                             \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::tcl::set_error(TCL_ERR_CUDA_BASE + static_cast<int>(_e), "%s: %s", \
+                              #expr, cudaGetErrorString(_e));                            \
+  } while (0)
+
+#define TCL_REQUIRE(cond, code, ...)                           \
+  do {                                                         \
+    if (!(cond)) return ::tcl::set_error((code), __VA_ARGS__); \
+  } while (0)
+
+// 0 when the current device is sm_100 (B200); error otherwise.  Cached per device.
+int require_sm100();
+
+// Encode a 2D row-major [rows, cols] 16-bit tensor for TMA tiled loads with a
+// {box_cols, box_rows} box and the 128-byte swizzle.  Out-of-bounds elements
+// are zero-filled (ragged edge tiles rely on this).
+int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+
+// normalise backward (l2norm.cu), launched by tcl_ntxent_bwd after the gradient GEMM
+struct NormBwdJob {
+  const void* x;
+  const float* inv_norm;
+  const float* gpart;  // [n_split][rows][dim]
+  const float* scale;  // device scalar written by the gradient kernel
+  void* dx;
+};
+struct NormBwdParams {
+  NormBwdJob job[3];
+};
+int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim,
+                      int64_t x_stride, int n_split, float eps, cudaStream_t st);
+
+static inline bool aligned_to(const void* p, size_t a) {
+  return (reinterpret_cast<uintptr_t>(p) % a) == 0;
+}
+
+}  // namespace tcl

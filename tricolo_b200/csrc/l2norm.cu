@@ -1,0 +1,335 @@
+// K1 (L2-normalise prologue), 16-bit cast, 16-bit transpose and the normalise
+// backward.  All HBM-bound streaming kernels: one warp per row, 16-byte
+// vector accesses, fp32 math.
+//
+// Reference semantics: torch.nn.functional.normalize(p=2, dim=1) as called at
+// tricolo/loss/nt_xent.py:56-57, i.e. x / max(||x||_2, eps) with eps = 1e-12,
+// and its autograd.
+#include "host_common.h"
+#include "../../include/tricolo_b200.h"
+
+namespace tcl {
+
+struct PtrPack3 {
+  const void* in[TCL_MAX_TENSORS];
+  void* out[TCL_MAX_TENSORS];
+  float* aux[TCL_MAX_TENSORS];
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<double>(const double* p, float (&v)[4]) {
+  double2 a = *reinterpret_cast<const double2*>(p);
+  double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = (float)a.x; v[1] = (float)a.y; v[2] = (float)b.x; v[3] = (float)b.y;
+}
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&t.x));
+  float2 b = __half22float2(*reinterpret_cast<__half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<double>(double* p, const float (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, const float (&v)[4]) {
+  uint2 t;
+  *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(v[0], v[1]);
+  *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 t;
+  *reinterpret_cast<__nv_bfloat162*>(&t.x) = __floats2bfloat162_rn(v[0], v[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&t.y) = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// K1: one warp per row.  kNormalise=false gives the plain 16-bit cast.
+// The row is read once into registers when dim <= 32*4*kMaxIter, else twice.
+// ---------------------------------------------------------------------------
+template <typename TIn, typename TOut, bool kNormalise>
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(PtrPack3 pk, int64_t rows, int dim,
+                                                         int64_t x_stride, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const TIn* x = static_cast<const TIn*>(pk.in[blockIdx.y]) + row * x_stride;
+  TOut* z = static_cast<TOut*>(pk.out[blockIdx.y]) + row * dim;
+  constexpr int kMaxIter = 4;  // 512 elements stay in registers
+  float v[kMaxIter][4];
+  float ss = 0.f;
+  const bool in_regs = dim <= 32 * 4 * kMaxIter;
+  if (in_regs) {
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < dim) {
+        load4<TIn>(x + c, v[it]);
+        ss += v[it][0] * v[it][0] + v[it][1] * v[it][1] + v[it][2] * v[it][2] + v[it][3] * v[it][3];
+      }
+    }
+  } else if (kNormalise) {
+    for (int c = lane * 4; c < dim; c += 128) {
+      float t[4];
+      load4<TIn>(x + c, t);
+      ss += t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3];
+    }
+  }
+  float inv = 1.f;
+  if (kNormalise) {
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0) pk.aux[blockIdx.y][row] = inv;
+  }
+  if (in_regs) {
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < dim) {
+        float o[4] = {v[it][0] * inv, v[it][1] * inv, v[it][2] * inv, v[it][3] * inv};
+        store4<TOut>(z + c, o);
+      }
+    }
+  } else {
+    for (int c = lane * 4; c < dim; c += 128) {
+      float t[4];
+      load4<TIn>(x + c, t);
+      float o[4] = {t[0] * inv, t[1] * inv, t[2] * inv, t[3] * inv};
+      store4<TOut>(z + c, o);
+    }
+  }
+}
+
+template <typename TIn, bool kNormalise>
+static int launch_fwd_t(const PtrPack3& pk, int n_tensors, int64_t rows, int dim, int64_t stride,
+                        int op_format, float eps, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_tensors);
+  if (op_format == TCL_OP_F16)
+    l2norm_fwd_kernel<TIn, __half, kNormalise><<<grid, 256, 0, st>>>(pk, rows, dim, stride, eps);
+  else
+    l2norm_fwd_kernel<TIn, __nv_bfloat16, kNormalise>
+        <<<grid, 256, 0, st>>>(pk, rows, dim, stride, eps);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+template <bool kNormalise>
+static int launch_fwd(const PtrPack3& pk, int n_tensors, int x_dtype, int64_t rows, int dim,
+                      int64_t stride, int op_format, float eps, cudaStream_t st) {
+  switch (x_dtype) {
+    case TCL_DT_F32: return launch_fwd_t<float, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
+    case TCL_DT_F64: return launch_fwd_t<double, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
+    case TCL_DT_F16: return launch_fwd_t<__half, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
+    case TCL_DT_BF16: return launch_fwd_t<__nv_bfloat16, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
+  }
+  return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
+}
+
+static size_t dtype_size(int dt) {
+  return dt == TCL_DT_F32 ? 4 : dt == TCL_DT_F64 ? 8 : 2;
+}
+
+// ---------------------------------------------------------------------------
+// 16-bit transpose: [rows, dim] -> [dim, ld_t], 64x64 tiles through shared memory
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose16_kernel(PtrPack3 pk, int64_t rows, int dim,
+                                                          int64_t ld_t) {
+  __shared__ uint16_t tile[64][66];
+  const uint16_t* in = static_cast<const uint16_t*>(pk.in[blockIdx.z]);
+  uint16_t* out = static_cast<uint16_t*>(pk.out[blockIdx.z]);
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  // read: each thread reads 2 adjacent columns (4 bytes) of 8 rows
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + i * 8;
+    const int c = tx * 2;
+    uint32_t w = 0;
+    if (r0 + r < rows && c0 + c < dim)
+      w = *reinterpret_cast<const uint32_t*>(in + (r0 + r) * dim + c0 + c);
+    tile[r][c] = static_cast<uint16_t>(w & 0xffffu);
+    tile[r][c + 1] = static_cast<uint16_t>(w >> 16);
+  }
+  __syncthreads();
+  // write: out[c0 + c][r0 + r], two adjacent r per thread
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = ty + i * 8;
+    const int r = tx * 2;
+    if (c0 + c < dim && r0 + r < rows) {
+      const uint32_t w = static_cast<uint32_t>(tile[r][c]) |
+                         (static_cast<uint32_t>(r0 + r + 1 < rows ? tile[r + 1][c] : 0) << 16);
+      uint16_t* dst = out + static_cast<int64_t>(c0 + c) * ld_t + r0 + r;
+      if (r0 + r + 1 < ld_t)
+        *reinterpret_cast<uint32_t*>(dst) = w;
+      else
+        *dst = static_cast<uint16_t>(w & 0xffffu);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Normalise backward (+ reduction of the split-K partials of the gradient GEMM).
+//   g  = scale * sum_s gpart[s][row][:]
+//   z  = x * inv
+//   dx = clamped ? g * inv : (g - (g.z) z) * inv
+// "clamped" (||x|| < eps): the reference's clamp_min has zero derivative there, so
+// the projection term vanishes.
+// ---------------------------------------------------------------------------
+
+template <typename T>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(NormBwdParams pr, int64_t rows, int dim,
+                                                         int64_t x_stride, int n_split, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const NormBwdJob& jb = pr.job[blockIdx.y];
+  const T* x = static_cast<const T*>(jb.x) + row * x_stride;
+  T* dx = static_cast<T*>(jb.dx) + row * dim;
+  const float inv = jb.inv_norm[row];
+  const float scale = *jb.scale;
+  const bool clamped = inv >= 1.f / eps;
+  constexpr int kMaxIter = 4;
+  float g[kMaxIter][4], z[kMaxIter][4];
+  float dot = 0.f;
+  const int64_t split_stride = rows * static_cast<int64_t>(dim);
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < dim) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < n_split; ++s) {
+        float t[4];
+        load4<float>(jb.gpart + s * split_stride + row * dim + c, t);
+        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += t[3];
+      }
+      float xv[4];
+      load4<T>(x + c, xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[it][e] = acc[e] * scale;
+        z[it][e] = xv[e] * inv;
+        dot += g[it][e] * z[it][e];
+      }
+    }
+  }
+  dot = warp_sum(dot);
+  if (clamped) dot = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < dim) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (g[it][e] - dot * z[it][e]) * inv;
+      store4<T>(dx + c, o);
+    }
+  }
+}
+
+int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim,
+                      int64_t x_stride, int n_split, float eps, cudaStream_t st) {
+  TCL_REQUIRE(dim <= 512 && dim % 4 == 0, TCL_ERR_BAD_SHAPE, "normalise backward: dim %d > 512", dim);
+  dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_jobs);
+  switch (x_dtype) {
+    case TCL_DT_F32: l2norm_bwd_kernel<float><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
+    case TCL_DT_F64: l2norm_bwd_kernel<double><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
+    case TCL_DT_F16: l2norm_bwd_kernel<__half><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
+    case TCL_DT_BF16: l2norm_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
+    default: return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
+  }
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+}  // namespace tcl
+
+using namespace tcl;
+
+extern "C" int tcl_l2norm_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t rows,
+                              int64_t dim, int64_t x_row_stride, void* const* z, int op_format,
+                              float* const* inv_norm, float eps, void* stream) {
+  TCL_REQUIRE(n_tensors >= 1 && n_tensors <= TCL_MAX_TENSORS, TCL_ERR_BAD_ARG, "n_tensors %d", n_tensors);
+  TCL_REQUIRE(rows >= 0 && dim >= 8 && dim % 8 == 0, TCL_ERR_BAD_SHAPE,
+              "l2norm: dim must be a positive multiple of 8 (got %lld)", (long long)dim);
+  TCL_REQUIRE(x_row_stride >= dim && (x_row_stride * dtype_size(x_dtype)) % 16 == 0, TCL_ERR_BAD_ALIGN,
+              "l2norm: row stride %lld not 16-byte aligned", (long long)x_row_stride);
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  if (int e = require_sm100()) return e;
+  if (rows == 0) return TCL_OK;
+  PtrPack3 pk{};
+  for (int i = 0; i < n_tensors; ++i) {
+    TCL_REQUIRE(x[i] && z[i] && inv_norm[i], TCL_ERR_BAD_ARG, "l2norm: null pointer (tensor %d)", i);
+    TCL_REQUIRE(aligned_to(x[i], 16) && aligned_to(z[i], 16), TCL_ERR_BAD_ALIGN, "l2norm: pointers must be 16-byte aligned");
+    pk.in[i] = x[i]; pk.out[i] = z[i]; pk.aux[i] = inv_norm[i];
+  }
+  return launch_fwd<true>(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, op_format, eps,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim,
+                              int64_t x_row_stride, void* y, int op_format, void* stream) {
+  TCL_REQUIRE(rows >= 0 && dim >= 8 && dim % 8 == 0, TCL_ERR_BAD_SHAPE,
+              "cast: dim must be a positive multiple of 8 (got %lld)", (long long)dim);
+  TCL_REQUIRE(x && y && aligned_to(x, 16) && aligned_to(y, 16), TCL_ERR_BAD_ALIGN, "cast: pointers must be non-null, 16-byte aligned");
+  TCL_REQUIRE(x_row_stride >= dim && (x_row_stride * dtype_size(x_dtype)) % 16 == 0, TCL_ERR_BAD_ALIGN, "cast: row stride");
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  if (int e = require_sm100()) return e;
+  if (rows == 0) return TCL_OK;
+  PtrPack3 pk{};
+  pk.in[0] = x; pk.out[0] = y;
+  return launch_fwd<false>(pk, 1, x_dtype, rows, (int)dim, x_row_stride, op_format, 0.f,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tcl_transpose_16bit(int n_tensors, const void* const* z, int64_t rows, int64_t dim,
+                                   void* const* zt, int64_t ld_t, void* stream) {
+  TCL_REQUIRE(n_tensors >= 1 && n_tensors <= TCL_MAX_TENSORS, TCL_ERR_BAD_ARG, "n_tensors %d", n_tensors);
+  TCL_REQUIRE(rows >= 0 && dim >= 2 && dim % 2 == 0, TCL_ERR_BAD_SHAPE, "transpose: dim %lld", (long long)dim);
+  TCL_REQUIRE(ld_t >= rows && ld_t % 8 == 0, TCL_ERR_BAD_ALIGN, "transpose: ld_t %lld must be >= rows and a multiple of 8", (long long)ld_t);
+  if (int e = require_sm100()) return e;
+  if (rows == 0) return TCL_OK;
+  PtrPack3 pk{};
+  for (int i = 0; i < n_tensors; ++i) {
+    TCL_REQUIRE(z[i] && zt[i] && aligned_to(z[i], 4) && aligned_to(zt[i], 16), TCL_ERR_BAD_ALIGN, "transpose: pointer alignment");
+    pk.in[i] = z[i]; pk.out[i] = zt[i];
+  }
+  dim3 grid(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((dim + 63) / 64), n_tensors);
+  transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pk, rows, (int)dim, ld_t);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}

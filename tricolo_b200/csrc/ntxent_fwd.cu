@@ -1,0 +1,432 @@
+// K2 — NT-Xent forward: similarity GEMM on tcgen05 with a fused sum-exp
+// epilogue.  Replaces tricolo/loss/nt_xent.py:62-72 (torch.eye, the two
+// matmuls, the two log_softmax passes); the B x B logits exist only in TMEM.
+//
+// Work decomposition: CTA (i-block, j-split, pair) keeps its 128 rows of the row
+// operand resident in shared memory (dim/64 swizzled 16 KB K-blocks) and sweeps a
+// range of 128-column tiles of the column operand, streamed through a TMA ring.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM owner), 2..5 = epilogue.
+// Two 128-column TMEM accumulators alternate so the epilogue of tile t overlaps
+// the MMAs of tile t+1.
+//
+// Epilogue math (c1 = log2(e)/tau, fixed shift c1 because |S| <= 1 after K1):
+//   e_ij = 2^(c1*S_ij - c1); row sums stay in registers across the sweep, column
+//   sums of the tile are reduced over the 128 rows with a register butterfly
+//   (quad TMEM load layout) and written to a per-(i-block) partial buffer, so the
+//   final sums are formed in a fixed order (deterministic, no atomics).
+#include "host_common.h"
+#include "../../include/tricolo_b200.h"
+
+namespace tcl {
+
+static constexpr int FW_BM = 128, FW_BN = 128, FW_BK = 64;
+static constexpr int FW_KB_BYTES = FW_BM * FW_BK * 2;  // 16 KB
+static constexpr int FW_MAX_KB = 8;                     // dim <= 512
+static constexpr int FW_STAGES = 5;
+static constexpr int FW_THREADS = 192;
+
+struct FwdParams {
+  CUtensorMap tm_row[TCL_MAX_PAIRS];
+  CUtensorMap tm_col[TCL_MAX_PAIRS];
+  float* row_part;  // [pairs][n_jsplit][n_rows]
+  float* col_part;  // [pairs][n_iblocks][n_cols]
+  float* diag2;     // [pairs][n_rows]
+  int n_rows, n_cols, row_offset;
+  int num_kb, n_jtiles, n_jsplit, n_iblocks;
+  float c1;
+  uint32_t idesc;
+};
+
+// shared memory map (offsets from the 1024-aligned base)
+struct FwdSmem {
+  static constexpr uint32_t x_off = 0;                                      // num_kb * 16 KB
+  static constexpr uint32_t ring_off(int num_kb) { return num_kb * FW_KB_BYTES; }
+  static constexpr uint32_t bar_off(int num_kb) { return ring_off(num_kb) + FW_STAGES * FW_KB_BYTES; }
+  // barriers: full[S], empty[S], x_full, tmem_full[2], tmem_empty[2]  (8 B each), tmem slot (4 B)
+  static constexpr uint32_t colbuf_off(int num_kb) { return bar_off(num_kb) + 256; }  // 2*4*128 floats
+  static constexpr uint32_t total(int num_kb) { return colbuf_off(num_kb) + 2 * 4 * 128 * 4 + 1024; }
+};
+
+template <bool kMasked>
+__device__ __forceinline__ void fwd_tile_epilogue(uint32_t tmem_acc, int q, int lane, float c1,
+                                                  float (&rs)[4], float (&cs)[32], int row_base,
+                                                  int col_base, int n_rows, int n_cols,
+                                                  int diag_delta, bool has_diag, float* diag_out) {
+  // quad layout: ql = lane/4 -> rows, p = lane%4 -> column pairs
+  const int ql = lane >> 2, p = lane & 3;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) cs[c] = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r_lo = q * 32 + h * 16 + ql;  // tile-local rows r_lo and r_lo + 8
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t v[16];
+      tmem_ld_16x256b_x4(tmem_addr(tmem_acc, q * 32 + h * 16, cc * 32), v);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = cc * 32 + g * 8 + 2 * p + e;  // tile-local column
+          const float s0 = __uint_as_float(v[4 * g + e]);      // row r_lo
+          const float s1 = __uint_as_float(v[4 * g + 2 + e]);  // row r_lo + 8
+          float e0 = ex2_approx(fmaf(s0, c1, -c1));
+          float e1 = ex2_approx(fmaf(s1, c1, -c1));
+          if (has_diag) {
+            // global row index == global column index  <=>  local col == local row + diag_delta
+            if (col == r_lo + diag_delta && (!kMasked || row_base + r_lo < n_rows))
+              diag_out[r_lo] = s0 * c1;
+            if (col == r_lo + 8 + diag_delta && (!kMasked || row_base + r_lo + 8 < n_rows))
+              diag_out[r_lo + 8] = s1 * c1;
+          }
+          if (kMasked) {
+            const bool cv = col_base + col < n_cols;
+            const bool r0v = row_base + r_lo < n_rows;
+            const bool r1v = row_base + r_lo + 8 < n_rows;
+            e0 = (cv && r0v) ? e0 : 0.f;
+            e1 = (cv && r1v) ? e1 : 0.f;
+          }
+          rs[2 * h + 0] += e0;
+          rs[2 * h + 1] += e1;
+          cs[cc * 8 + g * 2 + e] += e0 + e1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const int num_kb = P.num_kb;
+  const uint32_t x_smem = base + FwdSmem::x_off;
+  const uint32_t ring = base + FwdSmem::ring_off(num_kb);
+  const uint32_t bars = base + FwdSmem::bar_off(num_kb);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (FW_STAGES + s); };
+  const uint32_t x_full_bar = bars + 8u * (2 * FW_STAGES);
+  auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * FW_STAGES + 1 + b); };
+  auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * FW_STAGES + 3 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * FW_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + FwdSmem::bar_off(num_kb) + 8u * (2 * FW_STAGES + 5));
+  float* colbuf = reinterpret_cast<float*>(base_ptr + FwdSmem::colbuf_off(num_kb));  // [2][4][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ib = blockIdx.x, js = blockIdx.y, pair = blockIdx.z;
+  const int i0 = ib * FW_BM;
+  // contiguous range of column tiles for this split
+  const int t_begin = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * js) / P.n_jsplit);
+  const int t_end = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * (js + 1)) / P.n_jsplit);
+  const int n_tiles = t_end - t_begin;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&P.tm_row[pair]);
+    tma_prefetch_desc(&P.tm_col[pair]);
+    for (int s = 0; s < FW_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(x_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // resident row block
+      mbar_arrive_expect_tx(x_full_bar, num_kb * FW_KB_BYTES);
+      for (int kb = 0; kb < num_kb; ++kb)
+        tma_load_2d(x_smem + kb * FW_KB_BYTES, &P.tm_row[pair], x_full_bar, kb * FW_BK, i0);
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = (t_begin + t) * FW_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % FW_STAGES;
+          const uint32_t ph = (it / FW_STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), FW_KB_BYTES);
+          tma_load_2d(ring + s * FW_KB_BYTES, &P.tm_col[pair], full_bar(s), kb * FW_BK, j0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(x_full_bar, 0);
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int b = t & 1;
+        mbar_wait(tmem_empty_bar(b), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem + b * FW_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % FW_STAGES;
+          const uint32_t ph = (it / FW_STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_k_sw128(x_smem + kb * FW_KB_BYTES);
+          const uint64_t bd = umma_desc_k_sw128(ring + s * FW_KB_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < FW_BK / 16; ++kk)
+            tc_mma_f16(acc, ad + 2 * kk, bd + 2 * kk, P.idesc, (kb | kk) != 0);
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tmem_full_bar(b));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
+    const int ql = lane >> 2, p = lane & 3;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    float cs[32];
+    float* diag_out = P.diag2 + static_cast<int64_t>(pair) * P.n_rows + i0;
+    const bool row_edge = i0 + FW_BM > P.n_rows;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int b = t & 1;
+      const int j0 = (t_begin + t) * FW_BN;
+      mbar_wait(tmem_full_bar(b), (t >> 1) & 1);
+      tc_fence_after();
+      // diagonal: global row = row_offset + i0 + r, global col = j0 + c  ->  c = r + delta
+      const int diag_delta = P.row_offset + i0 - j0;
+      const bool has_diag = diag_delta > -FW_BN && diag_delta < FW_BM;
+      const bool masked = row_edge || (j0 + FW_BN > P.n_cols);
+      if (masked)
+        fwd_tile_epilogue<true>(tmem + b * FW_BN, q, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
+                                diag_delta, has_diag, diag_out);
+      else
+        fwd_tile_epilogue<false>(tmem + b * FW_BN, q, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
+                                 diag_delta, has_diag, diag_out);
+      // TMEM buffer fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar(b));
+
+      // column sums: butterfly over the 8 row groups (lane bits 4,3,2)
+      float a16[16], a8[8], a4[4];
+      {
+        const bool hi = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float send = hi ? cs[i] : cs[i + 16];
+          const float keep = hi ? cs[i + 16] : cs[i];
+          a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float send = hi ? a16[i] : a16[i + 8];
+          const float keep = hi ? a16[i + 8] : a16[i];
+          a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool hi = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = hi ? a8[i] : a8[i + 4];
+          const float keep = hi ? a8[i + 4] : a8[i];
+          a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+      }
+      // this thread now owns cidx = bit4*16 + bit3*8 + bit2*4 + i
+      float* cb = colbuf + (t & 1) * 512 + q * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int cidx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + i;
+        const int cc = cidx >> 3, g = (cidx >> 1) & 3, e = cidx & 1;
+        cb[cc * 32 + g * 8 + 2 * p + e] = a4[i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      {
+        const float* c0 = colbuf + (t & 1) * 512;
+        const float tot = c0[et] + c0[128 + et] + c0[256 + et] + c0[384 + et];
+        if (j0 + et < P.n_cols)
+          P.col_part[(static_cast<int64_t>(pair) * P.n_iblocks + ib) * P.n_cols + j0 + et] = tot;
+      }
+    }
+    // row sums: reduce over the 4 column-pair lanes, then one store per row
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+    }
+    if (p == 0) {
+      float* rp = P.row_part + (static_cast<int64_t>(pair) * P.n_jsplit + js) * P.n_rows;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = i0 + q * 32 + (r >> 1) * 16 + ql + (r & 1) * 8;
+        if (row < P.n_rows) rp[row] = rs[r];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// fixed-order reduction of the partial buffers
+__global__ void fwd_reduce_kernel(const float* __restrict__ row_part, const float* __restrict__ col_part,
+                                  float* __restrict__ row_sum, float* __restrict__ col_sum, int n_pairs,
+                                  int n_rows, int n_cols, int n_jsplit, int n_iblocks) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rows) {
+    float a = 0.f;
+    for (int s = 0; s < n_jsplit; ++s) a += row_part[(static_cast<int64_t>(pair) * n_jsplit + s) * n_rows + i];
+    row_sum[static_cast<int64_t>(pair) * n_rows + i] = a;
+  }
+  if (i < n_cols) {
+    float a = 0.f;
+    for (int b = 0; b < n_iblocks; ++b) a += col_part[(static_cast<int64_t>(pair) * n_iblocks + b) * n_cols + i];
+    col_sum[static_cast<int64_t>(pair) * n_cols + i] = a;
+  }
+}
+
+// lse + loss; one block per pair, fixed-order tree so the result is reproducible
+__global__ void __launch_bounds__(1024) fwd_finalize_kernel(
+    int n_rows, int n_cols, int row_offset, float c1, float alpha, const float* __restrict__ row_sum,
+    const float* __restrict__ col_sum, const float* __restrict__ diag2, float* __restrict__ lse2_row,
+    float* __restrict__ lse2_col, float* __restrict__ loss_parts, float* __restrict__ loss) {
+  const int pair = blockIdx.x;
+  const float* rs = row_sum + static_cast<int64_t>(pair) * n_rows;
+  const float* cs = col_sum + static_cast<int64_t>(pair) * n_cols;
+  const float* dg = diag2 + static_cast<int64_t>(pair) * n_rows;
+  float* lr = lse2_row + static_cast<int64_t>(pair) * n_rows;
+  float* lc = lse2_col + static_cast<int64_t>(pair) * n_cols;
+  for (int j = threadIdx.x; j < n_cols; j += blockDim.x) lc[j] = log2f(cs[j]) + c1;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+    const float l = log2f(rs[i]) + c1;
+    lr[i] = l;
+    a += static_cast<double>(l - dg[i]);
+    const int j = row_offset + i;
+    if (j < n_cols) b += static_cast<double>((log2f(cs[j]) + c1) - dg[i]);
+  }
+  __shared__ double sa[1024], sb[1024];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sb[threadIdx.x] += sb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double ln2 = 0.69314718055994530942;
+    const double pa = sa[0] * ln2, pb = sb[0] * ln2;
+    loss_parts[pair * 2 + 0] = static_cast<float>(pa);
+    loss_parts[pair * 2 + 1] = static_cast<float>(pb);
+    if (loss != nullptr)
+      loss[pair] = static_cast<float>((alpha * pa + (1.0 - alpha) * pb) / n_cols);
+  }
+}
+
+static int fwd_split(int n_pairs, int n_iblocks, int n_jtiles) {
+  // enough CTAs for ~4 waves of 148 SMs, at least 2 column tiles per CTA
+  int want = (4 * kNumSMsB200 + n_pairs * n_iblocks - 1) / (n_pairs * n_iblocks);
+  int max_split = n_jtiles / 2 > 0 ? n_jtiles / 2 : 1;
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  return want;
+}
+
+}  // namespace tcl
+
+using namespace tcl;
+
+extern "C" size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, int64_t n_cols) {
+  if (n_pairs < 1 || n_rows < 1 || n_cols < 1) return 0;
+  const int n_iblocks = static_cast<int>((n_rows + FW_BM - 1) / FW_BM);
+  const int n_jtiles = static_cast<int>((n_cols + FW_BN - 1) / FW_BN);
+  const int n_jsplit = fwd_split(n_pairs, n_iblocks, n_jtiles);
+  return sizeof(float) * static_cast<size_t>(n_pairs) *
+         (static_cast<size_t>(n_jsplit) * n_rows + static_cast<size_t>(n_iblocks) * n_cols);
+}
+
+extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* const* zcol,
+                              int64_t n_rows, int64_t n_cols, int64_t dim, int64_t row_offset,
+                              int op_format, float inv_tau, float* row_sumexp, float* col_sumexp,
+                              float* diag2, void* workspace, size_t workspace_bytes, void* stream) {
+  TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "ntxent_fwd: n_pairs %d", n_pairs);
+  TCL_REQUIRE(n_rows >= 1 && n_cols >= 1 && n_rows < (1 << 24) && n_cols < (1 << 24), TCL_ERR_BAD_SHAPE,
+              "ntxent_fwd: batch sizes out of range (%lld x %lld)", (long long)n_rows, (long long)n_cols);
+  TCL_REQUIRE(dim >= 64 && dim % 64 == 0 && dim <= 64 * FW_MAX_KB, TCL_ERR_BAD_SHAPE,
+              "ntxent_fwd: dim must be a multiple of 64 in [64, 512] (got %lld)", (long long)dim);
+  TCL_REQUIRE(row_offset >= 0 && row_offset + n_rows <= n_cols, TCL_ERR_BAD_SHAPE,
+              "ntxent_fwd: local rows [%lld, %lld) must lie inside the global batch %lld",
+              (long long)row_offset, (long long)(row_offset + n_rows), (long long)n_cols);
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  const float c1 = inv_tau * 1.4426950408889634f;
+  TCL_REQUIRE(inv_tau > 0.f && 2.f * c1 < 120.f, TCL_ERR_BAD_ARG,
+              "ntxent_fwd: temperature %g too small for the fixed-shift sum-exp (need tau >= 0.025)", 1.0 / inv_tau);
+  TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && workspace, TCL_ERR_BAD_ARG, "ntxent_fwd: null pointer");
+  TCL_REQUIRE(workspace_bytes >= tcl_ntxent_fwd_workspace_bytes(n_pairs, n_rows, n_cols), TCL_ERR_WORKSPACE,
+              "ntxent_fwd: workspace too small");
+  if (int e = require_sm100()) return e;
+
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  for (int p = 0; p < n_pairs; ++p) {
+    TCL_REQUIRE(zrow[p] && zcol[p], TCL_ERR_BAD_ARG, "ntxent_fwd: null operand (pair %d)", p);
+    if (int e = make_tmap_2d_16bit(&P.tm_row[p], zrow[p], n_rows, dim, dim, FW_BM, FW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&P.tm_col[p], zcol[p], n_cols, dim, dim, FW_BN, FW_BK)) return e;
+  }
+  P.n_rows = (int)n_rows; P.n_cols = (int)n_cols; P.row_offset = (int)row_offset;
+  P.num_kb = (int)(dim / 64);
+  P.n_iblocks = (int)((n_rows + FW_BM - 1) / FW_BM);
+  P.n_jtiles = (int)((n_cols + FW_BN - 1) / FW_BN);
+  P.n_jsplit = fwd_split(n_pairs, P.n_iblocks, P.n_jtiles);
+  P.c1 = c1;
+  P.idesc = umma_idesc_f16(FW_BM, FW_BN, op_format);
+  P.row_part = static_cast<float*>(workspace);
+  P.col_part = P.row_part + static_cast<size_t>(n_pairs) * P.n_jsplit * n_rows;
+  P.diag2 = diag2;
+
+  const int smem = (int)FwdSmem::total(P.num_kb);
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(P.n_iblocks, P.n_jsplit, n_pairs);
+  ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  const int nmax = (int)(n_rows > n_cols ? n_rows : n_cols);
+  fwd_reduce_kernel<<<dim3((nmax + 255) / 256, n_pairs), 256, 0, st>>>(
+      P.row_part, P.col_part, row_sumexp, col_sumexp, n_pairs, P.n_rows, P.n_cols, P.n_jsplit, P.n_iblocks);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+extern "C" int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row_offset,
+                                   float inv_tau, float alpha, const float* row_sumexp,
+                                   const float* col_sumexp, const float* diag2, float* lse2_row,
+                                   float* lse2_col, float* loss_parts, float* loss, void* stream) {
+  TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "finalize: n_pairs %d", n_pairs);
+  TCL_REQUIRE(n_rows >= 1 && n_cols >= 1, TCL_ERR_BAD_SHAPE, "finalize: sizes");
+  TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && lse2_row && lse2_col && loss_parts, TCL_ERR_BAD_ARG, "finalize: null pointer");
+  if (int e = require_sm100()) return e;
+  const float c1 = inv_tau * 1.4426950408889634f;
+  fwd_finalize_kernel<<<n_pairs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
