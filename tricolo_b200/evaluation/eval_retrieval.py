@@ -1,0 +1,250 @@
+"""Text->shape retrieval and RR@k / NDCG@k / MRR on sm_100a behind the reference's names.
+
+Mirrors tricolo/evaluation/eval_retrieval.py:
+    construct_embeddings_matrix (:6-65)   host: tuple list -> matrices + labels
+    compute_nearest_neighbors   (:133-146) GPU: similarity GEMM (K2') + top-k (K4)
+    compute_pr_at_k             (:149-207) host fp64 finalise from top-k indices and GT ranks
+    get_nearest_info            (:210-246) host id mapping
+    compute_metrics             (:249-278) orchestration, returns the same dict
+plus the tensor-in fast entry `retrieve()` for device-resident inputs (C5-sized runs,
+where a list of a million Python tuples would itself be the bottleneck).
+
+Deviations from the reference, all stated:
+  * similarities are fp32 (16-bit operands, fp32 accumulate) instead of fp64;
+  * ties: (similarity desc, gallery index asc) — the reference's order is undefined;
+  * `sort_indices` is not materialised as a [Q, G] int64 array (88 MB at the val size,
+    1.6 TB at 1M x 200k): compute_nearest_neighbors returns a lazy `SimilarityOrder`
+    that yields the ground-truth ranks on the GPU and materialises rows only on demand.
+"""
+from __future__ import annotations
+
+import json
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+
+OPERAND_FORMAT = ops.BF16  # raw, un-normalised embeddings: bf16 keeps fp32's range (BASELINE north_star)
+BLOCK_QUERIES = 65536      # queries per GEMM/top-k chunk of the fast entry
+
+
+def construct_embeddings_matrix(dataset, embeddings_dict, model_id_to_label=None, label_to_model_id=None):
+    """Same outputs as eval_retrieval.py:6-65 (text float64 [Q,D], gallery [G,D], labels int64, ...)."""
+    assert (model_id_to_label is None) == (label_to_model_id is None)
+    tuples = embeddings_dict["caption_embedding_tuples"]
+    sample = tuples[0][-1]
+    assert sample.ndim == 1
+    num_embeddings = len(tuples)
+    text = np.zeros((num_embeddings, sample.shape[0]))
+    labels = np.zeros(num_embeddings, dtype=np.int64)
+    new_dicts = model_id_to_label is None
+    if new_dicts:
+        model_id_to_label, label_to_model_id = {}, {}
+    shapes, labels_shape = [], []
+    for q, (_caption, category, model_id, text_vec, shape_vec) in enumerate(tuples):
+        if dataset == "Primitives":  # :45-46
+            model_id = category
+        if new_dicts and model_id not in model_id_to_label:
+            lab = len(model_id_to_label)
+            model_id_to_label[model_id] = lab
+            label_to_model_id[lab] = model_id
+            shapes.append(shape_vec)
+            labels_shape.append(lab)
+        text[q] = text_vec
+        labels[q] = model_id_to_label[model_id]
+    gallery = np.vstack(shapes)
+    return (text, gallery, labels, np.array(labels_shape).astype(int), model_id_to_label, num_embeddings,
+            label_to_model_id)
+
+
+class SimilarityOrder:
+    """Stand-in for the reference's `sort_indices` [Q, G] (eval_retrieval.py:82).
+
+    Holds the device-resident fp32 similarity matrix. `ranks(labels)` gives the 1-based
+    position of gallery item labels[q] in query q's ordering (what :184-186 and :217-219
+    use sort_indices for) with the K4 kernel; `materialize()` / `[i]` produce explicit
+    orderings (stable device sort) for callers that really want them.
+    """
+
+    def __init__(self, sim: torch.Tensor, n_gallery: int):
+        self.sim, self.n_gallery = sim, n_gallery
+
+    def __len__(self):
+        return self.sim.shape[0]
+
+    @property
+    def shape(self):
+        return (self.sim.shape[0], self.n_gallery)
+
+    def ranks(self, labels) -> np.ndarray:
+        lab = torch.as_tensor(np.asarray(labels), dtype=torch.int64, device=self.sim.device)
+        _, _, _, nb = ops.topk_rank(self.sim, self.n_gallery, 1, lab)
+        return nb.cpu().numpy().astype(np.int64) + 1
+
+    def materialize(self, rows=None) -> np.ndarray:
+        s = self.sim[:, : self.n_gallery] if rows is None else self.sim[rows, : self.n_gallery]
+        return torch.sort(s, dim=-1, descending=True, stable=True).indices.cpu().numpy()
+
+    def __getitem__(self, i):
+        return self.materialize(i)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialize()
+        return a if dtype is None else a.astype(dtype)
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("tricolo_b200.evaluation needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _flip_distances_like_reference(val: np.ndarray, block: Optional[int]) -> np.ndarray:
+    """eval_retrieval.py:78 calls np.flip without an axis: rows come back in reverse query order
+    (per 3000-query block when Q > 8000, :105-125). Reproduced so `distance` in nearest.jsonl matches."""
+    if block is None:
+        return val[::-1].copy()
+    out = np.empty_like(val)
+    for s in range(0, val.shape[0], block):
+        out[s:s + block] = val[s:s + block][::-1]
+    return out
+
+
+def compute_nearest_neighbors(fit_embeddings_matrix, query_embeddings_matrix, n_neighbors):
+    """(distances [Q,k] f64, indices [Q,k] i64, sort_indices) like eval_retrieval.py:133-146."""
+    fit = np.asarray(fit_embeddings_matrix)
+    query = np.asarray(query_embeddings_matrix)
+    if fit.shape == query.shape and np.allclose(fit, query):
+        raise NotImplementedError("self-retrieval (fit == query, eval_retrieval.py:84-98) is outside the "
+                                  "text->shape path; no fallback")
+    dev = _device()
+    q16 = ops.cast_16bit(torch.from_numpy(np.ascontiguousarray(query)).to(dev), OPERAND_FORMAT)
+    g16 = ops.cast_16bit(torch.from_numpy(np.ascontiguousarray(fit)).to(dev), OPERAND_FORMAT)
+    sim, n_g = ops.sim_gemm(q16, g16)
+    dummy = torch.zeros((sim.shape[0],), dtype=torch.int64, device=dev)
+    val, idx, _, _ = ops.topk_rank(sim, n_g, n_neighbors, dummy)
+    n_q = query.shape[0]
+    distances = _flip_distances_like_reference(val.cpu().numpy().astype(np.float64), 3000 if n_q > 8000 else None)
+    return distances, idx.cpu().numpy().astype(np.int64), SimilarityOrder(sim, n_g)
+
+
+def metrics_from_ranks(indices: np.ndarray, rank: np.ndarray, labels: np.ndarray, n_neighbors: int,
+                       fit_labels: Optional[np.ndarray] = None) -> dict:
+    """Host fp64 finalise with the reference's NumPy op order (eval_retrieval.py:161-206)."""
+    q = indices.shape[0]
+    fit_labels = labels if fit_labels is None else np.asarray(fit_labels)
+    rel_score = np.equal(fit_labels[indices], labels[:, None]).astype(np.float32)
+    num_correct = np.cumsum(rel_score, axis=1, dtype=np.float32)
+    num_relevant = np.bincount(fit_labels)[labels]
+    rel_score_ideal = (np.arange(n_neighbors)[None, :] < np.minimum(num_relevant, n_neighbors)[:, None]).astype(np.float32)
+    # sequential fp64 accumulation, as the Python loop at :184-187
+    r_rank = float(np.cumsum(1.0 / rank.astype(np.float64))[-1]) / q
+    dcg_d = np.log2(np.arange(1, n_neighbors + 1) + 1)
+    dcg = np.cumsum((np.exp2(rel_score) - 1) / dcg_d, axis=1)
+    dcg_ideal = np.cumsum((np.exp2(rel_score_ideal) - 1) / dcg_d, axis=1)
+    ndcg = dcg / dcg_ideal
+    return {
+        "precision": np.sum(num_correct / np.arange(1, n_neighbors + 1), axis=0) / q,
+        "recall": np.sum(num_correct / num_relevant[:, None], axis=0) / q,
+        "recall_rate": np.sum(num_correct > 0, axis=0) / q,
+        "ndcg": np.sum(ndcg, axis=0) / q,
+        "mrr": r_rank,
+    }
+
+
+def compute_pr_at_k(indices, sort_indices, labels, n_neighbors, num_embeddings, fit_labels=None):
+    """eval_retrieval.py:149-207. `sort_indices` may be a SimilarityOrder (ranks on the GPU) or an
+    explicit [Q, G] array (ranks by search, as the reference)."""
+    labels = np.asarray(labels)
+    fl = labels if fit_labels is None else np.asarray(fit_labels)
+    unique_gallery = fl.shape[0] == np.unique(fl).shape[0] and np.array_equal(fl, np.arange(fl.shape[0]))
+    if isinstance(sort_indices, SimilarityOrder) and unique_gallery:
+        rank = sort_indices.ranks(labels)
+    else:
+        order = np.asarray(sort_indices)
+        rank = np.argmax(fl[order] == labels[:, None], axis=1).astype(np.int64) + 1
+    return metrics_from_ranks(np.asarray(indices)[:num_embeddings], rank[:num_embeddings], labels[:num_embeddings],
+                              n_neighbors, fl)
+
+
+def get_nearest_info(indices, sort_indices, fit_labels, labels, label_to_model_id, caption_tuples):
+    """eval_retrieval.py:210-246: model ids of queries and neighbours (+ reciprocal ranks)."""
+    labels = np.asarray(labels)
+    if isinstance(sort_indices, SimilarityOrder):
+        rank = sort_indices.ranks(labels)
+    else:
+        rank = np.argmax(np.asarray(fit_labels)[np.asarray(sort_indices)] == labels[:, None], axis=1) + 1
+    r_rank_list = [1 / int(r) for r in rank]
+    query_model_ids = [t[2] for t in caption_tuples[: len(labels)]]
+    cat_ids = [t[1] for t in caption_tuples[: len(labels)]]
+    nearest_model_ids = [[label_to_model_id[int(c)] for c in row] for row in np.asarray(indices)]
+    assert len(query_model_ids) == len(nearest_model_ids)
+    return query_model_ids, cat_ids, nearest_model_ids, r_rank_list
+
+
+def print_nearest_info(categories, query_model_ids, nearest_model_ids, distances, path="nearest.jsonl"):
+    """eval_retrieval.py:281-304: one JSON line per query, in np.random.permutation order (the
+    global NumPy RNG is consumed exactly as the reference does, :289)."""
+    perm = np.random.permutation(len(nearest_model_ids))
+    with open(path, "w") as f:
+        for i in perm:
+            f.write(json.dumps({"cat_id": categories[i], "groundtruth": query_model_ids[i] + ("-%04d" % i),
+                                "retrieved_models": nearest_model_ids[i], "distance": distances[i].tolist()}) + "\n")
+
+
+def _print_results(pr_at_k):
+    print("\nRR@1 RR@5 NDCG@5 MRR")
+    print(f'{round(pr_at_k["recall_rate"][0] * 100, 2)} {round(pr_at_k["recall_rate"][4] * 100, 2)} '
+          f'{round(pr_at_k["ndcg"][4] * 100, 2)} {round(pr_at_k["mrr"] * 100, 2)}')
+
+
+def retrieve(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k: int = 5,
+             block_queries: int = BLOCK_QUERIES, operand_format: int = OPERAND_FORMAT):
+    """Tensor-in fast entry: device-resident text [Q,D], gallery [G,D], labels [Q] (int64 gallery index).
+
+    Returns (topk_val [Q,k] f32, topk_idx [Q,k] i32, rank [Q] i32) on the device. Queries are processed
+    in blocks so the fp32 similarity buffer stays bounded (block_queries x G x 4 bytes)."""
+    g16 = gallery if gallery.dtype == ops.L.op_torch_dtype(operand_format) else ops.cast_16bit(gallery, operand_format)
+    n_q, n_g = text.shape[0], gallery.shape[0]
+    dev = text.device
+    val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    rank = torch.empty((n_q,), dtype=torch.int32, device=dev)
+    ld = (n_g + 3) // 4 * 4
+    buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
+    labels = labels.to(torch.int64)
+    for s in range(0, n_q, block_queries):
+        e = min(s + block_queries, n_q)
+        tq = text[s:e]
+        q16 = tq if tq.dtype == g16.dtype else ops.cast_16bit(tq, operand_format)
+        sim, _ = ops.sim_gemm(q16, g16, out=buf[: e - s])
+        v, i, _, nb = ops.topk_rank(sim, n_g, k, labels[s:e])
+        val[s:e], idx[s:e] = v, i
+        rank[s:e] = nb + 1
+    return val, idx, rank
+
+
+def compute_metrics(dataset, embeddings_dict, print_results=False, write_nearest=True):
+    """Drop-in for eval_retrieval.py:249-278: same input format, same returned dict."""
+    (text, gallery, labels, fit_labels, _model_id_to_label, num_embeddings,
+     label_to_model_id) = construct_embeddings_matrix(dataset, embeddings_dict)
+    n_neighbors = 5  # :257
+    dev = _device()
+    t_dev = torch.from_numpy(text).to(dev)
+    g_dev = torch.from_numpy(np.ascontiguousarray(gallery)).to(dev)
+    l_dev = torch.from_numpy(labels).to(dev)
+    val, idx, rank = retrieve(t_dev, g_dev, l_dev, n_neighbors)
+    indices = idx.cpu().numpy().astype(np.int64)
+    rank_h = rank.cpu().numpy().astype(np.int64)
+    pr_at_k = metrics_from_ranks(indices, rank_h, labels, n_neighbors, fit_labels)
+    if write_nearest:
+        distances = _flip_distances_like_reference(val.cpu().numpy().astype(np.float64),
+                                                   3000 if num_embeddings > 8000 else None)
+        tuples = embeddings_dict["caption_embedding_tuples"]
+        nearest_model_ids = [[label_to_model_id[int(c)] for c in row] for row in indices]
+        print_nearest_info([t[1] for t in tuples], [t[2] for t in tuples], nearest_model_ids, distances)
+    if print_results:
+        _print_results(pr_at_k)
+    return pr_at_k

@@ -1,0 +1,213 @@
+"""Tensor-level wrappers of the C-ABI entry points (one function per export).
+
+PyTorch is used here for device memory and streams only; every computation is
+an sm_100a kernel behind include/tricolo_b200.h.  All functions enqueue on the
+current CUDA stream and return without synchronising.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+LIB = L.LIB
+F16, BF16 = L.TCL_OP_F16, L.TCL_OP_BF16
+EPS = 1e-12  # F.normalize default used at tricolo/loss/nt_xent.py:56-57
+
+
+def _rows_2d(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"expected a [rows, dim] matrix, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1 or (t.stride(0) * t.element_size()) % 16 != 0 or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t
+
+
+def l2norm_fwd(xs: Sequence[torch.Tensor], op_format: int = F16, eps: float = EPS):
+    """K1. Returns ([z 16-bit [rows, dim]], [inv_norm fp32 [rows]]). nt_xent.py:56-57."""
+    dev = L.require_cuda(*xs)
+    xs = [_rows_2d(x) for x in xs]
+    rows, dim = xs[0].shape
+    for x in xs:
+        if x.shape != xs[0].shape or x.dtype != xs[0].dtype:
+            raise ValueError("l2norm_fwd: all tensors must share shape and dtype")
+    same_stride = all(x.stride(0) == xs[0].stride(0) for x in xs)
+    if not same_stride:
+        xs = [x.contiguous() for x in xs]
+    zs = [torch.empty((rows, dim), dtype=L.op_torch_dtype(op_format), device=dev) for _ in xs]
+    invs = [torch.empty((rows,), dtype=torch.float32, device=dev) for _ in xs]
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_l2norm_fwd(len(xs), L.ptr_array(xs), L.dtype_code(xs[0]), rows, dim, xs[0].stride(0),
+                                   L.ptr_array(zs), op_format, L.ptr_array(invs), eps, L.stream_ptr(dev)))
+    return zs, invs, xs
+
+
+def cast_16bit(x: torch.Tensor, op_format: int = BF16) -> torch.Tensor:
+    dev = L.require_cuda(x)
+    x = _rows_2d(x)
+    y = torch.empty(x.shape, dtype=L.op_torch_dtype(op_format), device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_cast_16bit(L.ptr(x), L.dtype_code(x), x.shape[0], x.shape[1], x.stride(0), L.ptr(y),
+                                   op_format, L.stream_ptr(dev)))
+    return y
+
+
+def transpose_16bit(zs: Sequence[torch.Tensor]) -> Tuple[List[torch.Tensor], int]:
+    """[rows, dim] -> [dim, ld_t] (ld_t = rows rounded up to 8)."""
+    dev = L.require_cuda(*zs)
+    rows, dim = zs[0].shape
+    ld_t = (rows + 7) // 8 * 8
+    zts = [torch.empty((dim, ld_t), dtype=z.dtype, device=dev) for z in zs]
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_transpose_16bit(len(zs), L.ptr_array(zs), rows, dim, L.ptr_array(zts), ld_t, L.stream_ptr(dev)))
+    return zts, ld_t
+
+
+def ntxent_fwd(zrows: Sequence[torch.Tensor], zcols: Sequence[torch.Tensor], row_offset: int, inv_tau: float,
+               op_format: int = F16):
+    """K2. Returns row_sumexp [P, n_rows], col_sumexp [P, n_cols] (partial over the given rows), diag2 [P, n_rows]."""
+    dev = L.require_cuda(*zrows, *zcols)
+    p = len(zrows)
+    n_rows, dim = zrows[0].shape
+    n_cols = zcols[0].shape[0]
+    row_sum = torch.empty((p, n_rows), dtype=torch.float32, device=dev)
+    col_sum = torch.empty((p, n_cols), dtype=torch.float32, device=dev)
+    diag2 = torch.empty((p, n_rows), dtype=torch.float32, device=dev)
+    ws_bytes = LIB.tcl_ntxent_fwd_workspace_bytes(p, n_rows, n_cols)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_ntxent_fwd(p, L.ptr_array(zrows), L.ptr_array(zcols), n_rows, n_cols, dim, row_offset,
+                                   op_format, inv_tau, L.ptr(row_sum), L.ptr(col_sum), L.ptr(diag2), L.ptr(ws),
+                                   ws_bytes, L.stream_ptr(dev)))
+    return row_sum, col_sum, diag2
+
+
+def ntxent_finalize(row_sum, col_sum, diag2, row_offset: int, inv_tau: float, alpha: float, want_loss: bool = True):
+    dev = L.require_cuda(row_sum, col_sum, diag2)
+    p, n_rows = row_sum.shape
+    n_cols = col_sum.shape[1]
+    lse2_row = torch.empty_like(row_sum)
+    lse2_col = torch.empty_like(col_sum)
+    parts = torch.empty((p, 2), dtype=torch.float32, device=dev)
+    loss = torch.empty((p,), dtype=torch.float32, device=dev) if want_loss else None
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_ntxent_finalize(p, n_rows, n_cols, row_offset, inv_tau, alpha, L.ptr(row_sum), L.ptr(col_sum),
+                                        L.ptr(diag2), L.ptr(lse2_row), L.ptr(lse2_col), L.ptr(parts), L.ptr(loss),
+                                        L.stream_ptr(dev)))
+    return lse2_row, lse2_col, parts, loss
+
+
+class BwdSegmentSpec:
+    __slots__ = ("z_other", "z_other_t", "lse2_self", "lse2_other", "grad_scale", "w_self", "w_other")
+
+    def __init__(self, z_other, z_other_t, lse2_self, lse2_other, grad_scale, w_self, w_other):
+        self.z_other, self.z_other_t = z_other, z_other_t
+        self.lse2_self, self.lse2_other = lse2_self, lse2_other
+        self.grad_scale, self.w_self, self.w_other = grad_scale, w_self, w_other
+
+
+class BwdJobSpec:
+    __slots__ = ("z_self", "x_self", "inv_norm", "segments")
+
+    def __init__(self, z_self, x_self, inv_norm, segments):
+        self.z_self, self.x_self, self.inv_norm, self.segments = z_self, x_self, inv_norm, segments
+
+
+def ntxent_bwd(jobs: Sequence[BwdJobSpec], n_other: int, self_offset: int, ld_t: int, inv_tau: float,
+               op_format: int = F16, eps: float = EPS) -> List[torch.Tensor]:
+    """K3 + normalise backward. Returns dx (dtype/shape of x_self) per job."""
+    x0 = jobs[0].x_self
+    dev = L.require_cuda(x0)
+    n_self, dim = x0.shape
+    arr = (L.BwdJob * len(jobs))()
+    dxs, keep = [], []
+    for j, job in enumerate(jobs):
+        if job.x_self.shape != x0.shape or job.x_self.dtype != x0.dtype or job.x_self.stride(0) != x0.stride(0):
+            raise ValueError("ntxent_bwd: all jobs must share shape, dtype and row stride")
+        dx = torch.empty((n_self, dim), dtype=x0.dtype, device=dev)
+        dxs.append(dx)
+        arr[j].z_self = job.z_self.data_ptr()
+        arr[j].x_self = job.x_self.data_ptr()
+        arr[j].inv_norm = job.inv_norm.data_ptr()
+        arr[j].dx = dx.data_ptr()
+        arr[j].n_segments = len(job.segments)
+        for s, sg in enumerate(job.segments):
+            a = arr[j].seg[s]
+            a.z_other = sg.z_other.data_ptr()
+            a.z_other_t = sg.z_other_t.data_ptr()
+            a.lse2_self = sg.lse2_self.data_ptr()
+            a.lse2_other = sg.lse2_other.data_ptr()
+            a.grad_scale = 0 if sg.grad_scale is None else sg.grad_scale.data_ptr()
+            a.w_self, a.w_other = sg.w_self, sg.w_other
+            keep.append(sg)
+    ws_bytes = LIB.tcl_ntxent_bwd_workspace_bytes(len(jobs), n_self, dim)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_ntxent_bwd(len(jobs), arr, n_self, n_other, dim, self_offset, ld_t, L.dtype_code(x0),
+                                   x0.stride(0), op_format, inv_tau, eps, L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
+    return dxs
+
+
+def sim_gemm(q16: torch.Tensor, g16: torch.Tensor, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
+    """K2'. S = Q G^T in fp32 with leading dimension ld (multiple of 4). Returns (S [n_q, ld], n_g)."""
+    dev = L.require_cuda(q16, g16)
+    if q16.dtype != g16.dtype or q16.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("sim_gemm: operands must both be float16 or both bfloat16")
+    n_q, dim = q16.shape
+    n_g = g16.shape[0]
+    ld = (n_g + 3) // 4 * 4
+    if out is None:
+        out = torch.empty((n_q, ld), dtype=torch.float32, device=dev)
+    op = F16 if q16.dtype == torch.float16 else BF16
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_sim_gemm(L.ptr(q16), L.ptr(g16), n_q, n_g, dim, op, L.ptr(out), out.stride(0), L.stream_ptr(dev)))
+    return out, n_g
+
+
+def topk_rank(s: torch.Tensor, n_g: int, k: int, labels: torch.Tensor, idx_base: int = 0,
+              gt_sim_in: Optional[torch.Tensor] = None):
+    """K4. Returns (topk_val [Q,k] f32, topk_idx [Q,k] i32, gt_sim [Q] f32, n_before [Q] i32)."""
+    dev = L.require_cuda(s, labels)
+    n_q = s.shape[0]
+    if labels.dtype != torch.int64:
+        labels = labels.to(torch.int64)
+    val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    gt = torch.empty((n_q,), dtype=torch.float32, device=dev) if gt_sim_in is None else gt_sim_in
+    nb = torch.empty((n_q,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_topk_rank(L.ptr(s), s.stride(0), n_q, n_g, k, L.ptr(labels), idx_base, L.ptr(gt_sim_in),
+                                  L.ptr(val), L.ptr(idx), L.ptr(gt), L.ptr(nb), L.stream_ptr(dev)))
+    return val, idx, gt, nb
+
+
+def gather_gt_sim(s: torch.Tensor, n_g: int, labels: torch.Tensor, idx_base: int) -> torch.Tensor:
+    dev = L.require_cuda(s, labels)
+    out = torch.empty((s.shape[0],), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_gather_gt_sim(L.ptr(s), s.stride(0), s.shape[0], n_g, L.ptr(labels), idx_base, L.ptr(out),
+                                      L.stream_ptr(dev)))
+    return out
+
+
+def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
+    """cand_* [n_shards, Q, k] -> merged (val [Q,k], idx [Q,k])."""
+    dev = L.require_cuda(cand_val, cand_idx)
+    n_shards, n_q, k = cand_val.shape
+    cand_val, cand_idx = cand_val.contiguous(), cand_idx.contiguous()
+    val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_topk_merge(L.ptr(cand_val), L.ptr(cand_idx), n_shards, n_q, k, L.ptr(val), L.ptr(idx),
+                                   L.stream_ptr(dev)))
+    return val, idx
+
+
+def debug_tmem_probe(device="cuda") -> torch.Tensor:
+    out = torch.zeros((4, 2, 32, 16), dtype=torch.int32, device=device)
+    with torch.cuda.device(out.device):
+        L.check(LIB.tcl_debug_tmem_probe(L.ptr(out), L.stream_ptr(out.device)))
+    return out
