@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Benchmark of the TriCoLo embedding-similarity hot path on B200 (contract: task spec, "bench.py").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU port of the reference path
+    torchrun-style launch for N > 1 (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env).
+
+Workload (config.workload = "c4"): BASELINE.json configs[3] — global-negative trimodal InfoNCE, global
+batch 8192, dim 512, tau 0.1, alpha 0.25, forward + backward, STRONG scaling: the global batch is fixed and
+each of the N ranks owns B/N rows (at N=1 the whole problem runs on one GPU).  metric = pairs/s =
+global batch / time of one fwd+bwd of the whole three-term loss.  A secondary object "retrieval" reports
+configs[4]-shaped sharded top-5 retrieval (queries/s); "small_batch" reports configs[1] (B=256) latency.
+
+One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TAU, ALPHA, DIM = 0.1, 0.25, 512
+FEATURE_KEYS = ("text_features", "image_features", "voxel_features")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2"])
+    ap.add_argument("--batch", type=int, default=0, help="override the global batch")
+    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--retrieval-queries", type=int, default=1_000_000)
+    ap.add_argument("--retrieval-gallery", type=int, default=200_000)
+    ap.add_argument("--op-format", default="f16", choices=["f16", "bf16"])
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period_s, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_features(batch, rows, row0, seed=7, device="cpu", dtype=None):
+    """SURVEY.md §8d C4 inputs: correlated modalities (base + 0.5 noise), seed 7; rows [row0, row0+rows)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(batch, DIM, generator=g)
+    out = {}
+    for k in FEATURE_KEYS:
+        out[k] = (base + 0.5 * torch.randn(batch, DIM, generator=g))[row0:row0 + rows].contiguous()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """CPU port of the reference path (oracle.torch_trimodal = the same PyTorch ops as nt_xent.py, autograd
+    backward) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import ntxent_oracle as NO
+
+    batch = args.batch or (8192 if args.workload == "c4" else 256)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    feats = make_features(batch, batch, 0)
+
+    def step(fd):
+        fd = {k: v.clone().requires_grad_(True) for k, v in fd.items()}
+        out = NO.torch_trimodal(fd, TAU, ALPHA)
+        out["train_loss/total_loss"].backward()
+        return float(out["train_loss/total_loss"])
+
+    # probe once; if a full-size step is too slow, time a bounded sample: a smaller global batch
+    t0 = time.perf_counter()
+    step(feats)
+    probe = time.perf_counter() - t0
+    sample_batch = batch
+    budget_s = 150.0
+    while probe * (sample_batch / batch) ** 2 * (args.steps + args.warmup) > budget_s and sample_batch > 1024:
+        sample_batch //= 2
+    if sample_batch != batch:
+        feats = make_features(sample_batch, sample_batch, 0)
+    for _ in range(max(args.warmup - 1, 1)):
+        step(feats)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(feats)
+    dt = (time.perf_counter() - t0) / args.steps
+    # cost is quadratic in the batch: a full-size step costs (batch/sample)^2 sample steps
+    full_step = dt * (batch / sample_batch) ** 2
+    value = batch / full_step
+    sample = (f"full workload per step (B={batch}, 3 pair terms, fwd+bwd, fp32)" if sample_batch == batch else
+              f"B={sample_batch} sub-batch per step, extrapolated x{(batch // sample_batch) ** 2} (cost is quadratic in B)")
+    line = {
+        "impl": "reference", "metric": "infonce_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd", "global_batch": batch,
+                   "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA, "pairs": 3},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from tricolo_b200 import _lib, ops
+    from tricolo_b200.distributed import global_trimodal_ntxent, sharded_retrieve
+    from tricolo_b200.evaluation import retrieve
+    from tricolo_b200.loss import trimodal_ntxent
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    op = ops.F16 if args.op_format == "f16" else ops.BF16
+    batch = args.batch or (8192 if args.workload == "c4" else 256)
+    assert batch % (128 * world) == 0 or world == 1, "global batch must split into 128-row blocks per rank"
+    b_loc = batch // world
+    row0 = rank * b_loc
+    host = make_features(batch, b_loc, row0)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    feats = [host[k].to(dev).requires_grad_(True) for k in FEATURE_KEYS]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def loss_fn(fs):
+        if world > 1:
+            return global_trimodal_ntxent(fs, TAU, ALPHA, op_format=op)
+        return trimodal_ntxent(fs, TAU, ALPHA, op_format=op)
+
+    def step(fs):
+        for f in fs:
+            f.grad = None
+        losses = loss_fn(fs)
+        losses.sum().backward()
+        return losses
+
+    def timed(fn, steps, warmup):
+        """Device time of `steps` calls, L2 flushed (untimed) before each; returns per-step ms list."""
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        barrier()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- main timed region: K steps, kernel events + clocks sampled meanwhile
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step(feats)
+    torch.cuda.synchronize(dev)
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    sampler.start()
+    wall0 = time.perf_counter()
+    times = timed(lambda: step(feats), args.steps, 0)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.finish()
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    total_ms = max_over_ranks(sum(times))
+    ms_per_step = total_ms / args.steps
+    value = batch / (ms_per_step * 1e-3)
+
+    # ---------------- per-kernel numbers and the roofline of the dominant kernel
+    pairs = 3
+    flops_fwd = 2.0 * b_loc * batch * DIM * pairs           # one similarity GEMM per pair
+    flops_bwd = 4.0 * b_loc * batch * DIM * pairs           # two gradient GEMMs per pair (algorithmic)
+    kern = {}
+    for name, (ms, n) in prof.items():
+        kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / args.steps}
+    def tf(flops, name):
+        return flops / (kern[name]["ms_per_launch"] * 1e-3) / 1e12 if name in kern else None
+    bytes_l2n = 3 * (b_loc * DIM * 4 + b_loc * DIM * 2 + b_loc * 4)
+    if "ntxent_fwd" in kern:
+        kern["ntxent_fwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_fwd, "ntxent_fwd")})
+    if "ntxent_bwd" in kern:
+        kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
+                                   "executed_tflops": tf(flops_bwd * 3.0, "ntxent_bwd")})
+    if "l2norm_fwd" in kern:
+        kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9})
+    peak_tf = peaks["tf_sustained"]
+    ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
+    roofline = {"kernel": "ntxent_bwd_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (ach / peak_tf) if ach else None, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "algorithmic_flops_per_launch": flops_bwd,
+                "whole_step": {"algorithmic_flops": flops_fwd + flops_bwd,
+                               "achieved": (flops_fwd + flops_bwd) / (ms_per_step * 1e-3) / 1e12,
+                               "frac": (flops_fwd + flops_bwd) / (ms_per_step * 1e-3) / 1e12 / peak_tf}}
+
+    # ---------------- e2e: host buffers in, loss + gradients back to the host, every step
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = [torch.empty((b_loc, DIM), dtype=torch.float32).pin_memory() for _ in FEATURE_KEYS]
+    loss_host = torch.empty((3,), dtype=torch.float32).pin_memory()
+    d2h = sum(t.numel() * 4 for t in out_host) + 12
+
+    def e2e_step():
+        fs = [host[k].to(dev, non_blocking=True).requires_grad_(True) for k in FEATURE_KEYS]
+        losses = loss_fn(fs)
+        losses.sum().backward()
+        loss_host.copy_(losses.detach(), non_blocking=True)
+        for o, f in zip(out_host, fs):
+            o.copy_(f.grad, non_blocking=True)
+
+    e2e_times = timed(e2e_step, args.steps, max(3, args.warmup))
+    e2e_ms = max_over_ranks(sum(e2e_times)) / args.steps
+    e2e = {"value": batch / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "tricolo_b200.loss.trimodal_ntxent(...).sum().backward() on pinned host fp32 embeddings"}
+
+    # ---------------- secondary: small batch (configs[1]) latency
+    small = None
+    if world == 1 and args.workload == "c4":
+        sf = [x.to(dev).requires_grad_(True) for x in make_features(256, 256, 0, seed=1234).values()]
+        st = timed(lambda: step(sf), 50, 10)
+        small = {"workload": "c2: trimodal B=256 fwd+bwd", "ms_per_step": statistics.median(st),
+                 "pairs_per_s": 256 / (statistics.median(st) * 1e-3)}
+
+    # ---------------- secondary: sharded retrieval (configs[4]-shaped)
+    retrieval = None
+    if not args.no_retrieval:
+        retrieval = bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrieve, sharded_retrieve, _lib)
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(batch)
+
+    if rank == 0:
+        line = {
+            "metric": "infonce_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if op == ops.F16 else "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd (BASELINE configs[3])",
+                       "global_batch": batch, "rows_per_rank": b_loc, "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA,
+                       "pairs": 3, "accumulate": "f32", "l2": "flushed (256 MB write) before every timed step",
+                       "parallelism": f"row-block x{world}"},
+            "roofline": roofline, "kernels": kern, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "small_batch": small, "retrieval": retrieval,
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrieve, sharded_retrieve, _lib):
+    import torch
+
+    n_q, n_g = args.retrieval_queries, args.retrieval_gallery
+    g_loc = n_g // world
+    base = rank * g_loc
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    gal = torch.randn(g_loc, DIM, generator=gen, device=dev).bfloat16()
+    genq = torch.Generator(device=dev).manual_seed(99)  # same queries / labels on every rank
+    text = torch.randn(n_q, DIM, generator=genq, device=dev).bfloat16()
+    labels = torch.randint(0, n_g, (n_q,), generator=genq, device=dev)
+    block = 8192
+
+    def run():
+        if world > 1:
+            return sharded_retrieve(text, gal, labels, base, 5, block_queries=block)
+        return retrieve(text, gal, labels, 5, block_queries=block)
+
+    steps = 2
+    _lib.profile_enable(True)
+    t = timed(run, steps, 1)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    ms = max_over_ranks(sum(t)) / steps
+    out = {"metric": "retrieval_queries_per_s", "value": n_q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+           "config": {"workload": "c5: sharded top-5 retrieval (BASELINE configs[4])", "queries": n_q, "gallery": n_g,
+                      "gallery_per_rank": g_loc, "dim": DIM, "k": 5, "block_queries": block, "operands": "bf16"}}
+    if "topk_rank" in prof:
+        ms_k, n_k = prof["topk_rank"]
+        bytes_k = (n_q * g_loc * 4 + n_q * 5 * 8 + n_q * 8) / (n_q / block)  # per launch (one query block)
+        gbs = bytes_k / (ms_k / n_k * 1e-3) / 1e9
+        out["topk_roofline"] = {"kernel": "topk_rank_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "ms_per_launch": ms_k / n_k}
+    if "sim_gemm" in prof:
+        ms_g, n_g_l = prof["sim_gemm"]
+        fl = 2.0 * block * g_loc * DIM
+        tfs = fl / (ms_g / n_g_l * 1e-3) / 1e12
+        out["gemm_roofline"] = {"kernel": "sim_gemm_kernel", "bound": "tensor", "achieved": tfs, "peak": peaks["tf_sustained"],
+                                "unit": "TFLOP/s", "frac": tfs / peaks["tf_sustained"], "ms_per_launch": ms_g / n_g_l,
+                                "hbm_write_gbs": block * g_loc * 4 / (ms_g / n_g_l * 1e-3) / 1e9}
+    return out
+
+
+def cpu_baseline(batch):
+    """The oracle's CPU-PyTorch port of the reference loss on the host cores: bounded sample (~10-30 s)."""
+    import torch
+
+    from oracle import ntxent_oracle as NO
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_batch = min(batch, 2048)
+    feats = make_features(sample_batch, sample_batch, 0)
+
+    def step():
+        fd = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+        out = NO.torch_trimodal(fd, TAU, ALPHA)
+        out["train_loss/total_loss"].backward()
+
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+        step()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    full = dt * (batch / sample_batch) ** 2
+    return {"value": batch / full, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{n} fwd+bwd steps of the trimodal loss at B={sample_batch} (fp32, torch CPU, {cores} threads), "
+                      f"scaled x{(batch // sample_batch) ** 2} to B={batch} (cost is quadratic in B)",
+            "ms_per_sample_step": dt * 1e3}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a B200; there is no CPU path")
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -179,6 +179,31 @@ int tcl_topk_merge(const float* cand_val, const int32_t* cand_idx, int n_shards,
                    int k, float* topk_val, int32_t* topk_idx, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Measurement hooks (bench.py).  tcl_launch_count: kernels launched by this library
+ * since load.  With profiling enabled every kernel launch is bracketed by CUDA events
+ * on its launch stream; tcl_profile_read synchronises on those events and returns the
+ * summed device time and launch count of one kernel id since the last enable.
+ * ------------------------------------------------------------------------- */
+enum {
+  TCL_K_L2NORM_FWD = 0,
+  TCL_K_CAST16 = 1,
+  TCL_K_TRANSPOSE16 = 2,
+  TCL_K_NTXENT_FWD = 3,
+  TCL_K_FWD_REDUCE = 4,
+  TCL_K_FWD_FINALIZE = 5,
+  TCL_K_NTXENT_BWD = 6,
+  TCL_K_L2NORM_BWD = 7,
+  TCL_K_SIM_GEMM = 8,
+  TCL_K_TOPK_RANK = 9,
+  TCL_K_GATHER_GT = 10,
+  TCL_K_TOPK_MERGE = 11,
+  TCL_K_COUNT = 12
+};
+int64_t tcl_launch_count(void);
+int tcl_profile_enable(int on);
+int tcl_profile_read(int kernel_id, double* total_ms, int64_t* launches);
+
+/* ---------------------------------------------------------------------------
  * Bring-up / test hooks (not part of the product path).
  * tcl_debug_tmem_probe: writes lane*64+col into a 128x32 TMEM block and reads it back
  * through the 16x256b load shape; out[(warp*2+half)*32*16 + thread*16 + reg].

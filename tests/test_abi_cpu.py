@@ -1,0 +1,101 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tricolo_b200.h declares;
+argument validation that needs no GPU; host-side logic of the drop-in modules."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tricolo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tcl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from tricolo_b200 import _lib
+
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    raw = ctypes.CDLL(str(_lib.lib_path()))
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes binding table and header disagree"
+    assert _lib.LIB.tcl_version() == 1
+    assert _lib.LIB.tcl_last_error_string() is not None
+
+
+def test_bwd_struct_layout_matches_header():
+    from tricolo_b200 import _lib
+
+    # tcl_bwd_segment: 5 pointers + 2 floats = 48 bytes; tcl_bwd_job: 4 pointers + 2 int32 + 2 segments
+    assert ctypes.sizeof(_lib.BwdSegment) == 48
+    assert ctypes.sizeof(_lib.BwdJob) == 4 * 8 + 8 + 2 * 48
+
+
+def test_argument_validation_without_gpu():
+    """Shape/alignment checks run before any CUDA call, so they are testable on the CPU box."""
+    from tricolo_b200 import _lib
+
+    L = _lib.LIB
+    buf = ctypes.create_string_buffer(4096)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = L.tcl_topk_rank(p, 8, 4, 8, 17, p, 0, None, p, p, p, p, None)  # k > 16
+    assert rc == 4 and b"k must be" in L.tcl_last_error_string()
+    rc = L.tcl_sim_gemm(p, p, 4, 4, 12, 1, p, 4, None)  # dim not a multiple of 8
+    assert rc == 1
+    arr = (ctypes.c_void_p * 1)(p.value)
+    rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 100, 0, 0, 10.0, p, p, p, p, 1 << 20, None)  # dim % 64
+    assert rc == 1
+    rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 128, 0, 0, 1000.0, p, p, p, p, 1 << 20, None)  # tau too small
+    assert rc == 4 and b"temperature" in L.tcl_last_error_string()
+    assert L.tcl_ntxent_fwd_workspace_bytes(3, 8192, 8192) > 0
+    assert L.tcl_ntxent_bwd_workspace_bytes(3, 8192, 512) >= 3 * 8192 * 512 * 4
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    from tricolo_b200.loss import NTXentLoss
+
+    fn = NTXentLoss(0.1, 0.25)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fn(torch.randn(8, 64), torch.randn(8, 64))
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tricolo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_host_metrics_finalise_matches_oracle():
+    from oracle import retrieval_oracle as RO
+    from tricolo_b200.evaluation import construct_embeddings_matrix, metrics_from_ranks
+
+    tuples = RO.make_val_shaped(seed=3, n_shapes=300, n_queries=1000, dim=128, round_bf16=True)
+    ref = RO.compute_metrics(tuples)
+    text, gal, labels, fit_labels, m2l, n, l2m = construct_embeddings_matrix("x", {"caption_embedding_tuples": tuples})
+    r_text, r_gal, r_labels, _, _, _ = RO.build_matrices(tuples)
+    assert np.array_equal(text, r_text) and np.array_equal(gal, r_gal) and np.array_equal(labels, r_labels)
+    assert n == 1000 and l2m[m2l["m5"]] == "m5"
+    got = metrics_from_ranks(ref["_indices"], ref["_rank"], labels, 5, fit_labels)
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.array_equal(got[k], ref[k])
+    assert got["mrr"] == ref["mrr"]
+
+
+def test_distance_flip_quirk():
+    from tricolo_b200.evaluation.eval_retrieval import _flip_distances_like_reference
+
+    v = np.arange(20.0).reshape(10, 2)
+    assert np.array_equal(_flip_distances_like_reference(v, None), v[::-1])
+    out = _flip_distances_like_reference(v, 4)
+    assert np.array_equal(out[:4], v[:4][::-1]) and np.array_equal(out[8:], v[8:][::-1])

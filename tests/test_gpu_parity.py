@@ -1,0 +1,362 @@
+"""GPU parity tests (run with -m gpu on a B200): the sm_100a path, called through the
+C ABI, against the CPU oracle and the golden vectors produced by the reference itself.
+
+Tolerances (BASELINE.json north_star): loss and gradients rtol 1e-3 on bf16-rounded
+inputs; top-k indices, ranks and RR/NDCG bit-exact on the fp32 similarities under the
+(similarity desc, index asc) order.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ntxent_oracle as NO
+from oracle import retrieval_oracle as RO
+from tests.cases import GRAD_CASES, LOSS_CASES, bf16_rounded, loss_case
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TAU, ALPHA = 0.1, 0.25
+RTOL = 1e-3  # north_star: "Loss and gradients must agree within rtol 1e-3"
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import tricolo_b200  # noqa: F401  (raises if the CUDA library is missing)
+    from tricolo_b200 import ops
+    from tricolo_b200 import loss as L
+    from tricolo_b200 import evaluation as E
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.ops, ns.loss, ns.eval = ops, L, E
+    return ns
+
+
+def _grad_close(got: torch.Tensor, ref: np.ndarray, scale_hint: float):
+    """Gradient check: norm-wise and element-wise (against the largest reference entry) rtol 1e-3.
+    `scale_hint` is the natural magnitude of a gradient entry; used as the absolute floor when the
+    reference gradient vanishes analytically (e.g. identical rows)."""
+    got = got.double().cpu().numpy()
+    ref_norm = np.linalg.norm(ref)
+    floor = scale_hint * np.sqrt(ref.size)
+    assert np.linalg.norm(got - ref) <= RTOL * max(ref_norm, floor), (np.linalg.norm(got - ref), ref_norm)
+    assert np.abs(got - ref).max() <= 2 * RTOL * max(np.abs(ref).max(), scale_hint)
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_trimodal_loss_and_grads_vs_oracle(tb, name):
+    feats = bf16_rounded(loss_case(name))
+    dev = {k: v.cuda().requires_grad_(True) for k, v in feats.items()}
+    fn = tb.loss.NTXentLoss(TAU, ALPHA)
+    losses = tb.loss.calculate_losses(dev, "train_loss", fn)
+    losses["train_loss/total_loss"].backward()
+    ref_l, ref_g = NO.trimodal_forward_backward({k: v.numpy() for k, v in feats.items()}, TAU, ALPHA)
+    assert list(losses.keys()) == list(ref_l.keys())
+    for k, v in ref_l.items():
+        assert losses[k].dtype == torch.float32 and losses[k].dim() == 0
+        assert float(losses[k].detach()) == pytest.approx(v, rel=RTOL)
+    b = next(iter(feats.values())).shape[0]
+    for k, v in dev.items():
+        norms = feats[k].norm(dim=1)
+        hint = 1.0 / (b * TAU * float(norms[norms > 0].median()) * np.sqrt(feats[k].shape[1])) * 1e-3
+        _grad_close(v.grad, ref_g[k], hint)
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_loss_vs_reference_golden(tb, golden, name):
+    """Directly against the numbers the reference code produced (tests/golden/make_golden.py)."""
+    feats = bf16_rounded(loss_case(name))
+    dev = {k: v.cuda() for k, v in feats.items()}
+    fn = tb.loss.NTXentLoss(TAU, ALPHA)
+    with torch.no_grad():
+        losses = tb.loss.calculate_losses(dev, "train_loss", fn)
+    for k, v in golden["cases"][f"{name}.bf16"]["losses"].items():
+        assert float(losses[k]) == pytest.approx(v, rel=RTOL)
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_grads_vs_reference_golden(tb, name):
+    z = np.load(os.path.join(HERE, "golden", "loss_grads.npz"))
+    feats = bf16_rounded(loss_case(name))
+    dev = {k: v.cuda().requires_grad_(True) for k, v in feats.items()}
+    fn = tb.loss.NTXentLoss(TAU, ALPHA)
+    tb.loss.calculate_losses(dev, "train_loss", fn)["train_loss/total_loss"].backward()
+    for k, v in dev.items():
+        ref = z[f"{name}.bf16.{k}"].astype(np.float64)
+        got = v.grad[::4]
+        if name == "KAT3":
+            # row 0 of the text matrix is zero: its gradient is g / eps ~ 1e8 and dominates every norm;
+            # check it separately from the regular rows
+            if k == "text_features":
+                _grad_close(got[:1], ref[:1], 0.0)
+                got, ref = got[1:], ref[1:]
+        _grad_close(got, ref, 0.0)
+
+
+def test_bimodal_module_signature_and_order(tb, golden):
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(64, 512, generator=g).cuda()
+    b = torch.randn(64, 512, generator=g).cuda()
+    fn = tb.loss.NTXentLoss(temperature=TAU, alpha_weight=ALPHA)
+    assert len(list(fn.parameters())) == 0 and len(fn.state_dict()) == 0
+    ab, ba = float(fn(a, b)), float(fn(b, a))
+    assert ab == pytest.approx(golden["order"]["ab"], rel=RTOL)
+    assert ba == pytest.approx(golden["order"]["ba"], rel=RTOL)
+    assert ab != ba  # alpha != 0.5: argument order matters
+    with pytest.raises(NotImplementedError):
+        fn(a, b, norm=False)
+    with pytest.raises(RuntimeError):
+        fn(a.cpu(), b.cpu())  # no CPU path
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_input_dtypes(tb, dtype):
+    g = torch.Generator().manual_seed(21)
+    a32 = torch.randn(256, 512, generator=g).bfloat16().float()
+    b32 = torch.randn(256, 512, generator=g).bfloat16().float()
+    a = a32.to(dtype).cuda().requires_grad_(True)
+    b = b32.to(dtype).cuda().requires_grad_(True)
+    fn = tb.loss.NTXentLoss(TAU, ALPHA)
+    loss = fn(a, b)
+    loss.backward()
+    ref, ga, gb = NO.ntxent_forward_backward(a32.numpy(), b32.numpy(), TAU, ALPHA)
+    assert float(loss.detach()) == pytest.approx(ref, rel=RTOL)
+    assert a.grad.dtype == dtype
+    tol = RTOL if dtype == torch.float32 else 6e-3  # the gradient itself is rounded to the 16-bit input dtype
+    assert np.linalg.norm(a.grad.double().cpu().numpy() - ga) <= tol * np.linalg.norm(ga)
+    assert np.linalg.norm(b.grad.double().cpu().numpy() - gb) <= tol * np.linalg.norm(gb)
+
+
+def test_upstream_gradient_scaling_and_partial_requires_grad(tb):
+    g = torch.Generator().manual_seed(8)
+    f = [torch.randn(256, 512, generator=g).bfloat16().float() for _ in range(3)]
+    t = f[0].cuda().requires_grad_(True)
+    i = f[1].cuda()  # no gradient wanted
+    v = f[2].cuda().requires_grad_(True)
+    losses = tb.loss.trimodal_ntxent([t, i, v], TAU, ALPHA)
+    w = torch.tensor([2.0, -0.5, 4096.0], device="cuda")
+    (losses * w).sum().backward()
+    assert i.grad is None
+    gt = np.zeros_like(f[0].numpy(), dtype=np.float64)
+    gv = np.zeros_like(gt)
+    for p, (a, b) in enumerate([(0, 1), (0, 2), (1, 2)]):
+        _, ga, gb = NO.ntxent_forward_backward(f[a].numpy(), f[b].numpy(), TAU, ALPHA, grad_out=float(w[p]))
+        if a == 0:
+            gt += ga
+        if b == 2:
+            gv += gb
+    assert np.linalg.norm(t.grad.double().cpu().numpy() - gt) <= RTOL * np.linalg.norm(gt)
+    assert np.linalg.norm(v.grad.double().cpu().numpy() - gv) <= RTOL * np.linalg.norm(gv)
+
+
+def test_large_batch_properties(tb):
+    """B = 4096 (oracle too slow in fp64 loops? no — 4096^2 is fine) plus size-independent properties:
+    gradient rows are orthogonal to the inputs (normalise backward) and permutation equivariance."""
+    g = torch.Generator().manual_seed(13)
+    base = torch.randn(4096, 512, generator=g)
+    f = [(base + 0.5 * torch.randn(4096, 512, generator=g)).bfloat16().float() for _ in range(3)]
+    dev = [x.cuda().requires_grad_(True) for x in f]
+    losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA)
+    losses.sum().backward()
+    ref_l, ref_g = NO.trimodal_forward_backward(
+        {"text_features": f[0].numpy(), "image_features": f[1].numpy(), "voxel_features": f[2].numpy()}, TAU, ALPHA)
+    for p, k in enumerate(["train_loss/text_image_loss", "train_loss/text_voxel_loss", "train_loss/image_voxel_loss"]):
+        assert float(losses[p].detach()) == pytest.approx(ref_l[k], rel=RTOL)
+    for x, k in zip(dev, ["text_features", "image_features", "voxel_features"]):
+        assert np.linalg.norm(x.grad.double().cpu().numpy() - ref_g[k]) <= RTOL * np.linalg.norm(ref_g[k])
+        # dx_i . x_i = 0 for every row
+        dots = (x.grad.double() * x.detach().double()).sum(1).abs().max().item()
+        assert dots <= 1e-5 * x.grad.double().norm(dim=1).max().item() * x.detach().double().norm(dim=1).max().item()
+    # permuting the batch permutes gradients and leaves the losses unchanged (up to summation order)
+    perm = torch.randperm(4096, generator=g)
+    dev_p = [x.detach()[perm.cuda()].clone().requires_grad_(True) for x in dev]
+    losses_p = tb.loss.trimodal_ntxent(dev_p, TAU, ALPHA)
+    losses_p.sum().backward()
+    assert torch.allclose(losses_p.detach(), losses.detach(), rtol=1e-5)
+    for x, xp in zip(dev, dev_p):
+        assert torch.allclose(xp.grad, x.grad[perm.cuda()], rtol=1e-3, atol=1e-3 * x.grad.abs().max().item())
+
+
+def test_bf16_operand_mode_runs_and_is_less_accurate(tb):
+    """bf16 tensor-core operands are supported (north_star wording) but cannot meet rtol 1e-3 on gradients;
+    the default is fp16 operands. This test documents the measured gap."""
+    feats = bf16_rounded(loss_case("G2"))
+    ref_l, ref_g = NO.trimodal_forward_backward({k: v.numpy() for k, v in feats.items()}, TAU, ALPHA)
+    errs = {}
+    for op in (tb.ops.F16, tb.ops.BF16):
+        dev = [v.cuda().requires_grad_(True) for v in feats.values()]
+        losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA, op_format=op)
+        losses.sum().backward()
+        assert float(losses.sum().detach()) == pytest.approx(ref_l["train_loss/total_loss"], rel=RTOL)
+        errs[op] = max(np.linalg.norm(x.grad.double().cpu().numpy() - ref_g[k]) / np.linalg.norm(ref_g[k])
+                       for x, k in zip(dev, feats.keys()))
+    assert errs[tb.ops.F16] <= RTOL
+    assert errs[tb.ops.BF16] <= 1e-2
+    assert errs[tb.ops.BF16] > errs[tb.ops.F16]
+
+
+def test_unsupported_inputs_raise(tb):
+    a = torch.randn(64, 100).cuda()  # dim not a multiple of 64
+    fn = tb.loss.NTXentLoss(TAU, ALPHA)
+    with pytest.raises(Exception):
+        fn(a, a.clone())
+    with pytest.raises(Exception):
+        tb.loss.NTXentLoss(0.001, ALPHA)(torch.randn(64, 128).cuda(), torch.randn(64, 128).cuda())  # tau too small
+
+
+# ------------------------------------------------------------------------------ retrieval
+def _eval_gpu(tb, tuples, k=5):
+    text, gal, labels, fit_labels, _, _ = RO.build_matrices(tuples)
+    t = torch.from_numpy(text).cuda()
+    g = torch.from_numpy(gal).cuda()
+    lab = torch.from_numpy(labels).cuda()
+    val, idx, rank = tb.eval.retrieve(t, g, lab, k)
+    sim, n_g = tb.ops.sim_gemm(tb.ops.cast_16bit(t, tb.ops.BF16), tb.ops.cast_16bit(g, tb.ops.BF16))
+    return text, gal, labels, fit_labels, val.cpu().numpy(), idx.cpu().numpy(), rank.cpu().numpy(), sim[:, :n_g].cpu().numpy()
+
+
+def test_retrieval_integer_kat_bit_exact(tb):
+    """Integer-valued embeddings: every dot product is exact in any precision, rows are full of ties ->
+    indices, ranks and metrics must equal the stable-sort restatement bit for bit."""
+    tuples = RO.make_integer_kat()
+    ref = RO.compute_metrics(tuples)
+    text, gal, labels, fit_labels, val, idx, rank, sim = _eval_gpu(tb, tuples)
+    assert np.array_equal(sim.astype(np.float64), RO.similarities(text, gal))
+    assert np.array_equal(idx, ref["_indices"])
+    assert np.array_equal(rank, ref["_rank"])
+    assert np.array_equal(val.astype(np.float64), ref["_values"])
+    os.chdir("/tmp")
+    got = tb.eval.compute_metrics("Text2ShapeChairTable", {"caption_embedding_tuples": tuples})
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.array_equal(got[k], ref[k]) and got[k].dtype == np.float64 and got[k].shape == (5,)
+    assert got["mrr"] == ref["mrr"] and isinstance(got["mrr"], float)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=3, n_shapes=300, n_queries=1000, dim=128, round_bf16=True),
+    dict(round_bf16=True),
+    dict(round_bf16=True, trimodal_gallery=True),
+])
+def test_retrieval_val_shaped(tb, golden, kw):
+    """C3-shaped data. (1) selection stage bit-exact against the stable-sort restatement on the GPU's own
+    fp32 similarity matrix; (2) against the fp64 reference: identical wherever the fp64 margin exceeds 1e-5,
+    metrics within 1e-3."""
+    tuples = RO.make_val_shaped(**kw)
+    text, gal, labels, fit_labels, val, idx, rank, sim = _eval_gpu(tb, tuples)
+    # (1) same numbers in, same selection out
+    on_gpu_sims = RO.compute_metrics(tuples, sim=sim)
+    assert np.array_equal(idx, on_gpu_sims["_indices"])
+    assert np.array_equal(rank, on_gpu_sims["_rank"])
+    assert np.array_equal(val, on_gpu_sims["_values"])
+    os.chdir("/tmp")
+    got = tb.eval.compute_metrics("Text2ShapeChairTable", {"caption_embedding_tuples": tuples})
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.array_equal(got[k], on_gpu_sims[k])
+    assert got["mrr"] == on_gpu_sims["mrr"]
+    # (2) fp64 reference
+    ref = RO.compute_metrics(tuples)
+    sim64 = RO.similarities(text, gal)
+    assert np.abs(sim - sim64).max() < 5e-6  # bf16-exact inputs, fp32 accumulation over 512 terms
+    srt = -np.sort(-sim64, axis=1)
+    safe_rows = (srt[:, :5] - srt[:, 1:6]).min(axis=1) > 1e-5
+    assert safe_rows.mean() > 0.9
+    assert np.array_equal(idx[safe_rows], ref["_indices"][safe_rows])
+    s_gt = sim64[np.arange(len(labels)), labels]
+    gap = np.abs(sim64 - s_gt[:, None])
+    gap[np.arange(len(labels)), labels] = np.inf
+    safe_rank = gap.min(axis=1) > 1e-5
+    assert safe_rank.mean() > 0.9
+    assert np.array_equal(rank[safe_rank], ref["_rank"][safe_rank])
+    for k in ("recall_rate", "ndcg"):
+        assert np.abs(got[k] - ref[k]).max() < 1e-3
+    assert abs(got["mrr"] - ref["mrr"]) < 1e-3
+
+
+def test_retrieval_vs_reference_golden(tb, golden):
+    """The reference's own outputs (fp64) for the C3 generator: metrics within 1e-3."""
+    os.chdir("/tmp")
+    got = tb.eval.compute_metrics("Text2ShapeChairTable", {"caption_embedding_tuples": RO.make_val_shaped(round_bf16=True)})
+    ref = golden["eval"]["C3.bf16"]
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.abs(got[k] - np.array(ref[k])).max() < 1e-3
+    assert abs(got["mrr"] - ref["mrr"]) < 1e-3
+
+
+def test_inner_trio_signatures(tb):
+    tuples = RO.make_val_shaped(seed=3, n_shapes=300, n_queries=1000, dim=128, round_bf16=True)
+    E = tb.eval
+    (text, gal, labels, fit_labels, m2l, n, l2m) = E.construct_embeddings_matrix("x", {"caption_embedding_tuples": tuples})
+    r_text, r_gal, r_labels, r_fit, r_first, r_ids = RO.build_matrices(tuples)
+    assert text.dtype == np.float64 and np.array_equal(text, r_text) and np.array_equal(gal, r_gal)
+    assert labels.dtype == np.int64 and np.array_equal(labels, r_labels) and np.array_equal(fit_labels, r_fit)
+    dist, idx, order = E.compute_nearest_neighbors(gal, text, 5)
+    assert dist.shape == (1000, 5) and idx.shape == (1000, 5) and idx.dtype == np.int64 and dist.dtype == np.float64
+    ref = RO.compute_metrics(tuples, sim=order.sim[:, :300].cpu().numpy())
+    assert np.array_equal(idx, ref["_indices"])
+    # reference quirk: distances come back in reverse query order (np.flip without axis, :78)
+    assert np.array_equal(dist, ref["_values"][::-1].astype(np.float64))
+    pr = E.compute_pr_at_k(idx, order, labels, 5, n, fit_labels)
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.array_equal(pr[k], ref[k])
+    assert pr["mrr"] == ref["mrr"]
+    # explicit ordering path (what the reference passes): same result
+    pr2 = E.compute_pr_at_k(idx, np.asarray(order), labels, 5, n, fit_labels)
+    assert pr2["mrr"] == pr["mrr"]
+    q_ids, cats, near, rr = E.get_nearest_info(idx, order, fit_labels, labels, l2m, tuples)
+    assert q_ids[0] == tuples[0][2] and len(near) == 1000 and near[0][0] == l2m[int(idx[0, 0])]
+    assert rr == [1 / int(r) for r in ref["_rank"]]
+
+
+def test_retrieval_edge_cases(tb):
+    ops = tb.ops
+    # gallery smaller than k, ragged sizes, single query
+    for (q, g, d) in ((1, 3, 64), (5, 130, 72), (129, 257, 520)):
+        gen = torch.Generator().manual_seed(q * g)
+        t = torch.randint(-2, 3, (q, d), generator=gen).float().cuda()
+        gal = torch.randint(-2, 3, (g, d), generator=gen).float().cuda()
+        lab = torch.randint(0, g, (q,), generator=gen).cuda()
+        val, idx, rank = tb.eval.retrieve(t, gal, lab, 5)
+        sim = (t.double() @ gal.double().t()).cpu().numpy()
+        rv, ri, rr = RO.topk_and_rank(sim, lab.cpu().numpy(), min(5, g))
+        assert np.array_equal(idx.cpu().numpy()[:, : min(5, g)], ri)
+        assert np.array_equal(rank.cpu().numpy(), rr)
+        if g < 5:
+            assert (idx.cpu().numpy()[:, g:] == -1).all()
+    # blocked queries give the same answer as one block
+    gen = torch.Generator().manual_seed(77)
+    t = torch.randn(1000, 128, generator=gen).bfloat16().float().cuda()
+    gal = torch.randn(333, 128, generator=gen).bfloat16().float().cuda()
+    lab = torch.randint(0, 333, (1000,), generator=gen).cuda()
+    a = tb.eval.retrieve(t, gal, lab, 5)
+    b = tb.eval.retrieve(t, gal, lab, 5, block_queries=96)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_large_retrieval_properties(tb):
+    """C5-shaped slice (65k queries x 25k gallery = one rank's shard): consistency between the sharded
+    (3 gallery shards + merge) and unsharded paths, and planted nearest neighbours are found."""
+    ops = tb.ops
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    G, Q, D = 25000, 16384, 512
+    gal = torch.randn(G, D, generator=gen, device="cuda").bfloat16()
+    owner = torch.randint(0, G, (Q,), generator=gen, device="cuda")
+    text = (gal[owner].float() + 0.5 * torch.randn(Q, D, generator=gen, device="cuda")).bfloat16()
+    val, idx, rank = tb.eval.retrieve(text, gal, owner, 5)
+    assert (rank == 1).float().mean().item() > 0.99  # planted neighbour wins
+    assert (idx[:, 0].long() == owner).float().mean().item() > 0.99
+    assert (val[:, :-1] >= val[:, 1:]).all()  # sorted descending
+    # sharded path
+    bounds = [0, 8000, 17000, G]
+    sims = [ops.sim_gemm(text, gal[lo:hi].contiguous()) for lo, hi in zip(bounds[:-1], bounds[1:])]
+    gts = sum(ops.gather_gt_sim(s, n, owner, lo) for (s, n), lo in zip(sims, bounds[:-1]))
+    cv, ci, nb = [], [], 0
+    for (s, n), lo in zip(sims, bounds[:-1]):
+        v, i, _, b = ops.topk_rank(s, n, 5, owner, lo, gts)
+        cv.append(v); ci.append(i); nb = nb + b
+    mv, mi = ops.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, idx) and torch.equal(mv, val) and torch.equal(nb + 1, rank)

@@ -16,6 +16,10 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtricolo_b200.so"
 
 TCL_OP_F16, TCL_OP_BF16 = 0, 1
 TCL_DT_F32, TCL_DT_F16, TCL_DT_BF16, TCL_DT_F64 = 0, 1, 2, 3
+KERNEL_IDS = {
+    "l2norm_fwd": 0, "cast16": 1, "transpose16": 2, "ntxent_fwd": 3, "fwd_reduce": 4, "fwd_finalize": 5,
+    "ntxent_bwd": 6, "l2norm_bwd": 7, "sim_gemm": 8, "topk_rank": 9, "gather_gt": 10, "topk_merge": 11,
+}
 
 _DTYPE_CODE = {
     torch.float32: TCL_DT_F32,
@@ -77,6 +81,9 @@ SIGNATURES = {
     "tcl_topk_rank": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_gather_gt_sim": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "tcl_topk_merge": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "tcl_launch_count": (_i64, []),
+    "tcl_profile_enable": (_i, [_i]),
+    "tcl_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "tcl_debug_tmem_probe": (_i, [_vp, _vp]),
 }
 
@@ -147,3 +154,22 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
         elif t.device != dev:
             raise RuntimeError(f"tricolo_b200: tensors on different devices ({dev} vs {t.device})")
     return dev
+
+
+def launch_count() -> int:
+    return int(LIB.tcl_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(LIB.tcl_profile_enable(1 if on else 0))
+
+
+def profile_read() -> dict:
+    """{kernel name: (total device ms, launches)} since the last profile_enable(True)."""
+    out = {}
+    for name, kid in KERNEL_IDS.items():
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(LIB.tcl_profile_read(kid, C.byref(ms), C.byref(n)))
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out

@@ -52,6 +52,16 @@ struct NormBwdParams {
 int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim,
                       int64_t x_stride, int n_split, float eps, cudaStream_t st);
 
+// launch accounting + optional event timing (api.cu)
+void prof_begin(int kernel_id, cudaStream_t st);
+void prof_end(int kernel_id, cudaStream_t st);
+struct ProfScope {
+  int id;
+  cudaStream_t st;
+  ProfScope(int i, cudaStream_t s) : id(i), st(s) { prof_begin(id, st); }
+  ~ProfScope() { prof_end(id, st); }
+};
+
 static inline bool aligned_to(const void* p, size_t a) {
   return (reinterpret_cast<uintptr_t>(p) % a) == 0;
 }

@@ -137,6 +137,7 @@ template <typename TIn, bool kNormalise>
 static int launch_fwd_t(const PtrPack3& pk, int n_tensors, int64_t rows, int dim, int64_t stride,
                         int op_format, float eps, cudaStream_t st) {
   dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_tensors);
+  ProfScope prof(kNormalise ? TCL_K_L2NORM_FWD : TCL_K_CAST16, st);
   if (op_format == TCL_OP_F16)
     l2norm_fwd_kernel<TIn, __half, kNormalise><<<grid, 256, 0, st>>>(pk, rows, dim, stride, eps);
   else
@@ -265,6 +266,7 @@ int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t 
                       int64_t x_stride, int n_split, float eps, cudaStream_t st) {
   TCL_REQUIRE(dim <= 512 && dim % 4 == 0, TCL_ERR_BAD_SHAPE, "normalise backward: dim %d > 512", dim);
   dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_jobs);
+  ProfScope prof(TCL_K_L2NORM_BWD, st);
   switch (x_dtype) {
     case TCL_DT_F32: l2norm_bwd_kernel<float><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
     case TCL_DT_F64: l2norm_bwd_kernel<double><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
@@ -329,7 +331,10 @@ extern "C" int tcl_transpose_16bit(int n_tensors, const void* const* z, int64_t 
     pk.in[i] = z[i]; pk.out[i] = zt[i];
   }
   dim3 grid(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((dim + 63) / 64), n_tensors);
-  transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pk, rows, (int)dim, ld_t);
+  {
+    ProfScope prof(TCL_K_TRANSPOSE16, static_cast<cudaStream_t>(stream));
+    transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pk, rows, (int)dim, ld_t);
+  }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }

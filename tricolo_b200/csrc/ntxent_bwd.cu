@@ -407,6 +407,7 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   const int smem = (int)BwdSmem::total(P.num_kb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(n_iblocks, P.n_dhalf * P.n_split, n_jobs);
+  prof_begin(TCL_K_NTXENT_BWD, st);
   if (op_format == TCL_OP_F16) {
     static int set = 0;
     if (set < smem) { TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_kernel<TCL_OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = smem; }
@@ -416,6 +417,7 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     if (set < smem) { TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_kernel<TCL_OP_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = smem; }
     ntxent_bwd_kernel<TCL_OP_BF16><<<grid, BW_THREADS, smem, st>>>(P);
   }
+  prof_end(TCL_K_NTXENT_BWD, st);
   TCL_CHECK_CUDA(cudaGetLastError());
   return launch_l2norm_bwd(N, n_jobs, x_dtype, n_self, (int)dim, x_row_stride, P.n_split, eps, st);
 }

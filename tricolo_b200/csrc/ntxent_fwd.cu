@@ -407,11 +407,17 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(P.n_iblocks, P.n_jsplit, n_pairs);
-  ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);
+  {
+    ProfScope prof(TCL_K_NTXENT_FWD, st);
+    ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);
+  }
   TCL_CHECK_CUDA(cudaGetLastError());
   const int nmax = (int)(n_rows > n_cols ? n_rows : n_cols);
-  fwd_reduce_kernel<<<dim3((nmax + 255) / 256, n_pairs), 256, 0, st>>>(
-      P.row_part, P.col_part, row_sumexp, col_sumexp, n_pairs, P.n_rows, P.n_cols, P.n_jsplit, P.n_iblocks);
+  {
+    ProfScope prof(TCL_K_FWD_REDUCE, st);
+    fwd_reduce_kernel<<<dim3((nmax + 255) / 256, n_pairs), 256, 0, st>>>(
+        P.row_part, P.col_part, row_sumexp, col_sumexp, n_pairs, P.n_rows, P.n_cols, P.n_jsplit, P.n_iblocks);
+  }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
@@ -425,8 +431,11 @@ extern "C" int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, 
   TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && lse2_row && lse2_col && loss_parts, TCL_ERR_BAD_ARG, "finalize: null pointer");
   if (int e = require_sm100()) return e;
   const float c1 = inv_tau * 1.4426950408889634f;
-  fwd_finalize_kernel<<<n_pairs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss);
+  {
+    ProfScope prof(TCL_K_FWD_FINALIZE, static_cast<cudaStream_t>(stream));
+    fwd_finalize_kernel<<<n_pairs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss);
+  }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }

@@ -173,8 +173,11 @@ extern "C" int tcl_sim_gemm(const void* q, const void* g, int64_t n_q, int64_t n
   }
   dim3 grid(static_cast<unsigned>((n_g + SG_BN - 1) / SG_BN), static_cast<unsigned>((n_q + SG_BM - 1) / SG_BM));
   TCL_REQUIRE(grid.y <= 65535, TCL_ERR_BAD_SHAPE, "sim_gemm: more than 65535*128 query rows per call; chunk the queries");
-  sim_gemm_kernel<<<grid, 192, SG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      tm_a, tm_b, s, ld_s, (int)n_q, (int)n_g, (int)dim, umma_idesc_f16(SG_BM, SG_BN, op_format));
+  {
+    ProfScope prof(TCL_K_SIM_GEMM, static_cast<cudaStream_t>(stream));
+    sim_gemm_kernel<<<grid, 192, SG_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+        tm_a, tm_b, s, ld_s, (int)n_q, (int)n_g, (int)dim, umma_idesc_f16(SG_BM, SG_BN, op_format));
+  }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }

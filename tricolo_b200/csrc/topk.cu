@@ -195,6 +195,7 @@ extern "C" int tcl_topk_rank(const float* s, int64_t ld_s, int64_t n_q, int64_t 
   if (n_q == 0) return TCL_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>((n_q + 7) / 8);
+  ProfScope prof(TCL_K_TOPK_RANK, st);
   if (k <= 5)
     topk_rank_kernel<5><<<grid, 256, 0, st>>>(s, ld_s, n_q, (int)n_g, k, labels, idx_base, gt_sim_in,
                                               topk_val, topk_idx, gt_sim_out, n_before);
@@ -212,6 +213,7 @@ extern "C" int tcl_gather_gt_sim(const float* s, int64_t ld_s, int64_t n_q, int6
   TCL_REQUIRE(n_q >= 0 && n_g >= 1 && ld_s >= n_g, TCL_ERR_BAD_SHAPE, "gather_gt: shape");
   if (int e = require_sm100()) return e;
   if (n_q == 0) return TCL_OK;
+  ProfScope prof(TCL_K_GATHER_GT, static_cast<cudaStream_t>(stream));
   gather_gt_kernel<<<static_cast<unsigned>((n_q + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       s, ld_s, n_q, n_g, labels, idx_base, gt_sim);
   TCL_CHECK_CUDA(cudaGetLastError());
@@ -226,6 +228,7 @@ extern "C" int tcl_topk_merge(const float* cand_val, const int32_t* cand_idx, in
   TCL_REQUIRE(cand_val && cand_idx && topk_val && topk_idx, TCL_ERR_BAD_ARG, "merge: null pointer");
   if (int e = require_sm100()) return e;
   if (n_q == 0) return TCL_OK;
+  ProfScope prof(TCL_K_TOPK_MERGE, static_cast<cudaStream_t>(stream));
   topk_merge_kernel<<<static_cast<unsigned>((n_q + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       cand_val, cand_idx, n_shards, n_q, k, topk_val, topk_idx);
   TCL_CHECK_CUDA(cudaGetLastError());

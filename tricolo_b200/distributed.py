@@ -1,0 +1,152 @@
+"""Multi-GPU forms of the hot path: one process per GPU, torch.distributed (NCCL over NVLink).
+
+Training — global-negative trimodal InfoNCE (BASELINE.json configs[3]).  The reference never
+gathers negatives; the semantics here are "the reference loss evaluated on the
+concatenated global batch".  Each rank holds B/W rows of every modality and owns that row block
+of each logit matrix:
+    all-gather   16-bit normalised embeddings                 (W-1)/W * 3*B*D*2 bytes in
+    all-reduce   column sum-exp partials, 3 x [B] fp32         (fixed shift -> plain sums)
+    all-gather   row LSEs 3 x [B/W] fp32, all-reduce loss partials
+The backward is the same directional kernel as on one GPU, run for the local rows of each
+modality against ALL rows of the partner modality, so every local gradient is complete without a
+gradient reduce-scatter (the recompute the kernel does anyway replaces the exchange).
+
+Retrieval — gallery sharded over ranks (configs[4]): every rank scores all queries against its
+shard; ground-truth similarities are all-reduced (owner contributes, others add 0), local top-k
+lists are all-gathered and merged, rank counts are all-reduced.
+"""
+from __future__ import annotations
+
+from itertools import combinations
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .loss.nt_xent import DEFAULT_OP_FORMAT
+
+
+def _world(group=None):
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+class _GlobalNTXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, temperature, alpha, op_format, pairs, group, grad_world_scale, *feats):
+        world, rank = _world(group)
+        inv_tau = 1.0 / float(temperature)
+        feats = [f.detach() for f in feats]
+        b_loc, dim = feats[0].shape
+        b_glob = b_loc * world
+        row_offset = rank * b_loc
+        zs, invs, xs = ops.l2norm_fwd(feats, op_format)
+        # all-gather each modality straight into its [B, D] operand (rank-major rows)
+        z_all = []
+        for z in zs:
+            full = torch.empty((b_glob, dim), dtype=z.dtype, device=z.device)
+            dist.all_gather_into_tensor(full, z, group=group)
+            z_all.append(full)
+        zrows = [zs[a] for a, _ in pairs]
+        zcols = [z_all[b] for _, b in pairs]
+        row_sum, col_sum, diag2 = ops.ntxent_fwd(zrows, zcols, row_offset, inv_tau, op_format)
+        dist.all_reduce(col_sum, group=group)
+        lse2_row, lse2_col, parts, _ = ops.ntxent_finalize(row_sum, col_sum, diag2, row_offset, inv_tau, alpha,
+                                                           want_loss=False)
+        dist.all_reduce(parts, group=group)
+        loss = (alpha * parts[:, 0] + (1.0 - alpha) * parts[:, 1]) / b_glob
+        # row LSEs of every rank (needed when a local column block meets all rows in the backward)
+        lse2_row_all = torch.empty((world * len(pairs), b_loc), dtype=torch.float32, device=lse2_row.device)
+        dist.all_gather_into_tensor(lse2_row_all, lse2_row, group=group)  # [W*P, b_loc], rank-major
+        lse2_row_all = lse2_row_all.view(world, len(pairs), b_loc).permute(1, 0, 2).reshape(len(pairs), b_glob).contiguous()
+        ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale))
+        ctx.save_for_backward(lse2_row_all, lse2_col, *xs, *zs, *invs, *z_all)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        inv_tau, alpha, op_format, pairs, row_offset, b_glob, gscale = ctx.cfg
+        saved = ctx.saved_tensors
+        lse2_row_all, lse2_col = saved[0], saved[1]
+        n = (len(saved) - 2) // 4
+        xs, zs, invs, z_all = (saved[2:2 + n], saved[2 + n:2 + 2 * n], saved[2 + 2 * n:2 + 3 * n],
+                               saved[2 + 3 * n:])
+        b_loc = zs[0].shape[0]
+        grad_losses = (grad_losses.to(torch.float32) * gscale).contiguous()
+        zts, ld_t = ops.transpose_16bit(z_all)
+        jobs, owners = [], []
+        sl = slice(row_offset, row_offset + b_loc)
+        for m in range(n):
+            if not ctx.needs_input_grad[6 + m]:
+                continue
+            segs = []
+            for p, (a, b) in enumerate(pairs):
+                if m == a:
+                    segs.append(ops.BwdSegmentSpec(z_all[b], zts[b], lse2_row_all[p, sl], lse2_col[p],
+                                                   grad_losses[p:p + 1], alpha, 1.0 - alpha))
+                elif m == b:
+                    segs.append(ops.BwdSegmentSpec(z_all[a], zts[a], lse2_col[p, sl], lse2_row_all[p],
+                                                   grad_losses[p:p + 1], 1.0 - alpha, alpha))
+            if segs:
+                jobs.append(ops.BwdJobSpec(zs[m], xs[m], invs[m], segs))
+                owners.append(m)
+        grads: List = [None] * n
+        if jobs:
+            for m, dx in zip(owners, ops.ntxent_bwd(jobs, b_glob, row_offset, ld_t, inv_tau, op_format)):
+                grads[m] = dx
+        return (None, None, None, None, None, None, *grads)
+
+
+def global_trimodal_ntxent(feats: Sequence[torch.Tensor], temperature: float, alpha: float, group=None,
+                           op_format: int = DEFAULT_OP_FORMAT, grad_world_scale: float = 1.0) -> torch.Tensor:
+    """Per-pair losses of the GLOBAL batch (identical on every rank); gradients are
+    d(global loss)/d(local rows). Under DDP (which averages parameter gradients over ranks) pass
+    grad_world_scale=world_size to reproduce the single-process global-batch gradient."""
+    feats = list(feats)
+    pairs = list(combinations(range(len(feats)), 2))
+    return _GlobalNTXent.apply(float(temperature), float(alpha), op_format, pairs, group, grad_world_scale, *feats)
+
+
+def global_calculate_losses(output_dict, loss_prefix, temperature, alpha, group=None, **kw):
+    """Sharded counterpart of TriCoLoNet._calculate_losses (tricolo_net.py:56-65), same keys."""
+    keys = list(output_dict.keys())
+    losses = global_trimodal_ntxent([output_dict[k] for k in keys], temperature, alpha, group, **kw)
+    out = {}
+    for p, (a, b) in enumerate(combinations(keys, 2)):
+        out[f"{loss_prefix}/{a[:-9]}_{b[:-9]}_loss"] = losses[p]
+    out[f"{loss_prefix}/total_loss"] = sum(out.values())
+    return out
+
+
+def sharded_retrieve(text: torch.Tensor, gallery_shard: torch.Tensor, labels: torch.Tensor, idx_base: int,
+                     k: int = 5, group=None, block_queries: int = 8192, operand_format: int = ops.BF16):
+    """Gallery-sharded retrieval. text [Q,D] (all queries, replicated), gallery_shard [G_loc,D] with global
+    index base idx_base, labels [Q] global gallery indices. Returns (topk_val, topk_idx, rank) — identical on
+    every rank."""
+    world, _ = _world(group)
+    dt = ops.L.op_torch_dtype(operand_format)
+    g16 = gallery_shard if gallery_shard.dtype == dt else ops.cast_16bit(gallery_shard, operand_format)
+    n_q, n_g = text.shape[0], gallery_shard.shape[0]
+    dev = text.device
+    labels = labels.to(torch.int64)
+    val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    nb = torch.empty((n_q,), dtype=torch.int32, device=dev)
+    ld = (n_g + 3) // 4 * 4
+    buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
+    for s in range(0, n_q, block_queries):
+        e = min(s + block_queries, n_q)
+        tq = text[s:e]
+        q16 = tq if tq.dtype == dt else ops.cast_16bit(tq, operand_format)
+        sim, _ = ops.sim_gemm(q16, g16, out=buf[: e - s])
+        gt = ops.gather_gt_sim(sim, n_g, labels[s:e], idx_base)
+        dist.all_reduce(gt, group=group)  # owner shard contributes, the others add 0
+        v, i, _, b = ops.topk_rank(sim, n_g, k, labels[s:e], idx_base, gt)
+        val[s:e], idx[s:e], nb[s:e] = v, i, b
+    cand_v = torch.empty((world * n_q, k), dtype=torch.float32, device=dev)
+    cand_i = torch.empty((world * n_q, k), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(cand_v, val, group=group)
+    dist.all_gather_into_tensor(cand_i, idx, group=group)
+    dist.all_reduce(nb, group=group)
+    mv, mi = ops.topk_merge(cand_v.view(world, n_q, k), cand_i.view(world, n_q, k))
+    return mv, mi, nb + 1
