@@ -15,7 +15,8 @@
 // CTA = (i-block of 128 self rows, half of dim, split of the tile range, job).
 // The full-dim fp32 accumulator of 128 rows would need all 512 TMEM columns, so
 // each CTA owns 256 columns of dim (TMEM: 2 x 128 logit buffers + 256 accumulator).
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2..5 epilogue (thread = TMEM lane = row).
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2..9 epilogue (thread = TMEM lane = row; two warps
+// per lane quarter split the 128 logit columns).
 #include "host_common.h"
 #include "../../include/tricolo_b200.h"
 
@@ -24,7 +25,9 @@ namespace tcl {
 static constexpr int BW_BM = 128, BW_BN = 128, BW_BK = 64;
 static constexpr int BW_KB_BYTES = BW_BM * BW_BK * 2;  // 16 KB
 static constexpr int BW_STAGES = 4;
-static constexpr int BW_THREADS = 192;
+static constexpr int BW_EPI_WARPS = 8;  // two per TMEM lane quarter: columns 0-63 / 64-127 of the logit tile
+static constexpr int BW_EPI_THREADS = BW_EPI_WARPS * 32;
+static constexpr int BW_THREADS = 64 + BW_EPI_THREADS;
 static constexpr int BW_DH = 256;  // dim columns per CTA
 
 struct BwdSegDev {
@@ -123,9 +126,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
     mbar_init(x_full_bar, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(s_full_bar(b), 1);
-      mbar_init(s_empty_bar(b), 128);
+      mbar_init(s_empty_bar(b), BW_EPI_THREADS);
     }
-    mbar_init(g_full_bar, 128);
+    mbar_init(g_full_bar, BW_EPI_THREADS);
     mbar_init(g_empty_bar, 1);
     mbar_init(acc_full_bar, 1);
     fence_mbar_init();
@@ -224,10 +227,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // tile-local row == TMEM lane
-    const int et = threadIdx.x - 64;
-    const int grow = i0 + r;  // local self row
+    const int q = warp & 3;          // TMEM lane quarter
+    const int ch = (warp - 2) >> 2;  // column half of the logit tile == K-block of the G operand
+    const int r = q * 32 + lane;     // tile-local row == TMEM lane
+    const int et = threadIdx.x - 64;  // 0..255
+    const int grow = i0 + r;          // local self row
     // gradient scales: ratio to the largest magnitude keeps G' inside [-1, 1]
     float gs[2] = {0.f, 0.f};
     float gmax = 0.f;
@@ -238,83 +242,103 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
     const float inv_gmax = gmax > 0.f ? 1.f / gmax : 0.f;
     if (blockIdx.x == 0 && blockIdx.y == 0 && et == 0) *J.scale_out = gmax * P.out_scale;
 
+    // per-column factors 2^(c1 - lse_other_j) of tile t, fetched one tile ahead
+    auto load_bj = [&](int t) -> float {
+      if (et >= 128 || t >= n_tiles) return 0.f;
+      const int tt = t_begin + t;
+      const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
+      const int j = (tt % P.n_jtiles) * BW_BN + et;
+      return j < P.n_other ? ex2_approx(P.c1 - sg.lse2_other[j]) : 0.f;
+    };
+    if (et < 128 && n_tiles > 0) bj[et] = load_bj(0);
+    int cur_seg = -1;
+    float lse_i = 0.f, ws = 0.f, wo_i = 0.f, rr = 0.f;
+
     for (int t = 0; t < n_tiles; ++t) {
       const int tt = t_begin + t;
       const int si = tt / P.n_jtiles;
-      const BwdSegDev& sg = J.seg[si];
       const int j0 = (tt % P.n_jtiles) * BW_BN;
       const int b = t & 1;
-      const float rr = gs[si] * inv_gmax;
-      // per-row constants:  p_other = p_self * 2^(lse_self_i - c1) * 2^(c1 - lse_other_j)
-      const float lse_i = grow < P.n_self ? sg.lse2_self[grow] : 0.f;
-      const float ws = rr * sg.w_self;
-      const float wo_i = rr * sg.w_other * ex2_approx(lse_i - P.c1);
-      // per-column factors of this tile
-      {
-        const int j = j0 + et;
-        bj[(t & 1) * 128 + et] = j < P.n_other ? ex2_approx(P.c1 - sg.lse2_other[j]) : 0.f;
+      if (si != cur_seg) {  // per-row constants of this segment
+        const BwdSegDev& sg = J.seg[si];
+        cur_seg = si;
+        rr = gs[si] * inv_gmax;
+        lse_i = grow < P.n_self ? sg.lse2_self[grow] : 0.f;
+        ws = rr * sg.w_self;
+        // p_other = p_self * 2^(lse_self_i - c1) * 2^(c1 - lse_other_j)
+        wo_i = rr * sg.w_other * ex2_approx(lse_i - P.c1);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float bj_next = load_bj(t + 1);  // in flight while this tile is processed
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // bj[t&1] visible to all epilogue threads
       const float* bjt = bj + (t & 1) * 128;
       // diagonal of this segment: global self index == other index
       const int dcol = P.self_offset + grow - j0;  // tile-local column of the positive
 
       mbar_wait(s_full_bar(b), (t >> 1) & 1);
       tc_fence_after();
-      mbar_wait(g_empty_bar, (t & 1) ^ 1);  // previous gradient MMAs finished reading G
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_addr(tmem + b * BW_BN, q * 32, cc * 32), v);
-        tc_wait_ld();
-        uint32_t pk[16];
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(tmem_addr(tmem + b * BW_BN, q * 32, (2 * ch) * 32), v[0]);
+      tmem_ld_32x32b_x32(tmem_addr(tmem + b * BW_BN, q * 32, (2 * ch + 1) * 32), v[1]);
+      tc_wait_ld();
+      // logits are in registers: the TMEM buffer can be refilled
+      tc_fence_before();
+      mbar_arrive(s_empty_bar(b));
+      uint32_t pk[2][16];
+#pragma unroll
+      for (int cl = 0; cl < 2; ++cl) {
+        const int cc = 2 * ch + cl;
         const int dl = dcol - cc * 32;
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), P.c1, -lse_i));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), P.c1, -lse_i));
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[cl][e]), P.c1, -lse_i));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[cl][e + 1]), P.c1, -lse_i));
           const float g0 = fmaf(p0, fmaf(wo_i, bjt[cc * 32 + e], ws), (e == dl) ? -rr : 0.f);
           const float g1 = fmaf(p1, fmaf(wo_i, bjt[cc * 32 + e + 1], ws), (e + 1 == dl) ? -rr : 0.f);
-          pk[e >> 1] = pack2<kOp>(g0, g1);
-        }
-        // K-major, 128-byte-swizzled operand tile: row r, 16-byte chunk c16 -> c16 ^ (r & 7)
-        uint8_t* gk = g_ptr + (cc >> 1) * BW_KB_BYTES + r * 128;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int c16 = (cc & 1) * 4 + c4;
-          *reinterpret_cast<uint4*>(gk + ((c16 ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+          pk[cl][e >> 1] = pack2<kOp>(g0, g1);
         }
       }
-      // logits consumed; G visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(s_empty_bar(b));
+      mbar_wait(g_empty_bar, (t & 1) ^ 1);  // previous gradient MMAs finished reading G
+      // K-major, 128-byte-swizzled operand tile: row r, 16-byte chunk c16 -> c16 ^ (r & 7)
+      uint8_t* gk = g_ptr + ch * BW_KB_BYTES + r * 128;
+#pragma unroll
+      for (int cl = 0; cl < 2; ++cl) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int c16 = cl * 4 + c4;
+          *reinterpret_cast<uint4*>(gk + ((c16 ^ (r & 7)) << 4)) =
+              make_uint4(pk[cl][4 * c4], pk[cl][4 * c4 + 1], pk[cl][4 * c4 + 2], pk[cl][4 * c4 + 3]);
+        }
+      }
+      // G visible to the tensor core (async proxy)
       fence_proxy_async_smem();
       mbar_arrive(g_full_bar);
+      if (et < 128 && t + 1 < n_tiles) bj[((t + 1) & 1) * 128 + et] = bj_next;
     }
 
     if (n_tiles > 0) {
       mbar_wait(acc_full_bar, 0);
       tc_fence_after();
     }
+    // accumulator read-out: column half ch of this CTA's 256 dim columns
     float* gout = J.gpart + (static_cast<int64_t>(split) * P.n_self + grow) * P.dim + d0;
-    const int n_cols = n_dc * 128;
+    if (ch < n_dc) {
 #pragma unroll 1
-    for (int cc = 0; cc < n_cols / 32; ++cc) {
-      uint32_t v[32];
-      if (n_tiles > 0) {
-        tmem_ld_32x32b_x32(tmem_addr(tmem_acc, q * 32, cc * 32), v);
-        tc_wait_ld();
-      } else {
+      for (int cc = ch * 4; cc < ch * 4 + 4; ++cc) {
+        uint32_t v[32];
+        if (n_tiles > 0) {
+          tmem_ld_32x32b_x32(tmem_addr(tmem_acc, q * 32, cc * 32), v);
+          tc_wait_ld();
+        } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = 0u;
-      }
-      if (grow < P.n_self) {
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+        if (grow < P.n_self) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          *reinterpret_cast<float4*>(gout + cc * 32 + e) =
-              make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                          __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(gout + cc * 32 + e) =
+                make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                            __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
       }
     }
   }

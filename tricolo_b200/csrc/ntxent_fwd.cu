@@ -5,7 +5,8 @@
 // Work decomposition: CTA (i-block, j-split, pair) keeps its 128 rows of the row
 // operand resident in shared memory (dim/64 swizzled 16 KB K-blocks) and sweeps a
 // range of 128-column tiles of the column operand, streamed through a TMA ring.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM owner), 2..5 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM owner), 2..9 = epilogue (two warps per
+// TMEM lane quarter, each owning 64 of the tile's 128 columns).
 // Two 128-column TMEM accumulators alternate so the epilogue of tile t overlaps
 // the MMAs of tile t+1.
 //
@@ -23,12 +24,14 @@ static constexpr int FW_BM = 128, FW_BN = 128, FW_BK = 64;
 static constexpr int FW_KB_BYTES = FW_BM * FW_BK * 2;  // 16 KB
 static constexpr int FW_MAX_KB = 8;                     // dim <= 512
 static constexpr int FW_STAGES = 5;
-static constexpr int FW_THREADS = 192;
+static constexpr int FW_EPI_WARPS = 8;  // two per TMEM lane quarter, 64 tile columns each
+static constexpr int FW_EPI_THREADS = FW_EPI_WARPS * 32;
+static constexpr int FW_THREADS = 64 + FW_EPI_THREADS;
 
 struct FwdParams {
   CUtensorMap tm_row[TCL_MAX_PAIRS];
   CUtensorMap tm_col[TCL_MAX_PAIRS];
-  float* row_part;  // [pairs][n_jsplit][n_rows]
+  float* row_part;  // [pairs][2 * n_jsplit][n_rows]  (two column halves per split)
   float* col_part;  // [pairs][n_iblocks][n_cols]
   float* diag2;     // [pairs][n_rows]
   int n_rows, n_cols, row_offset;
@@ -47,30 +50,32 @@ struct FwdSmem {
   static constexpr uint32_t total(int num_kb) { return colbuf_off(num_kb) + 2 * 4 * 128 * 4 + 1024; }
 };
 
+// One epilogue warp: TMEM lane quarter q (32 rows), column half ch (64 of the tile's 128 columns).
 template <bool kMasked>
-__device__ __forceinline__ void fwd_tile_epilogue(uint32_t tmem_acc, int q, int lane, float c1,
-                                                  float (&rs)[4], float (&cs)[32], int row_base,
+__device__ __forceinline__ void fwd_tile_epilogue(uint32_t tmem_acc, int q, int ch, int lane, float c1,
+                                                  float (&rs)[4], float (&cs)[16], int row_base,
                                                   int col_base, int n_rows, int n_cols,
                                                   int diag_delta, bool has_diag, float* diag_out) {
   // quad layout: ql = lane/4 -> rows, p = lane%4 -> column pairs
   const int ql = lane >> 2, p = lane & 3;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) cs[c] = 0.f;
+  for (int c = 0; c < 16; ++c) cs[c] = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int r_lo = q * 32 + h * 16 + ql;  // tile-local rows r_lo and r_lo + 8
+    uint32_t v[2][16];
+    tmem_ld_16x256b_x4(tmem_addr(tmem_acc, q * 32 + h * 16, (2 * ch) * 32), v[0]);
+    tmem_ld_16x256b_x4(tmem_addr(tmem_acc, q * 32 + h * 16, (2 * ch + 1) * 32), v[1]);
+    tc_wait_ld();
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      uint32_t v[16];
-      tmem_ld_16x256b_x4(tmem_addr(tmem_acc, q * 32 + h * 16, cc * 32), v);
-      tc_wait_ld();
+    for (int cl = 0; cl < 2; ++cl) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int col = cc * 32 + g * 8 + 2 * p + e;  // tile-local column
-          const float s0 = __uint_as_float(v[4 * g + e]);      // row r_lo
-          const float s1 = __uint_as_float(v[4 * g + 2 + e]);  // row r_lo + 8
+          const int col = (2 * ch + cl) * 32 + g * 8 + 2 * p + e;  // tile-local column
+          const float s0 = __uint_as_float(v[cl][4 * g + e]);      // row r_lo
+          const float s1 = __uint_as_float(v[cl][4 * g + 2 + e]);  // row r_lo + 8
           float e0 = ex2_approx(fmaf(s0, c1, -c1));
           float e1 = ex2_approx(fmaf(s1, c1, -c1));
           if (has_diag) {
@@ -89,7 +94,7 @@ __device__ __forceinline__ void fwd_tile_epilogue(uint32_t tmem_acc, int q, int 
           }
           rs[2 * h + 0] += e0;
           rs[2 * h + 1] += e1;
-          cs[cc * 8 + g * 2 + e] += e0 + e1;
+          cs[cl * 8 + g * 2 + e] += e0 + e1;
         }
       }
     }
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
     mbar_init(x_full_bar, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), 128);
+      mbar_init(tmem_empty_bar(b), FW_EPI_THREADS);
     }
     fence_mbar_init();
   }
@@ -188,11 +193,12 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
       }
     }
   } else {
-    const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int ch = (warp - 2) >> 2;  // column half of the tile (64 columns)
+    const int et = threadIdx.x - 64;  // 0..255 among epilogue threads
     const int ql = lane >> 2, p = lane & 3;
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
-    float cs[32];
+    float cs[16];
     float* diag_out = P.diag2 + static_cast<int64_t>(pair) * P.n_rows + i0;
     const bool row_edge = i0 + FW_BM > P.n_rows;
     for (int t = 0; t < n_tiles; ++t) {
@@ -205,68 +211,68 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
       const bool has_diag = diag_delta > -FW_BN && diag_delta < FW_BM;
       const bool masked = row_edge || (j0 + FW_BN > P.n_cols);
       if (masked)
-        fwd_tile_epilogue<true>(tmem + b * FW_BN, q, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
+        fwd_tile_epilogue<true>(tmem + b * FW_BN, q, ch, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
                                 diag_delta, has_diag, diag_out);
       else
-        fwd_tile_epilogue<false>(tmem + b * FW_BN, q, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
+        fwd_tile_epilogue<false>(tmem + b * FW_BN, q, ch, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
                                  diag_delta, has_diag, diag_out);
       // TMEM buffer fully read -> hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(b));
 
-      // column sums: butterfly over the 8 row groups (lane bits 4,3,2)
-      float a16[16], a8[8], a4[4];
+      // column sums: butterfly over the 8 row groups (lane bits 4,3,2): 16 -> 8 -> 4 -> 2 values
+      float a8[8], a4[4], a2[2];
       {
         const bool hi = (lane & 16) != 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float send = hi ? cs[i] : cs[i + 16];
-          const float keep = hi ? cs[i + 16] : cs[i];
-          a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int i = 0; i < 8; ++i) {
+          const float send = hi ? cs[i] : cs[i + 8];
+          const float keep = hi ? cs[i + 8] : cs[i];
+          a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
       }
       {
         const bool hi = (lane & 8) != 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float send = hi ? a16[i] : a16[i + 8];
-          const float keep = hi ? a16[i + 8] : a16[i];
-          a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        for (int i = 0; i < 4; ++i) {
+          const float send = hi ? a8[i] : a8[i + 4];
+          const float keep = hi ? a8[i + 4] : a8[i];
+          a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
       }
       {
         const bool hi = (lane & 4) != 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = hi ? a8[i] : a8[i + 4];
-          const float keep = hi ? a8[i + 4] : a8[i];
-          a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        for (int i = 0; i < 2; ++i) {
+          const float send = hi ? a4[i] : a4[i + 2];
+          const float keep = hi ? a4[i + 2] : a4[i];
+          a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         }
       }
-      // this thread now owns cidx = bit4*16 + bit3*8 + bit2*4 + i
+      // this thread now owns cidx = bit4*8 + bit3*4 + bit2*2 + i  (cl = cidx>>3, g = (cidx>>1)&3, e = cidx&1)
       float* cb = colbuf + (t & 1) * 512 + q * 128;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int cidx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + i;
-        const int cc = cidx >> 3, g = (cidx >> 1) & 3, e = cidx & 1;
-        cb[cc * 32 + g * 8 + 2 * p + e] = a4[i];
+      for (int i = 0; i < 2; ++i) {
+        const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + i;
+        const int cl = cidx >> 3, g = (cidx >> 1) & 3, e = cidx & 1;
+        cb[(2 * ch + cl) * 32 + g * 8 + 2 * p + e] = a2[i];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et < 128) {
         const float* c0 = colbuf + (t & 1) * 512;
         const float tot = c0[et] + c0[128 + et] + c0[256 + et] + c0[384 + et];
         if (j0 + et < P.n_cols)
           P.col_part[(static_cast<int64_t>(pair) * P.n_iblocks + ib) * P.n_cols + j0 + et] = tot;
       }
     }
-    // row sums: reduce over the 4 column-pair lanes, then one store per row
+    // row sums: reduce over the 4 column-pair lanes, then one store per row and column half
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
       rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
     }
     if (p == 0) {
-      float* rp = P.row_part + (static_cast<int64_t>(pair) * P.n_jsplit + js) * P.n_rows;
+      float* rp = P.row_part + (static_cast<int64_t>(pair) * (2 * P.n_jsplit) + 2 * js + ch) * P.n_rows;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int row = i0 + q * 32 + (r >> 1) * 16 + ql + (r & 1) * 8;
@@ -357,7 +363,7 @@ extern "C" size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, in
   const int n_jtiles = static_cast<int>((n_cols + FW_BN - 1) / FW_BN);
   const int n_jsplit = fwd_split(n_pairs, n_iblocks, n_jtiles);
   return sizeof(float) * static_cast<size_t>(n_pairs) *
-         (static_cast<size_t>(n_jsplit) * n_rows + static_cast<size_t>(n_iblocks) * n_cols);
+         (static_cast<size_t>(2 * n_jsplit) * n_rows + static_cast<size_t>(n_iblocks) * n_cols);
 }
 
 extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* const* zcol,
@@ -396,7 +402,7 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
   P.c1 = c1;
   P.idesc = umma_idesc_f16(FW_BM, FW_BN, op_format);
   P.row_part = static_cast<float*>(workspace);
-  P.col_part = P.row_part + static_cast<size_t>(n_pairs) * P.n_jsplit * n_rows;
+  P.col_part = P.row_part + static_cast<size_t>(n_pairs) * 2 * P.n_jsplit * n_rows;
   P.diag2 = diag2;
 
   const int smem = (int)FwdSmem::total(P.num_kb);
@@ -416,7 +422,7 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
   {
     ProfScope prof(TCL_K_FWD_REDUCE, st);
     fwd_reduce_kernel<<<dim3((nmax + 255) / 256, n_pairs), 256, 0, st>>>(
-        P.row_part, P.col_part, row_sumexp, col_sumexp, n_pairs, P.n_rows, P.n_cols, P.n_jsplit, P.n_iblocks);
+        P.row_part, P.col_part, row_sumexp, col_sumexp, n_pairs, P.n_rows, P.n_cols, 2 * P.n_jsplit, P.n_iblocks);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;

@@ -90,27 +90,40 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int q = warp & 3;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int row = m0 + q * 32 + lane;
-    float* crow = c + static_cast<int64_t>(row) * ldc + n0;
+    // All TMA loads have landed and all MMAs have read them (tmem_full): the operand ring is dead and
+    // is reused as a per-warp 32x32 fp32 staging tile (row stride 36 floats: conflict-free both ways)
+    // so that every global store instruction writes four full 128-byte lines.
+    float* stage = reinterpret_cast<float*>(smem_raw + (base - raw)) + q * (32 * 36);
+    const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
     for (int cc = 0; cc < SG_BN / 32; ++cc) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, cc * 32), v);
       tc_wait_ld();
-      if (row < m) {
-        const int col0 = n0 + cc * 32;
-        if (col0 + 32 <= n) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(crow + cc * 32 + e) =
-                make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                            __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        } else {
+      for (int c4 = 0; c4 < 8; ++c4)
+        *reinterpret_cast<float4*>(stage + lane * 36 + c4 * 4) =
+            make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                        __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+      __syncwarp();
+      const int gcol = n0 + cc * 32 + sub_c;
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col0 + e < n) crow[cc * 32 + e] = __uint_as_float(v[e]);
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub_r;
+        const int grow = m0 + q * 32 + r;
+        const float4 x = *reinterpret_cast<const float4*>(stage + r * 36 + sub_c);
+        if (grow < m) {
+          float* dst = c + static_cast<int64_t>(grow) * ldc + gcol;
+          if (gcol + 4 <= n) {
+            *reinterpret_cast<float4*>(dst) = x;
+          } else {
+            if (gcol < n) dst[0] = x.x;
+            if (gcol + 1 < n) dst[1] = x.y;
+            if (gcol + 2 < n) dst[2] = x.z;
+          }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

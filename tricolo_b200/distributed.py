@@ -132,7 +132,7 @@ def sharded_retrieve(text: torch.Tensor, gallery_shard: torch.Tensor, labels: to
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     nb = torch.empty((n_q,), dtype=torch.int32, device=dev)
-    ld = (n_g + 3) // 4 * 4
+    ld = (n_g + 31) // 32 * 32
     buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
     for s in range(0, n_q, block_queries):
         e = min(s + block_queries, n_q)

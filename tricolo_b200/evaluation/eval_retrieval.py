@@ -212,7 +212,7 @@ def retrieve(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k:
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     rank = torch.empty((n_q,), dtype=torch.int32, device=dev)
-    ld = (n_g + 3) // 4 * 4
+    ld = (n_g + 31) // 32 * 32
     buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
     labels = labels.to(torch.int64)
     for s in range(0, n_q, block_queries):

@@ -152,13 +152,14 @@ def ntxent_bwd(jobs: Sequence[BwdJobSpec], n_other: int, self_offset: int, ld_t:
 
 
 def sim_gemm(q16: torch.Tensor, g16: torch.Tensor, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
-    """K2'. S = Q G^T in fp32 with leading dimension ld (multiple of 4). Returns (S [n_q, ld], n_g)."""
+    """K2'. S = Q G^T in fp32 with leading dimension ld (multiple of 32 floats = one 128-byte line).
+    Returns (S [n_q, ld], n_g)."""
     dev = L.require_cuda(q16, g16)
     if q16.dtype != g16.dtype or q16.dtype not in (torch.float16, torch.bfloat16):
         raise TypeError("sim_gemm: operands must both be float16 or both bfloat16")
     n_q, dim = q16.shape
     n_g = g16.shape[0]
-    ld = (n_g + 3) // 4 * 4
+    ld = (n_g + 31) // 32 * 32
     if out is None:
         out = torch.empty((n_q, ld), dtype=torch.float32, device=dev)
     op = F16 if q16.dtype == torch.float16 else BF16
