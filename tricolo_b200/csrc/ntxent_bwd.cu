@@ -349,13 +349,22 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
 
 static constexpr int kBwdMaxSplit = 8;
 static int bwd_split(int n_jobs, int n_iblocks, int n_dhalf, int min_tiles) {
-  // fill the 148 SMs once; every split costs an extra fp32 partial of the gradient
+  // One CTA per SM (224 KB shared memory): pick the split of the tile range that wastes the least
+  // of the last wave; every extra split costs one more fp32 partial of the gradient, so a larger
+  // split must buy at least 3 % of wave efficiency.
   const int ctas = n_jobs * n_iblocks * n_dhalf;
-  int want = kNumSMsB200 / ctas;
-  if (want < 1) want = 1;
-  if (want > kBwdMaxSplit) want = kBwdMaxSplit;
-  if (want > min_tiles) want = min_tiles;
-  return want;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= kBwdMaxSplit && s <= min_tiles; ++s) {
+    const int total = ctas * s;
+    const int waves = (total + kNumSMsB200 - 1) / kNumSMsB200;
+    const double eff = static_cast<double>(total) / (static_cast<double>(waves) * kNumSMsB200);
+    if (eff > best_eff + 0.03) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  return best;
 }
 
 }  // namespace tcl

@@ -345,12 +345,25 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
 }
 
 static int fwd_split(int n_pairs, int n_iblocks, int n_jtiles) {
-  // enough CTAs for ~4 waves of 148 SMs, at least 2 column tiles per CTA
-  int want = (4 * kNumSMsB200 + n_pairs * n_iblocks - 1) / (n_pairs * n_iblocks);
-  int max_split = n_jtiles / 2 > 0 ? n_jtiles / 2 : 1;
-  if (want > max_split) want = max_split;
-  if (want < 1) want = 1;
-  return want;
+  // One CTA per SM: choose the split of the column sweep that fills whole waves of 148 SMs best.
+  // Small problems (fewer CTAs than SMs) split down to one tile per CTA for latency; large ones keep
+  // >= 8 tiles per CTA so the resident row block (128 KB) is amortised.
+  const int ctas = n_pairs * n_iblocks;
+  const int min_tiles = ctas >= kNumSMsB200 ? 8 : 1;
+  int max_split = n_jtiles / min_tiles > 0 ? n_jtiles / min_tiles : 1;
+  if (max_split > 64) max_split = 64;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_split; ++s) {
+    const int total = ctas * s;
+    const int waves = (total + kNumSMsB200 - 1) / kNumSMsB200;
+    const double eff = static_cast<double>(total) / (static_cast<double>(waves) * kNumSMsB200);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  return best;
 }
 
 }  // namespace tcl
