@@ -17,62 +17,12 @@
 // each CTA owns 256 columns of dim (TMEM: 2 x 128 logit buffers + 256 accumulator).
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2..9 epilogue (thread = TMEM lane = row; two warps
 // per lane quarter split the 128 logit columns).
-#include "host_common.h"
+#include <stdlib.h>
+
+#include "ntxent_bwd.h"
 #include "../../include/tricolo_b200.h"
 
 namespace tcl {
-
-static constexpr int BW_BM = 128, BW_BN = 128, BW_BK = 64;
-static constexpr int BW_KB_BYTES = BW_BM * BW_BK * 2;  // 16 KB
-static constexpr int BW_STAGES = 4;
-static constexpr int BW_EPI_WARPS = 8;  // two per TMEM lane quarter: columns 0-63 / 64-127 of the logit tile
-static constexpr int BW_EPI_THREADS = BW_EPI_WARPS * 32;
-static constexpr int BW_THREADS = 64 + BW_EPI_THREADS;
-static constexpr int BW_DH = 256;  // dim columns per CTA
-
-struct BwdSegDev {
-  CUtensorMap tm_other;    // [n_other, dim]   box {64, 128}
-  CUtensorMap tm_other_t;  // [dim, n_other]   box {64, 128}
-  const float* lse2_self;
-  const float* lse2_other;
-  const float* grad_scale;
-  float w_self, w_other;
-};
-struct BwdJobDev {
-  CUtensorMap tm_self;  // [n_self, dim] box {64, 128}
-  BwdSegDev seg[2];
-  float* gpart;      // [n_split][n_self][dim]
-  float* scale_out;  // device scalar consumed by the normalise backward
-  int n_seg;
-};
-struct BwdParams {
-  BwdJobDev job[TCL_MAX_TENSORS];
-  int n_self, n_other, self_offset, dim;
-  int num_kb, n_jtiles, n_split, n_dhalf;
-  float c1;         // log2(e)/tau
-  float out_scale;  // 1/(tau*n_other)
-  uint32_t idesc;
-};
-
-struct BwdSmem {
-  static constexpr uint32_t x_off = 0;  // num_kb * 16 KB
-  static constexpr uint32_t g_off(int num_kb) { return num_kb * BW_KB_BYTES; }          // 2 * 16 KB
-  static constexpr uint32_t ring_off(int num_kb) { return g_off(num_kb) + 2 * BW_KB_BYTES; }
-  static constexpr uint32_t bar_off(int num_kb) { return ring_off(num_kb) + BW_STAGES * BW_KB_BYTES; }
-  static constexpr uint32_t bj_off(int num_kb) { return bar_off(num_kb) + 256; }  // 2 x 128 floats
-  static constexpr uint32_t total(int num_kb) { return bj_off(num_kb) + 1024 + 1024; }
-};
-
-template <int kOp>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (kOp == TCL_OP_F16) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  } else {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-}
 
 template <int kOp>
 __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_constant__ BwdParams P) {
@@ -408,6 +358,13 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   P.c1 = c1;
   P.out_scale = inv_tau / static_cast<float>(n_other);
   P.idesc = umma_idesc_f16(BW_BM, BW_BN, op_format);
+  P.idesc_n64 = umma_idesc_f16(BW_BM, 64, op_format);
+  // dim > 256: the two dim-half CTAs can run as a 2-CTA cluster that shares the logit recompute through
+  // DSMEM (ntxent_bwd_cluster.cu, 8 instead of 12 B^2 D executed).  Correct, but measured SLOWER on B200
+  // (1.22 ms vs 1.00 ms at B=8192x3): the 16 KB/tile G exchange sits on the per-tile critical path at the
+  // ~20 B/clk DSMEM rate and the N=64 logit MMAs are shared-memory-bound.  Kept behind an opt-in switch.
+  static const bool want_cluster = getenv("TRICOLO_B200_BWD_CLUSTER") != nullptr;
+  const bool use_cluster = P.n_dhalf == 2 && want_cluster;
   float* ws = static_cast<float*>(workspace);
   float* scales = ws;  // 64 floats reserved
   float* gbase = ws + 64;
@@ -421,7 +378,7 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
       TCL_REQUIRE(sg.z_other && sg.z_other_t && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, dim, BW_BN, BW_BK)) return e;
+      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, dim, use_cluster ? 64 : BW_BN, BW_BK)) return e;
       if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, 128, BW_BK)) return e;
       J.seg[s].lse2_self = sg.lse2_self;
       J.seg[s].lse2_other = sg.lse2_other;
@@ -441,7 +398,9 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(n_iblocks, P.n_dhalf * P.n_split, n_jobs);
   prof_begin(TCL_K_NTXENT_BWD, st);
-  if (op_format == TCL_OP_F16) {
+  if (use_cluster) {
+    if (int e = launch_bwd_cluster(P, n_iblocks, n_jobs, op_format, st)) return e;
+  } else if (op_format == TCL_OP_F16) {
     static int set = 0;
     if (set < smem) { TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_kernel<TCL_OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = smem; }
     ntxent_bwd_kernel<TCL_OP_F16><<<grid, BW_THREADS, smem, st>>>(P);

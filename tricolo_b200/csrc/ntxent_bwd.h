@@ -1,0 +1,64 @@
+// Shared declarations of the NT-Xent backward kernels (ntxent_bwd.cu: one CTA per dim half,
+// ntxent_bwd_cluster.cu: the two dim halves as a 2-CTA cluster exchanging G through DSMEM).
+#pragma once
+#include "host_common.h"
+
+namespace tcl {
+
+static constexpr int BW_BM = 128, BW_BN = 128, BW_BK = 64;
+static constexpr int BW_KB_BYTES = BW_BM * BW_BK * 2;  // 16 KB
+static constexpr int BW_STAGES = 4;
+static constexpr int BW_EPI_WARPS = 8;  // two per TMEM lane quarter
+static constexpr int BW_EPI_THREADS = BW_EPI_WARPS * 32;
+static constexpr int BW_THREADS = 64 + BW_EPI_THREADS;
+static constexpr int BW_DH = 256;  // dim columns per CTA
+
+struct BwdSegDev {
+  CUtensorMap tm_other;    // [n_other, dim]   box {64, 128} (cluster kernel: {64, 64})
+  CUtensorMap tm_other_t;  // [dim, n_other]   box {64, 128}
+  const float* lse2_self;
+  const float* lse2_other;
+  const float* grad_scale;
+  float w_self, w_other;
+};
+struct BwdJobDev {
+  CUtensorMap tm_self;  // [n_self, dim] box {64, 128}
+  BwdSegDev seg[2];
+  float* gpart;      // [n_split][n_self][dim]
+  float* scale_out;  // device scalar consumed by the normalise backward
+  int n_seg;
+};
+struct BwdParams {
+  BwdJobDev job[TCL_MAX_TENSORS];
+  int n_self, n_other, self_offset, dim;
+  int num_kb, n_jtiles, n_split, n_dhalf;
+  float c1;         // log2(e)/tau
+  float out_scale;  // 1/(tau*n_other)
+  uint32_t idesc;   // M=128, N=128
+  uint32_t idesc_n64;  // M=128, N=64 (cluster kernel: half logit tile)
+};
+
+struct BwdSmem {
+  static constexpr uint32_t x_off = 0;  // num_kb * 16 KB
+  static constexpr uint32_t g_off(int num_kb) { return num_kb * BW_KB_BYTES; }  // 2 * 16 KB
+  static constexpr uint32_t ring_off(int num_kb) { return g_off(num_kb) + 2 * BW_KB_BYTES; }
+  static constexpr uint32_t bar_off(int num_kb) { return ring_off(num_kb) + BW_STAGES * BW_KB_BYTES; }
+  static constexpr uint32_t bj_off(int num_kb) { return bar_off(num_kb) + 256; }  // 2 x 128 floats
+  static constexpr uint32_t total(int num_kb) { return bj_off(num_kb) + 1024 + 1024; }
+};
+
+template <int kOp>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (kOp == TCL_OP_F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+// ntxent_bwd_cluster.cu
+int launch_bwd_cluster(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
+
+}  // namespace tcl
