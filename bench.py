@@ -309,6 +309,24 @@ def run_ours(args, rank, world, local_rank):
         st = timed(lambda: step(sf), 50, 10)
         small = {"workload": "c2: trimodal B=256 fwd+bwd", "ms_per_step": statistics.median(st),
                  "pairs_per_s": 256 / (statistics.median(st) * 1e-3)}
+        # the same step captured once in a CUDA graph (what a launch-bound training loop would replay)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step(sf)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            for f in sf:
+                f.grad = None
+            with torch.cuda.graph(graph):
+                trimodal_ntxent(sf, TAU, ALPHA, op_format=op).sum().backward()
+            gt = timed(graph.replay, 50, 10)
+            small["graph_ms_per_step"] = statistics.median(gt)
+            small["graph_pairs_per_s"] = 256 / (statistics.median(gt) * 1e-3)
+        except Exception as e:  # report, never hide
+            small["graph_error"] = repr(e)[:200]
 
     # ---------------- secondary: sharded retrieval (configs[4]-shaped)
     retrieval = None

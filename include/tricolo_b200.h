@@ -144,6 +144,31 @@ int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Whole-loss entry points for one GPU: the kernels above sequenced by the library, so that a
+ * training step is two calls.  Replaces TriCoLoNet._calculate_losses (tricolo_net.py:56-65) +
+ * NTXentLoss.forward (nt_xent.py:24-74) and their autograd.
+ *   x[m]           n_tensors inputs [batch, dim] (x_dtype, common row stride)
+ *   pair_row/col   host arrays: pair p is loss(x[pair_row[p]], x[pair_col[p]])  (argument order matters)
+ *   state          caller-allocated, 256-byte aligned, tcl_ntxent_loss_state_bytes(); written by the
+ *                  forward, read by the backward (normalised operands, 1/norms, LSEs)
+ *   workspace      scratch, tcl_ntxent_loss_workspace_bytes(), 256-byte aligned
+ *   loss           [n_pairs] fp32 out
+ *   backward: grad_losses [n_pairs] device fp32 (upstream gradients), need_grad host flags [n_tensors],
+ *             dx[m] device outputs [batch, dim] in x_dtype (ignored where need_grad[m] == 0)
+ * ------------------------------------------------------------------------- */
+size_t tcl_ntxent_loss_state_bytes(int n_tensors, int n_pairs, int64_t batch, int64_t dim);
+size_t tcl_ntxent_loss_workspace_bytes(int n_tensors, int n_pairs, int64_t batch, int64_t dim);
+int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t batch, int64_t dim,
+                        int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                        int op_format, float inv_tau, float alpha, float eps, void* state, size_t state_bytes,
+                        void* workspace, size_t workspace_bytes, float* loss, void* stream);
+int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t batch, int64_t dim,
+                        int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                        int op_format, float inv_tau, float alpha, float eps, const void* state,
+                        const float* grad_losses, const uint8_t* need_grad_host, void* const* dx_host_ptrs,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * K2' — similarity GEMM for retrieval.           replaces eval_retrieval.py:74 (np.dot)
  * S[q, g] = Q[q,:] · G[g,:] (raw dot product, no normalisation), 16-bit operands,
  * fp32 accumulate, fp32 output with leading dimension ld_s (ld_s % 4 == 0).

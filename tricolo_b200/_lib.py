@@ -77,6 +77,12 @@ SIGNATURES = {
     "tcl_ntxent_finalize": (_i, [_i, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_ntxent_bwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
     "tcl_ntxent_bwd": (_i, [_i, C.POINTER(BwdJob), _i64, _i64, _i64, _i64, _i64, _i, _i64, _i, _f, _f, _vp, _sz, _vp]),
+    "tcl_ntxent_loss_state_bytes": (_sz, [_i, _i, _i64, _i64]),
+    "tcl_ntxent_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i64]),
+    "tcl_ntxent_loss_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 _i, _f, _f, _f, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "tcl_ntxent_loss_bwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 _i, _f, _f, _f, _vp, _vp, C.POINTER(C.c_uint8), _pp, _vp, _sz, _vp]),
     "tcl_sim_gemm": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _i64, _vp]),
     "tcl_topk_rank": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_gather_gt_sim": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),

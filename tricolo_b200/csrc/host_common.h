@@ -49,6 +49,10 @@ struct NormBwdJob {
 struct NormBwdParams {
   NormBwdJob job[3];
 };
+// sim_gemm_resident.cu: retrieval GEMM with the query block resident (dim % 64 == 0, dim <= 512)
+int launch_sim_gemm_resident(const void* q, const void* g, int64_t n_q, int64_t n_g, int64_t dim, int op_format,
+                             float* s, int64_t ld_s, cudaStream_t st);
+
 int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim,
                       int64_t x_stride, int n_split, float eps, cudaStream_t st);
 

@@ -1,0 +1,144 @@
+// Single-call forms of the whole loss forward / backward on one GPU: the host side of
+// TriCoLoNet._calculate_losses (tricolo/model/tricolo_net.py:56-65) + NTXentLoss.forward
+// (tricolo/loss/nt_xent.py:24-74) and of their autograd, as two C-ABI entry points.  They only
+// sequence the kernels of l2norm.cu / ntxent_fwd.cu / ntxent_bwd.cu over one caller-allocated
+// "state" buffer (kept between forward and backward) and one scratch workspace, so that a training
+// step costs two library calls instead of seven.
+#include "host_common.h"
+#include "../../include/tricolo_b200.h"
+
+namespace tcl {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// layout of the state buffer (all offsets 256-byte aligned)
+struct LossState {
+  size_t z, inv, row_sum, col_sum, diag2, lse_row, lse_col, parts, total;
+};
+static LossState loss_state_layout(int n_tensors, int n_pairs, int64_t batch, int64_t dim) {
+  LossState L;
+  size_t off = 0;
+  L.z = off;       off = align_up(off + static_cast<size_t>(n_tensors) * batch * dim * 2, 256);
+  L.inv = off;     off = align_up(off + static_cast<size_t>(n_tensors) * batch * 4, 256);
+  L.row_sum = off; off = align_up(off + static_cast<size_t>(n_pairs) * batch * 4, 256);
+  L.col_sum = off; off = align_up(off + static_cast<size_t>(n_pairs) * batch * 4, 256);
+  L.diag2 = off;   off = align_up(off + static_cast<size_t>(n_pairs) * batch * 4, 256);
+  L.lse_row = off; off = align_up(off + static_cast<size_t>(n_pairs) * batch * 4, 256);
+  L.lse_col = off; off = align_up(off + static_cast<size_t>(n_pairs) * batch * 4, 256);
+  L.parts = off;   off = align_up(off + static_cast<size_t>(n_pairs) * 2 * 4, 256);
+  L.total = off;
+  return L;
+}
+
+}  // namespace tcl
+
+using namespace tcl;
+
+extern "C" size_t tcl_ntxent_loss_state_bytes(int n_tensors, int n_pairs, int64_t batch, int64_t dim) {
+  if (n_tensors < 2 || n_tensors > TCL_MAX_TENSORS || n_pairs < 1 || n_pairs > TCL_MAX_PAIRS || batch < 1 || dim < 1) return 0;
+  return loss_state_layout(n_tensors, n_pairs, batch, dim).total;
+}
+
+extern "C" size_t tcl_ntxent_loss_workspace_bytes(int n_tensors, int n_pairs, int64_t batch, int64_t dim) {
+  if (n_tensors < 2 || n_tensors > TCL_MAX_TENSORS || n_pairs < 1 || n_pairs > TCL_MAX_PAIRS || batch < 1 || dim < 1) return 0;
+  const size_t fwd = tcl_ntxent_fwd_workspace_bytes(n_pairs, batch, batch);
+  const int64_t ld_t = (batch + 7) / 8 * 8;
+  const size_t bwd = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256) +
+                     tcl_ntxent_bwd_workspace_bytes(n_tensors, batch, dim);
+  return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                                   int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
+                                   const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
+                                   void* state, size_t state_bytes, void* workspace, size_t workspace_bytes,
+                                   float* loss, void* stream) {
+  TCL_REQUIRE(n_tensors >= 2 && n_tensors <= TCL_MAX_TENSORS && n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG,
+              "loss_fwd: %d tensors / %d pairs", n_tensors, n_pairs);
+  TCL_REQUIRE(x && pair_row && pair_col && state && workspace && loss, TCL_ERR_BAD_ARG, "loss_fwd: null pointer");
+  const LossState L = loss_state_layout(n_tensors, n_pairs, batch, dim);
+  TCL_REQUIRE(state_bytes >= L.total, TCL_ERR_WORKSPACE, "loss_fwd: state buffer too small");
+  TCL_REQUIRE(workspace_bytes >= tcl_ntxent_fwd_workspace_bytes(n_pairs, batch, batch), TCL_ERR_WORKSPACE, "loss_fwd: workspace too small");
+  TCL_REQUIRE(aligned_to(state, 256), TCL_ERR_BAD_ALIGN, "loss_fwd: state buffer must be 256-byte aligned");
+  char* st8 = static_cast<char*>(state);
+  void* z[TCL_MAX_TENSORS];
+  float* inv[TCL_MAX_TENSORS];
+  for (int m = 0; m < n_tensors; ++m) {
+    z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
+    inv[m] = reinterpret_cast<float*>(st8 + L.inv) + static_cast<size_t>(m) * batch;
+  }
+  if (int e = tcl_l2norm_fwd(n_tensors, x, x_dtype, batch, dim, x_row_stride, z, op_format, inv, eps, stream)) return e;
+  const void* zrow[TCL_MAX_PAIRS];
+  const void* zcol[TCL_MAX_PAIRS];
+  for (int p = 0; p < n_pairs; ++p) {
+    TCL_REQUIRE(pair_row[p] >= 0 && pair_row[p] < n_tensors && pair_col[p] >= 0 && pair_col[p] < n_tensors, TCL_ERR_BAD_ARG,
+                "loss_fwd: pair %d out of range", p);
+    zrow[p] = z[pair_row[p]];
+    zcol[p] = z[pair_col[p]];
+  }
+  float* row_sum = reinterpret_cast<float*>(st8 + L.row_sum);
+  float* col_sum = reinterpret_cast<float*>(st8 + L.col_sum);
+  float* diag2 = reinterpret_cast<float*>(st8 + L.diag2);
+  if (int e = tcl_ntxent_fwd(n_pairs, zrow, zcol, batch, batch, dim, 0, op_format, inv_tau, row_sum, col_sum, diag2,
+                             workspace, workspace_bytes, stream))
+    return e;
+  return tcl_ntxent_finalize(n_pairs, batch, batch, 0, inv_tau, alpha, row_sum, col_sum, diag2,
+                             reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
+                             reinterpret_cast<float*>(st8 + L.parts), loss, stream);
+}
+
+extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                                   int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
+                                   const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
+                                   const void* state, const float* grad_losses, const uint8_t* need_grad,
+                                   void* const* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  TCL_REQUIRE(n_tensors >= 2 && n_tensors <= TCL_MAX_TENSORS && n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG,
+              "loss_bwd: %d tensors / %d pairs", n_tensors, n_pairs);
+  TCL_REQUIRE(x && pair_row && pair_col && state && workspace && grad_losses && need_grad && dx, TCL_ERR_BAD_ARG, "loss_bwd: null pointer");
+  TCL_REQUIRE(workspace_bytes >= tcl_ntxent_loss_workspace_bytes(n_tensors, n_pairs, batch, dim), TCL_ERR_WORKSPACE, "loss_bwd: workspace too small");
+  TCL_REQUIRE(aligned_to(workspace, 256), TCL_ERR_BAD_ALIGN, "loss_bwd: workspace must be 256-byte aligned");
+  const LossState L = loss_state_layout(n_tensors, n_pairs, batch, dim);
+  const char* st8 = static_cast<const char*>(state);
+  char* ws8 = static_cast<char*>(workspace);
+  const int64_t ld_t = (batch + 7) / 8 * 8;
+  const void* z[TCL_MAX_TENSORS];
+  void* zt[TCL_MAX_TENSORS];
+  for (int m = 0; m < n_tensors; ++m) {
+    z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
+    zt[m] = ws8 + static_cast<size_t>(m) * dim * ld_t * 2;
+  }
+  if (int e = tcl_transpose_16bit(n_tensors, z, batch, dim, zt, ld_t, stream)) return e;
+  const size_t zt_bytes = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256);
+  const float* lse_row = reinterpret_cast<const float*>(st8 + L.lse_row);
+  const float* lse_col = reinterpret_cast<const float*>(st8 + L.lse_col);
+  tcl_bwd_job jobs[TCL_MAX_TENSORS];
+  memset(jobs, 0, sizeof(jobs));
+  int n_jobs = 0;
+  for (int m = 0; m < n_tensors; ++m) {
+    if (!need_grad[m]) continue;
+    tcl_bwd_job& J = jobs[n_jobs];
+    J.z_self = z[m];
+    J.x_self = x[m];
+    J.inv_norm = reinterpret_cast<const float*>(st8 + L.inv) + static_cast<size_t>(m) * batch;
+    J.dx = dx[m];
+    TCL_REQUIRE(J.dx != nullptr, TCL_ERR_BAD_ARG, "loss_bwd: dx[%d] is null", m);
+    for (int p = 0; p < n_pairs; ++p) {
+      if (pair_row[p] != m && pair_col[p] != m) continue;
+      TCL_REQUIRE(J.n_segments < 2, TCL_ERR_BAD_ARG, "loss_bwd: tensor %d takes part in more than two pairs", m);
+      tcl_bwd_segment& S = J.seg[J.n_segments++];
+      const bool is_row = pair_row[p] == m;  // self is the pair's first argument: row softmax weight alpha
+      const int o = is_row ? pair_col[p] : pair_row[p];
+      S.z_other = z[o];
+      S.z_other_t = zt[o];
+      S.lse2_self = (is_row ? lse_row : lse_col) + static_cast<size_t>(p) * batch;
+      S.lse2_other = (is_row ? lse_col : lse_row) + static_cast<size_t>(p) * batch;
+      S.grad_scale = grad_losses + p;
+      S.w_self = is_row ? alpha : 1.f - alpha;
+      S.w_other = is_row ? 1.f - alpha : alpha;
+    }
+    if (J.n_segments > 0) ++n_jobs;
+  }
+  if (n_jobs == 0) return TCL_OK;
+  return tcl_ntxent_bwd(n_jobs, jobs, batch, batch, dim, 0, ld_t, x_dtype, x_row_stride, op_format, inv_tau, eps,
+                        ws8 + zt_bytes, workspace_bytes - zt_bytes, stream);
+}

@@ -176,6 +176,10 @@ extern "C" int tcl_sim_gemm(const void* q, const void* g, int64_t n_q, int64_t n
   TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
   if (int e = require_sm100()) return e;
   if (n_q == 0) return TCL_OK;
+  // main form: query block resident in shared memory (sim_gemm_resident.cu); the tile-per-CTA
+  // kernel below covers dims the resident layout cannot hold.
+  if (dim % 64 == 0 && dim <= 512)
+    return launch_sim_gemm_resident(q, g, n_q, n_g, dim, op_format, s, ld_s, static_cast<cudaStream_t>(stream));
   CUtensorMap tm_a, tm_b;
   if (int e = make_tmap_2d_16bit(&tm_a, q, n_q, dim, dim, SG_BM, SG_BK)) return e;
   if (int e = make_tmap_2d_16bit(&tm_b, g, n_g, dim, dim, SG_BN, SG_BK)) return e;

@@ -14,9 +14,14 @@ from __future__ import annotations
 from itertools import combinations
 from typing import Dict, List, Sequence, Tuple
 
+import ctypes as C
+
 import torch
 
+from .. import _lib as L
 from .. import ops
+
+LIB = L.LIB
 
 # fp16 operands by default: same tcgen05 kind::f16 throughput as bf16, 3 more
 # mantissa bits; normalised embeddings lie in [-1, 1] so range is a non-issue.
@@ -28,51 +33,64 @@ def _pairs(n: int) -> List[Tuple[int, int]]:
     return list(combinations(range(n), 2))
 
 
+def _prep(feats):
+    """Row-major, 16-byte aligned rows with one common row stride (what the C ABI takes)."""
+    out = []
+    for f in feats:
+        if f.stride(1) != 1 or (f.stride(0) * f.element_size()) % 16 != 0 or f.data_ptr() % 16 != 0:
+            f = f.contiguous()
+        out.append(f)
+    if any(f.stride(0) != out[0].stride(0) for f in out):
+        out = [f.contiguous() for f in out]
+    return out
+
+
 class _FusedNTXent(torch.autograd.Function):
-    """losses[p] for every pair (a, b), a < b, of the given feature matrices."""
+    """losses[p] for every pair (a, b), a < b, of the given feature matrices.
+
+    Two library calls per step: tcl_ntxent_loss_fwd (K1 -> K2 -> reduce -> finalise) and
+    tcl_ntxent_loss_bwd (transpose -> K3 -> normalise backward); see include/tricolo_b200.h."""
 
     @staticmethod
     def forward(ctx, temperature: float, alpha: float, op_format: int, pairs, *feats: torch.Tensor):
+        dev = L.require_cuda(*feats)
+        xs = _prep([f.detach() for f in feats])
+        n, p = len(xs), len(pairs)
+        b, d = xs[0].shape
         inv_tau = 1.0 / float(temperature)
-        feats = [f.detach() for f in feats]
-        zs, invs, xs = ops.l2norm_fwd(feats, op_format)
-        zrows = [zs[a] for a, _ in pairs]
-        zcols = [zs[b] for _, b in pairs]
-        row_sum, col_sum, diag2 = ops.ntxent_fwd(zrows, zcols, 0, inv_tau, op_format)
-        lse2_row, lse2_col, _parts, loss = ops.ntxent_finalize(row_sum, col_sum, diag2, 0, inv_tau, alpha)
-        ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs))
-        ctx.save_for_backward(lse2_row, lse2_col, *xs, *zs, *invs)
+        pr = (C.c_int32 * p)(*[a for a, _ in pairs])
+        pc = (C.c_int32 * p)(*[c for _, c in pairs])
+        state_bytes = LIB.tcl_ntxent_loss_state_bytes(n, p, b, d)
+        ws_bytes = LIB.tcl_ntxent_loss_workspace_bytes(n, p, b, d)
+        state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        loss = torch.empty((p,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(LIB.tcl_ntxent_loss_fwd(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr, pc,
+                                            op_format, inv_tau, alpha, ops.EPS, state.data_ptr(), state_bytes,
+                                            ws.data_ptr(), ws_bytes, loss.data_ptr(), L.stream_ptr(dev)))
+        ctx.cfg = (inv_tau, float(alpha), op_format, pr, pc, ws_bytes)
+        ctx.save_for_backward(state, *xs)
         return loss
 
     @staticmethod
     def backward(ctx, grad_losses: torch.Tensor):
-        inv_tau, alpha, op_format, pairs = ctx.cfg
-        saved = ctx.saved_tensors
-        lse2_row, lse2_col = saved[0], saved[1]
-        n = (len(saved) - 2) // 3
-        xs, zs, invs = saved[2:2 + n], saved[2 + n:2 + 2 * n], saved[2 + 2 * n:]
-        grad_losses = grad_losses.to(torch.float32).contiguous()
-        zts, ld_t = ops.transpose_16bit(zs)
-        jobs, owners = [], []
-        for m in range(n):
-            if not ctx.needs_input_grad[4 + m]:
-                continue
-            segs = []
-            for p, (a, b) in enumerate(pairs):
-                if m == a:  # self is the row side: row softmax weight alpha (nt_xent.py:71,74)
-                    segs.append(ops.BwdSegmentSpec(zs[b], zts[b], lse2_row[p], lse2_col[p], grad_losses[p:p + 1],
-                                                   alpha, 1.0 - alpha))
-                elif m == b:  # self is the column side (nt_xent.py:72,74)
-                    segs.append(ops.BwdSegmentSpec(zs[a], zts[a], lse2_col[p], lse2_row[p], grad_losses[p:p + 1],
-                                                   1.0 - alpha, alpha))
-            if segs:
-                jobs.append(ops.BwdJobSpec(zs[m], xs[m], invs[m], segs))
-                owners.append(m)
-        grads: List = [None] * n
-        if jobs:
-            dxs = ops.ntxent_bwd(jobs, zs[0].shape[0], 0, ld_t, inv_tau, op_format)
-            for m, dx in zip(owners, dxs):
-                grads[m] = dx
+        inv_tau, alpha, op_format, pr, pc, ws_bytes = ctx.cfg
+        state, *xs = ctx.saved_tensors
+        n, p = len(xs), len(pr)
+        b, d = xs[0].shape
+        dev = xs[0].device
+        if grad_losses.dtype != torch.float32 or not grad_losses.is_contiguous():
+            grad_losses = grad_losses.to(torch.float32).contiguous()
+        need = (C.c_uint8 * n)(*[1 if ctx.needs_input_grad[4 + m] else 0 for m in range(n)])
+        dx_all = torch.empty((n, b, d), dtype=xs[0].dtype, device=dev)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        dxs = (C.c_void_p * n)(*[dx_all.data_ptr() + m * b * d * dx_all.element_size() for m in range(n)])
+        with torch.cuda.device(dev):
+            L.check(LIB.tcl_ntxent_loss_bwd(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr, pc,
+                                            op_format, inv_tau, alpha, ops.EPS, state.data_ptr(), grad_losses.data_ptr(),
+                                            need, dxs, ws.data_ptr(), ws_bytes, L.stream_ptr(dev)))
+        grads = [dx_all[m] if need[m] else None for m in range(n)]
         return (None, None, None, None, *grads)
 
 
