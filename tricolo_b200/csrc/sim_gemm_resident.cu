@@ -4,9 +4,16 @@
 // output, so re-streaming both operands per tile is L2-bound.  Here a CTA keeps its 128 query
 // rows (dim/64 swizzled 16 KB K-blocks) resident and sweeps a range of 128-row gallery tiles
 // that stream through a TMA ring; two TMEM accumulators alternate so that the epilogue of tile t
-// (TMEM -> registers -> full-sector global stores) overlaps
-// the MMAs of tile t+1.  Grid order: query block fastest, so the CTAs running at the same time
-// sweep the same gallery range and every gallery tile is fetched from HBM about once.
+// (TMEM -> registers -> full-sector streaming stores) overlaps the MMAs of tile t+1.
+//
+// Measured on B200 the single-CTA form is bound by L2 throughput (12.8 GB of gallery reads + 6.5 GB
+// of result writes per 8192 x 200k block, ~11 TB/s).  Two CTAs with adjacent query blocks therefore
+// form a cluster: each loads HALF of every gallery K-block (64 rows) and TMA-multicasts it into both
+// CTAs' rings, halving the L2 read traffic.  A ring slot is released by tcgen05.commit multicast to
+// both CTAs (empty barrier count 2), since each producer writes into both shared memories.
+//
+// Grid order: query block fastest, so the CTAs running at the same time sweep the same gallery range
+// and every gallery tile is fetched from HBM about once.
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2..9 epilogue (two per TMEM lane quarter, 64 columns each).
 #include "host_common.h"
 #include "../../include/tricolo_b200.h"
@@ -21,7 +28,7 @@ static constexpr int SR_THREADS = 64 + SR_EPI_WARPS * 32;
 
 struct SimResParams {
   CUtensorMap tm_q;  // [n_q, dim] box {64, 128}
-  CUtensorMap tm_g;  // [n_g, dim] box {64, 128}
+  CUtensorMap tm_g;  // [n_g, dim] box {64, 128 / cluster size}
   float* s;
   int64_t ld;
   int n_q, n_g, num_kb, n_gtiles, n_split;
@@ -34,6 +41,7 @@ struct SimResSmem {
   static constexpr uint32_t total(int num_kb) { return bar_off(num_kb) + 256 + 1024; }
 };
 
+template <int kCluster>
 __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const __grid_constant__ SimResParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -53,18 +61,22 @@ __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const 
       reinterpret_cast<volatile uint32_t*>(base_ptr + SimResSmem::bar_off(num_kb) + 8u * (2 * SR_STAGES + 5));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
   const int m0 = blockIdx.x * SR_BM;
   const int sp = blockIdx.y;
   const int t_begin = static_cast<int>((static_cast<int64_t>(P.n_gtiles) * sp) / P.n_split);
   const int t_end = static_cast<int>((static_cast<int64_t>(P.n_gtiles) * (sp + 1)) / P.n_split);
-  const int n_tiles = t_end - t_begin;
+  const int n_tiles = t_end - t_begin;  // identical for all CTAs of a cluster (same split)
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCluster) - 1u);
+  constexpr int kSliceRows = SR_BN / kCluster;  // gallery rows this CTA fetches per K-block
+  constexpr int kSliceBytes = SR_KB_BYTES / kCluster;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&P.tm_q);
     tma_prefetch_desc(&P.tm_g);
     for (int s = 0; s < SR_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kCluster);  // one tcgen05.commit per CTA of the cluster
     }
     mbar_init(q_full_bar, 1);
     for (int b = 0; b < 2; ++b) {
@@ -79,6 +91,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // peers' barriers exist before any multicast lands
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
 
@@ -93,9 +106,16 @@ __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const 
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % SR_STAGES;
           const uint32_t ph = (it / SR_STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(s), SR_KB_BYTES);
-          tma_load_2d(ring + s * SR_KB_BYTES, &P.tm_g, full_bar(s), kb * SR_BK, n0);
+          if (kCluster > 1) {
+            mbar_wait_cluster(empty_bar(s), ph ^ 1);          // every CTA of the cluster has consumed the slot
+            mbar_arrive_expect_tx(full_bar(s), SR_KB_BYTES);  // own slice + the peers' multicast slices
+            tma_load_2d_multicast(ring + s * SR_KB_BYTES + crank * kSliceBytes, &P.tm_g, full_bar(s), kb * SR_BK,
+                                  n0 + static_cast<int>(crank) * kSliceRows, kMask);
+          } else {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_arrive_expect_tx(full_bar(s), SR_KB_BYTES);
+            tma_load_2d(ring + s * SR_KB_BYTES, &P.tm_g, full_bar(s), kb * SR_BK, n0);
+          }
         }
       }
     }
@@ -117,7 +137,10 @@ __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const 
 #pragma unroll
           for (int kk = 0; kk < SR_BK / 16; ++kk)
             tc_mma_f16(tmem + b * SR_BN, ad + 2 * kk, bd + 2 * kk, P.idesc, (kb | kk) != 0);
-          tc_commit(empty_bar(s));
+          if (kCluster > 1)
+            tc_commit_multicast(empty_bar(s), kMask);
+          else
+            tc_commit(empty_bar(s));
         }
         tc_commit(tmem_full_bar(b));
       }
@@ -170,7 +193,8 @@ __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const 
 #pragma unroll
               for (int g = 0; g < 4; ++g)
                 __stcs(reinterpret_cast<float2*>(dst + cl * 32 + g * 8),
-                       make_float2(__uint_as_float(v[h][cl][4 * g + 2 * rr]), __uint_as_float(v[h][cl][4 * g + 2 * rr + 1])));
+                       make_float2(__uint_as_float(v[h][cl][4 * g + 2 * rr]),
+                                   __uint_as_float(v[h][cl][4 * g + 2 * rr + 1])));
           }
       } else {
 #pragma unroll
@@ -198,6 +222,7 @@ __global__ void __launch_bounds__(SR_THREADS, 1) sim_gemm_resident_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
@@ -224,29 +249,51 @@ int launch_sim_gemm_resident(const void* q, const void* g, int64_t n_q, int64_t 
                              float* s, int64_t ld_s, cudaStream_t st) {
   SimResParams P;
   memset(&P, 0, sizeof(P));
+  int n_mblocks = static_cast<int>((n_q + SR_BM - 1) / SR_BM);
+  // two query blocks per cluster share the gallery stream; a single block runs the plain kernel
+  const bool cluster = n_mblocks >= 2;
+  if (cluster) n_mblocks = (n_mblocks + 1) / 2 * 2;  // padded block: rows >= n_q, loads zero-filled, stores masked
   if (int e = make_tmap_2d_16bit(&P.tm_q, q, n_q, dim, dim, SR_BM, SR_BK)) return e;
-  if (int e = make_tmap_2d_16bit(&P.tm_g, g, n_g, dim, dim, SR_BN, SR_BK)) return e;
+  if (int e = make_tmap_2d_16bit(&P.tm_g, g, n_g, dim, dim, cluster ? SR_BN / 2 : SR_BN, SR_BK)) return e;
   P.s = s;
   P.ld = ld_s;
   P.n_q = static_cast<int>(n_q);
   P.n_g = static_cast<int>(n_g);
   P.num_kb = static_cast<int>(dim / 64);
   P.n_gtiles = static_cast<int>((n_g + SR_BN - 1) / SR_BN);
-  const int n_mblocks = static_cast<int>((n_q + SR_BM - 1) / SR_BM);
   P.n_split = sim_split(n_mblocks, P.n_gtiles);
   P.idesc = umma_idesc_f16(SR_BM, SR_BN, op_format);
   TCL_REQUIRE(P.n_split <= 65535, TCL_ERR_BAD_SHAPE, "sim_gemm: split out of range");
   const int smem = static_cast<int>(SimResSmem::total(P.num_kb));
-  static int set = 0;
-  if (set < smem) {
-    TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_gemm_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = smem;
+  ProfScope prof(TCL_K_SIM_GEMM, st);
+  if (cluster) {
+    static int set = 0;
+    if (set < smem) {
+      TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_gemm_resident_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      set = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_mblocks, P.n_split);
+    cfg.blockDim = dim3(SR_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sim_gemm_resident_kernel<2>, P));
+  } else {
+    static int set = 0;
+    if (set < smem) {
+      TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_gemm_resident_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      set = smem;
+    }
+    sim_gemm_resident_kernel<1><<<dim3(n_mblocks, P.n_split), SR_THREADS, smem, st>>>(P);
+    TCL_CHECK_CUDA(cudaGetLastError());
   }
-  {
-    ProfScope prof(TCL_K_SIM_GEMM, st);
-    sim_gemm_resident_kernel<<<dim3(n_mblocks, P.n_split), SR_THREADS, smem, st>>>(P);
-  }
-  TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
 
