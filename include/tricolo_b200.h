@@ -204,6 +204,25 @@ int tcl_topk_merge(const float* cand_val, const int32_t* cand_idx, int n_shards,
                    int k, float* topk_val, int32_t* topk_idx, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * K2'+K4 fused — retrieval without materialising S (dim % 64 == 0, dim <= 512, k <= 16).
+ * Same results as tcl_sim_gemm + tcl_topk_rank (same order, same rank definition), bit for bit:
+ * the per-query ground-truth similarity gt_sim[q] must be the number the tensor core produces for
+ * (q, label[q]); tcl_gt_sim_mma computes it with the identical MMA sequence on gathered gallery rows
+ * (0 where the label is outside [idx_base, idx_base+n_g): all-reduce(sum) over gallery shards).
+ *   tcl_gt_sim_mma      workspace >= n_q*dim*2 bytes (gathered rows), 16-byte aligned
+ *   tcl_sim_topk_fused  workspace tcl_sim_topk_fused_workspace_bytes() (only used when the gallery sweep
+ *                       is split over several CTAs per query block, i.e. few queries)
+ * ------------------------------------------------------------------------- */
+int tcl_gt_sim_mma(const void* q, const void* g, int64_t n_q, int64_t n_g, int64_t dim, int op_format,
+                   const int64_t* labels, int64_t idx_base, float* gt_sim, void* workspace,
+                   size_t workspace_bytes, void* stream);
+size_t tcl_sim_topk_fused_workspace_bytes(int64_t n_q, int64_t n_g, int k);
+int tcl_sim_topk_fused(const void* q, const void* g, int64_t n_q, int64_t n_g, int64_t dim, int op_format,
+                       int k, const int64_t* labels, int64_t idx_base, const float* gt_sim,
+                       float* topk_val, int32_t* topk_idx, int32_t* n_before, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Measurement hooks (bench.py).  tcl_launch_count: kernels launched by this library
  * since load.  With profiling enabled every kernel launch is bracketed by CUDA events
  * on its launch stream; tcl_profile_read synchronises on those events and returns the
@@ -222,7 +241,8 @@ enum {
   TCL_K_TOPK_RANK = 9,
   TCL_K_GATHER_GT = 10,
   TCL_K_TOPK_MERGE = 11,
-  TCL_K_COUNT = 12
+  TCL_K_SIM_TOPK_FUSED = 12,
+  TCL_K_COUNT = 13
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);

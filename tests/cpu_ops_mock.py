@@ -137,3 +137,17 @@ def topk_merge(cand_val, cand_idx):
     order = np.lexsort((i, -v), axis=1)[:, :k]
     return (torch.from_numpy(np.take_along_axis(v, order, 1)).float(),
             torch.from_numpy(np.take_along_axis(i, order, 1)).to(torch.int32))
+
+
+def gt_sim_mma(q16, g16, labels, idx_base=0):
+    loc = labels - idx_base
+    ok = (loc >= 0) & (loc < g16.shape[0])
+    rows = g16[loc.clamp(0, g16.shape[0] - 1)]
+    v = (q16.double() * rows.double()).sum(1).float()
+    return torch.where(ok, v, torch.zeros_like(v))
+
+
+def sim_topk_fused(q16, g16, k, labels, gt_sim, idx_base=0):
+    s, n_g = sim_gemm(q16, g16)
+    val, idx, _, nb = topk_rank(s, n_g, k, labels, idx_base, gt_sim)
+    return val, idx, nb

@@ -360,3 +360,52 @@ def test_large_retrieval_properties(tb):
         cv.append(v); ci.append(i); nb = nb + b
     mv, mi = ops.topk_merge(torch.stack(cv), torch.stack(ci))
     assert torch.equal(mi, idx) and torch.equal(mv, val) and torch.equal(nb + 1, rank)
+
+
+@pytest.mark.parametrize("q,g,d,k,ties", [
+    (1000, 300, 128, 5, False), (7424, 1486, 512, 5, False), (777, 1486, 512, 5, True), (300, 4099, 64, 16, False),
+    (50, 3, 64, 5, True), (129, 257, 192, 3, True), (20000, 25000, 512, 5, False),
+])
+def test_fused_retrieval_matches_unfused_bit_exact(tb, q, g, d, k, ties):
+    """K2'+K4 fused (similarities never leave the SM) against GEMM -> HBM -> top-k: identical values, indices
+    and ranks, including the ground-truth similarity produced by the diagonal-MMA pre-pass."""
+    ops = tb.ops
+    gen = torch.Generator().manual_seed(q * 7 + g)
+    if ties:
+        text = torch.randint(-2, 3, (q, d), generator=gen).float()
+        gal = torch.randint(-2, 3, (g, d), generator=gen).float()
+    else:
+        text = torch.randn(q, d, generator=gen)
+        gal = torch.randn(g, d, generator=gen)
+    lab = torch.randint(0, g, (q,), generator=gen).cuda()
+    t16, g16 = text.cuda().bfloat16(), gal.cuda().bfloat16()
+    sim, n_g = ops.sim_gemm(t16, g16)
+    gt_ref = torch.gather(sim[:, :n_g], 1, lab[:, None])[:, 0]
+    gt = ops.gt_sim_mma(t16, g16, lab)
+    assert torch.equal(gt, gt_ref)  # same MMA sequence -> same bits
+    a = tb.eval.retrieve(t16, g16, lab, k, fused=False)
+    b = tb.eval.retrieve(t16, g16, lab, k, fused=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    if ties:  # exact arithmetic: also equal to the oracle
+        rv, ri, rr = RO.topk_and_rank((text.double() @ gal.double().t()).numpy(), lab.cpu().numpy(), min(k, g))
+        assert np.array_equal(b[1].cpu().numpy()[:, : min(k, g)], ri) and np.array_equal(b[2].cpu().numpy(), rr)
+
+
+def test_fused_sharded_matches_unsharded(tb):
+    ops = tb.ops
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    G, Q, D = 25000, 4096, 512
+    gal = torch.randn(G, D, generator=gen, device="cuda").bfloat16()
+    text = torch.randn(Q, D, generator=gen, device="cuda").bfloat16()
+    lab = torch.randint(0, G, (Q,), generator=gen, device="cuda")
+    val, idx, rank = tb.eval.retrieve(text, gal, lab, 5, fused=True)
+    bounds = [0, 8000, 17000, G]
+    shards = [gal[lo:hi].contiguous() for lo, hi in zip(bounds[:-1], bounds[1:])]
+    gt = sum(ops.gt_sim_mma(text, s, lab, lo) for s, lo in zip(shards, bounds[:-1]))
+    cv, ci, nb = [], [], 0
+    for s, lo in zip(shards, bounds[:-1]):
+        v, i, b = ops.sim_topk_fused(text, s, 5, lab, gt, lo)
+        cv.append(v); ci.append(i); nb = nb + b
+    mv, mi = ops.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, idx) and torch.equal(mv, val) and torch.equal(nb + 1, rank)

@@ -119,29 +119,40 @@ def global_calculate_losses(output_dict, loss_prefix, temperature, alpha, group=
 
 
 def sharded_retrieve(text: torch.Tensor, gallery_shard: torch.Tensor, labels: torch.Tensor, idx_base: int,
-                     k: int = 5, group=None, block_queries: int = 8192, operand_format: int = ops.BF16):
+                     k: int = 5, group=None, block_queries: int = None, operand_format: int = ops.BF16,
+                     fused: bool = None):
     """Gallery-sharded retrieval. text [Q,D] (all queries, replicated), gallery_shard [G_loc,D] with global
     index base idx_base, labels [Q] global gallery indices. Returns (topk_val, topk_idx, rank) — identical on
-    every rank."""
+    every rank.  fused: see tricolo_b200.evaluation.retrieve."""
     world, _ = _world(group)
     dt = ops.L.op_torch_dtype(operand_format)
     g16 = gallery_shard if gallery_shard.dtype == dt else ops.cast_16bit(gallery_shard, operand_format)
-    n_q, n_g = text.shape[0], gallery_shard.shape[0]
+    n_q, n_g, dim = text.shape[0], gallery_shard.shape[0], text.shape[1]
     dev = text.device
+    if fused is None:
+        fused = dim % 64 == 0 and 64 <= dim <= 512 and k <= 16
+    if block_queries is None:
+        block_queries = 148 * 128 * 8 if fused else 8192
     labels = labels.to(torch.int64)
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     nb = torch.empty((n_q,), dtype=torch.int32, device=dev)
-    ld = (n_g + 31) // 32 * 32
-    buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
+    if not fused:
+        ld = (n_g + 31) // 32 * 32
+        buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
     for s in range(0, n_q, block_queries):
         e = min(s + block_queries, n_q)
         tq = text[s:e]
         q16 = tq if tq.dtype == dt else ops.cast_16bit(tq, operand_format)
-        sim, _ = ops.sim_gemm(q16, g16, out=buf[: e - s])
-        gt = ops.gather_gt_sim(sim, n_g, labels[s:e], idx_base)
-        dist.all_reduce(gt, group=group)  # owner shard contributes, the others add 0
-        v, i, _, b = ops.topk_rank(sim, n_g, k, labels[s:e], idx_base, gt)
+        if fused:
+            gt = ops.gt_sim_mma(q16, g16, labels[s:e], idx_base)
+            dist.all_reduce(gt, group=group)  # owner shard contributes, the others add 0
+            v, i, b = ops.sim_topk_fused(q16, g16, k, labels[s:e], gt, idx_base)
+        else:
+            sim, _ = ops.sim_gemm(q16, g16, out=buf[: e - s])
+            gt = ops.gather_gt_sim(sim, n_g, labels[s:e], idx_base)
+            dist.all_reduce(gt, group=group)
+            v, i, _, b = ops.topk_rank(sim, n_g, k, labels[s:e], idx_base, gt)
         val[s:e], idx[s:e], nb[s:e] = v, i, b
     cand_v = torch.empty((world * n_q, k), dtype=torch.float32, device=dev)
     cand_i = torch.empty((world * n_q, k), dtype=torch.int32, device=dev)

@@ -200,27 +200,50 @@ def _print_results(pr_at_k):
           f'{round(pr_at_k["ndcg"][4] * 100, 2)} {round(pr_at_k["mrr"] * 100, 2)}')
 
 
+FUSED_BLOCK_QUERIES = 148 * 128 * 8  # fused path: only bounds the gathered-row scratch (1 KB per query)
+
+
+def _fusable(dim: int, k: int) -> bool:
+    return dim % 64 == 0 and 64 <= dim <= 512 and 1 <= k <= 16
+
+
 def retrieve(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k: int = 5,
-             block_queries: int = BLOCK_QUERIES, operand_format: int = OPERAND_FORMAT):
+             block_queries: int = None, operand_format: int = OPERAND_FORMAT, fused: bool = None):
     """Tensor-in fast entry: device-resident text [Q,D], gallery [G,D], labels [Q] (int64 gallery index).
 
-    Returns (topk_val [Q,k] f32, topk_idx [Q,k] i32, rank [Q] i32) on the device. Queries are processed
-    in blocks so the fp32 similarity buffer stays bounded (block_queries x G x 4 bytes)."""
-    g16 = gallery if gallery.dtype == ops.L.op_torch_dtype(operand_format) else ops.cast_16bit(gallery, operand_format)
-    n_q, n_g = text.shape[0], gallery.shape[0]
+    Returns (topk_val [Q,k] f32, topk_idx [Q,k] i32, rank [Q] i32) on the device.
+
+    fused=True  (default when dim % 64 == 0 and dim <= 512): K2'+K4 fused kernel, the similarities stay in
+                TMEM/registers (tensor-bound).
+    fused=False : similarity GEMM (K2') into an fp32 block of block_queries x G, then the top-k/rank kernel
+                (K4, HBM-bound).  Both give identical results bit for bit."""
+    dt = ops.L.op_torch_dtype(operand_format)
+    g16 = gallery if gallery.dtype == dt else ops.cast_16bit(gallery, operand_format)
+    n_q, n_g, dim = text.shape[0], gallery.shape[0], text.shape[1]
     dev = text.device
+    if fused is None:
+        fused = _fusable(dim, k)
+    elif fused and not _fusable(dim, k):
+        raise ValueError(f"fused retrieval needs dim % 64 == 0, dim <= 512, k <= 16 (got dim={dim}, k={k})")
+    if block_queries is None:
+        block_queries = FUSED_BLOCK_QUERIES if fused else BLOCK_QUERIES
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     rank = torch.empty((n_q,), dtype=torch.int32, device=dev)
-    ld = (n_g + 31) // 32 * 32
-    buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
     labels = labels.to(torch.int64)
+    if not fused:
+        ld = (n_g + 31) // 32 * 32
+        buf = torch.empty((min(block_queries, n_q), ld), dtype=torch.float32, device=dev)
     for s in range(0, n_q, block_queries):
         e = min(s + block_queries, n_q)
         tq = text[s:e]
-        q16 = tq if tq.dtype == g16.dtype else ops.cast_16bit(tq, operand_format)
-        sim, _ = ops.sim_gemm(q16, g16, out=buf[: e - s])
-        v, i, _, nb = ops.topk_rank(sim, n_g, k, labels[s:e])
+        q16 = tq if tq.dtype == dt else ops.cast_16bit(tq, operand_format)
+        if fused:
+            gt = ops.gt_sim_mma(q16, g16, labels[s:e])
+            v, i, nb = ops.sim_topk_fused(q16, g16, k, labels[s:e], gt)
+        else:
+            sim, _ = ops.sim_gemm(q16, g16, out=buf[: e - s])
+            v, i, _, nb = ops.topk_rank(sim, n_g, k, labels[s:e])
         val[s:e], idx[s:e] = v, i
         rank[s:e] = nb + 1
     return val, idx, rank

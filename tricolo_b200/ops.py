@@ -207,6 +207,41 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
     return val, idx
 
 
+def gt_sim_mma(q16: torch.Tensor, g16: torch.Tensor, labels: torch.Tensor, idx_base: int = 0) -> torch.Tensor:
+    """Ground-truth similarity q . g[label - idx_base] produced by the same MMA sequence as the GEMM
+    (0 where the label is outside this gallery shard)."""
+    dev = L.require_cuda(q16, g16, labels)
+    n_q, dim = q16.shape
+    op = F16 if q16.dtype == torch.float16 else BF16
+    out = torch.empty((n_q,), dtype=torch.float32, device=dev)
+    ws = torch.empty((max(n_q * dim * 2, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_gt_sim_mma(L.ptr(q16), L.ptr(g16), n_q, g16.shape[0], dim, op, L.ptr(labels), idx_base,
+                                   L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    return out
+
+
+def sim_topk_fused(q16: torch.Tensor, g16: torch.Tensor, k: int, labels: torch.Tensor, gt_sim: torch.Tensor,
+                   idx_base: int = 0):
+    """K2'+K4 fused. Returns (topk_val [Q,k] f32, topk_idx [Q,k] i32, n_before [Q] i32)."""
+    dev = L.require_cuda(q16, g16, labels, gt_sim)
+    if q16.dtype != g16.dtype or q16.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("sim_topk_fused: operands must both be float16 or both bfloat16")
+    n_q, dim = q16.shape
+    n_g = g16.shape[0]
+    op = F16 if q16.dtype == torch.float16 else BF16
+    val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+    nb = torch.empty((n_q,), dtype=torch.int32, device=dev)
+    ws_bytes = LIB.tcl_sim_topk_fused_workspace_bytes(n_q, n_g, k)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_sim_topk_fused(L.ptr(q16), L.ptr(g16), n_q, n_g, dim, op, k, L.ptr(labels), idx_base,
+                                       L.ptr(gt_sim), L.ptr(val), L.ptr(idx), L.ptr(nb), L.ptr(ws), ws_bytes,
+                                       L.stream_ptr(dev)))
+    return val, idx, nb
+
+
 def debug_tmem_probe(device="cuda") -> torch.Tensor:
     out = torch.zeros((4, 2, 32, 16), dtype=torch.int32, device=device)
     with torch.cuda.device(out.device):
