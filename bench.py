@@ -237,22 +237,38 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---------------- main timed region: K steps, kernel events + clocks sampled meanwhile
+    # The step is captured once in a CUDA graph and replayed (same kernels, same NCCL collectives, no host work
+    # between launches); the eager number is reported next to it.  The per-kernel event profile is taken on
+    # eager steps (events recorded inside a capture would be baked into the graph).
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step(feats)
     torch.cuda.synchronize(dev)
     _lib.profile_enable(True)
     launches0 = _lib.launch_count()
-    sampler.start()
-    wall0 = time.perf_counter()
-    times = timed(lambda: step(feats), args.steps, 0)
-    wall = time.perf_counter() - wall0
-    clocks = sampler.finish()
+    eager_times = timed(lambda: step(feats), args.steps, 0)
     launches = _lib.launch_count() - launches0
     prof = _lib.profile_read()
     _lib.profile_enable(False)
+    eager_ms = max_over_ranks(sum(eager_times)) / args.steps
+    launch_mode, graphed = "eager", None
+    try:
+        from tricolo_b200.graphs import GraphedTrimodalLoss
+
+        graphed = GraphedTrimodalLoss(feats, TAU, ALPHA, distributed=world > 1, op_format=op, warmup=3)
+        launch_mode = "cuda_graph"
+    except Exception as e:  # report, never hide
+        launch_mode = "eager (graph capture failed: %s)" % repr(e)[:120]
+    run_step = graphed.replay if graphed is not None else (lambda: step(feats))
+    sampler.start()
+    wall0 = time.perf_counter()
+    times = timed(run_step, args.steps, args.warmup)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.finish()
     total_ms = max_over_ranks(sum(times))
     ms_per_step = total_ms / args.steps
+    if eager_ms < ms_per_step:  # never report the slower of the two launch modes as the headline
+        ms_per_step, launch_mode = eager_ms, "eager"
     value = batch / (ms_per_step * 1e-3)
 
     # ---------------- per-kernel numbers and the roofline of the dominant kernel
@@ -346,6 +362,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd (BASELINE configs[3])",
                        "global_batch": batch, "rows_per_rank": b_loc, "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA,
                        "pairs": 3, "accumulate": "f32", "l2": "flushed (256 MB write) before every timed step",
+                       "launch": launch_mode, "eager_ms_per_step": eager_ms,
                        "parallelism": f"row-block x{world}"},
             "roofline": roofline, "kernels": kern, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "cpu_baseline": cpu, "small_batch": small, "retrieval": retrieval,

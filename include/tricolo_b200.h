@@ -59,10 +59,13 @@ const char* tcl_last_error_string(void);
  * For each of n_tensors row-major [rows, dim] inputs: inv_norm[r] = 1/max(||x_r||, eps),
  * z[r,:] = x[r,:] * inv_norm[r] rounded to the 16-bit operand format.
  * x_row_stride in elements.  dim % 8 == 0.
+ * z_row_stride: row stride of every 16-bit operand matrix in elements (0 = dim, i.e. contiguous;
+ * otherwise >= dim and a multiple of 8).  A stride lets several modalities share one
+ * [rows, M*dim] buffer so that a single all-gather moves them all (tricolo_b200/distributed.py).
  * ------------------------------------------------------------------------- */
 int tcl_l2norm_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t rows,
-                   int64_t dim, int64_t x_row_stride, void* const* z_host_ptrs, int op_format,
-                   float* const* inv_norm_host_ptrs, float eps, void* stream);
+                   int64_t dim, int64_t x_row_stride, void* const* z_host_ptrs, int64_t z_row_stride,
+                   int op_format, float* const* inv_norm_host_ptrs, float eps, void* stream);
 
 /* 16-bit cast without normalisation (retrieval uses the raw dot product,
  * eval_retrieval.py:74).  Accepts f32/f64/f16/bf16 input. */
@@ -72,7 +75,7 @@ int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_
 /* [rows, dim] 16-bit -> [dim, ld_t] 16-bit (ld_t >= rows, ld_t % 8 == 0); operand
  * layout of the gradient GEMM in tcl_ntxent_bwd. */
 int tcl_transpose_16bit(int n_tensors, const void* const* z_host_ptrs, int64_t rows, int64_t dim,
-                        void* const* zt_host_ptrs, int64_t ld_t, void* stream);
+                        int64_t z_row_stride, void* const* zt_host_ptrs, int64_t ld_t, void* stream);
 
 /* ---------------------------------------------------------------------------
  * K2 — similarity GEMM + fused sum-exp epilogue.   replaces nt_xent.py:62-72 forward
@@ -89,7 +92,7 @@ int tcl_transpose_16bit(int n_tensors, const void* const* z_host_ptrs, int64_t r
 size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, int64_t n_cols);
 int tcl_ntxent_fwd(int n_pairs, const void* const* zrow_host_ptrs,
                    const void* const* zcol_host_ptrs, int64_t n_rows, int64_t n_cols, int64_t dim,
-                   int64_t row_offset, int op_format, float inv_tau, float* row_sumexp,
+                   int64_t z_row_stride, int64_t row_offset, int op_format, float inv_tau, float* row_sumexp,
                    float* col_sumexp, float* diag2, void* workspace, size_t workspace_bytes,
                    void* stream);
 
@@ -139,7 +142,7 @@ typedef struct {
 
 size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int64_t dim);
 int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int64_t n_other,
-                   int64_t dim, int64_t self_offset, int64_t ld_t, int x_dtype,
+                   int64_t dim, int64_t z_row_stride, int64_t self_offset, int64_t ld_t, int x_dtype,
                    int64_t x_row_stride, int op_format, float inv_tau, float eps,
                    void* workspace, size_t workspace_bytes, void* stream);
 

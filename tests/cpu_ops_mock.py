@@ -31,11 +31,15 @@ class BwdJobSpec:
         self.__dict__.update(locals())
 
 
-def l2norm_fwd(xs, op_format=F16, eps=1e-12):
+def l2norm_fwd(xs, op_format=F16, eps=1e-12, out=None):
     zs, invs = [], []
-    for x in xs:
+    for m, x in enumerate(xs):
         inv = 1.0 / x.float().norm(dim=1).clamp_min(eps)
-        zs.append((x.float() * inv[:, None]).to(_DT[op_format]))
+        z = (x.float() * inv[:, None]).to(_DT[op_format])
+        if out is not None:
+            out[m].copy_(z)
+            z = out[m]
+        zs.append(z)
         invs.append(inv)
     return zs, invs, list(xs)
 
@@ -93,7 +97,7 @@ def ntxent_bwd(jobs, n_other, self_offset, ld_t, inv_tau, op_format=F16, eps=1e-
             g[torch.arange(n_self), self_offset + torch.arange(n_self)] -= 1.0
             go = 1.0 if sg.grad_scale is None else float(sg.grad_scale)
             # the transposed operand must describe the same matrix
-            assert torch.equal(sg.z_other_t[:, :n_other].t(), sg.z_other)
+            assert torch.equal(sg.z_other_t[:, :n_other].t().contiguous(), sg.z_other.contiguous())
             acc += go * (g @ sg.z_other_t[:, :n_other].t().double())
         gz = acc * inv_tau / n_other
         x = job.x_self.double()

@@ -49,9 +49,9 @@ def test_argument_validation_without_gpu():
     rc = L.tcl_sim_gemm(p, p, 4, 4, 12, 1, p, 4, None)  # dim not a multiple of 8
     assert rc == 1
     arr = (ctypes.c_void_p * 1)(p.value)
-    rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 100, 0, 0, 10.0, p, p, p, p, 1 << 20, None)  # dim % 64
+    rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 100, 0, 0, 0, 10.0, p, p, p, p, 1 << 20, None)  # dim % 64
     assert rc == 1
-    rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 128, 0, 0, 1000.0, p, p, p, p, 1 << 20, None)  # tau too small
+    rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 128, 0, 0, 0, 1000.0, p, p, p, p, 1 << 20, None)  # tau too small
     assert rc == 4 and b"temperature" in L.tcl_last_error_string()
     assert L.tcl_ntxent_fwd_workspace_bytes(3, 8192, 8192) > 0
     assert L.tcl_ntxent_bwd_workspace_bytes(3, 8192, 512) >= 3 * 8192 * 512 * 4

@@ -69,14 +69,14 @@ _pp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "tcl_version": (_i, []),
     "tcl_last_error_string": (C.c_char_p, []),
-    "tcl_l2norm_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _pp, _i, _pp, _f, _vp]),
+    "tcl_l2norm_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _pp, _i64, _i, _pp, _f, _vp]),
     "tcl_cast_16bit": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp]),
-    "tcl_transpose_16bit": (_i, [_i, _pp, _i64, _i64, _pp, _i64, _vp]),
+    "tcl_transpose_16bit": (_i, [_i, _pp, _i64, _i64, _i64, _pp, _i64, _vp]),
     "tcl_ntxent_fwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
-    "tcl_ntxent_fwd": (_i, [_i, _pp, _pp, _i64, _i64, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tcl_ntxent_fwd": (_i, [_i, _pp, _pp, _i64, _i64, _i64, _i64, _i64, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tcl_ntxent_finalize": (_i, [_i, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_ntxent_bwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
-    "tcl_ntxent_bwd": (_i, [_i, C.POINTER(BwdJob), _i64, _i64, _i64, _i64, _i64, _i, _i64, _i, _f, _f, _vp, _sz, _vp]),
+    "tcl_ntxent_bwd": (_i, [_i, C.POINTER(BwdJob), _i64, _i64, _i64, _i64, _i64, _i64, _i, _i64, _i, _f, _f, _vp, _sz, _vp]),
     "tcl_ntxent_loss_state_bytes": (_sz, [_i, _i, _i64, _i64]),
     "tcl_ntxent_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i64]),
     "tcl_ntxent_loss_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

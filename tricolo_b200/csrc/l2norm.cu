@@ -82,12 +82,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------
 template <typename TIn, typename TOut, bool kNormalise>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(PtrPack3 pk, int64_t rows, int dim,
-                                                         int64_t x_stride, float eps) {
+                                                         int64_t x_stride, int64_t z_stride, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (row >= rows) return;
   const TIn* x = static_cast<const TIn*>(pk.in[blockIdx.y]) + row * x_stride;
-  TOut* z = static_cast<TOut*>(pk.out[blockIdx.y]) + row * dim;
+  TOut* z = static_cast<TOut*>(pk.out[blockIdx.y]) + row * z_stride;
   constexpr int kMaxIter = 4;  // 512 elements stay in registers
   float v[kMaxIter][4];
   float ss = 0.f;
@@ -135,26 +135,26 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(PtrPack3 pk, int64_t ro
 
 template <typename TIn, bool kNormalise>
 static int launch_fwd_t(const PtrPack3& pk, int n_tensors, int64_t rows, int dim, int64_t stride,
-                        int op_format, float eps, cudaStream_t st) {
+                        int64_t z_stride, int op_format, float eps, cudaStream_t st) {
   dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_tensors);
   ProfScope prof(kNormalise ? TCL_K_L2NORM_FWD : TCL_K_CAST16, st);
   if (op_format == TCL_OP_F16)
-    l2norm_fwd_kernel<TIn, __half, kNormalise><<<grid, 256, 0, st>>>(pk, rows, dim, stride, eps);
+    l2norm_fwd_kernel<TIn, __half, kNormalise><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
   else
     l2norm_fwd_kernel<TIn, __nv_bfloat16, kNormalise>
-        <<<grid, 256, 0, st>>>(pk, rows, dim, stride, eps);
+        <<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
 
 template <bool kNormalise>
 static int launch_fwd(const PtrPack3& pk, int n_tensors, int x_dtype, int64_t rows, int dim,
-                      int64_t stride, int op_format, float eps, cudaStream_t st) {
+                      int64_t stride, int64_t z_stride, int op_format, float eps, cudaStream_t st) {
   switch (x_dtype) {
-    case TCL_DT_F32: return launch_fwd_t<float, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
-    case TCL_DT_F64: return launch_fwd_t<double, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
-    case TCL_DT_F16: return launch_fwd_t<__half, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
-    case TCL_DT_BF16: return launch_fwd_t<__nv_bfloat16, kNormalise>(pk, n_tensors, rows, dim, stride, op_format, eps, st);
+    case TCL_DT_F32: return launch_fwd_t<float, kNormalise>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
+    case TCL_DT_F64: return launch_fwd_t<double, kNormalise>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
+    case TCL_DT_F16: return launch_fwd_t<__half, kNormalise>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
+    case TCL_DT_BF16: return launch_fwd_t<__nv_bfloat16, kNormalise>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
   }
   return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
 }
@@ -167,7 +167,7 @@ static size_t dtype_size(int dt) {
 // 16-bit transpose: [rows, dim] -> [dim, ld_t], 64x64 tiles through shared memory
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose16_kernel(PtrPack3 pk, int64_t rows, int dim,
-                                                          int64_t ld_t) {
+                                                          int64_t z_stride, int64_t ld_t) {
   __shared__ uint16_t tile[64][66];
   const uint16_t* in = static_cast<const uint16_t*>(pk.in[blockIdx.z]);
   uint16_t* out = static_cast<uint16_t*>(pk.out[blockIdx.z]);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) transpose16_kernel(PtrPack3 pk, int64_t r
     const int c = tx * 2;
     uint32_t w = 0;
     if (r0 + r < rows && c0 + c < dim)
-      w = *reinterpret_cast<const uint32_t*>(in + (r0 + r) * dim + c0 + c);
+      w = *reinterpret_cast<const uint32_t*>(in + (r0 + r) * z_stride + c0 + c);
     tile[r][c] = static_cast<uint16_t>(w & 0xffffu);
     tile[r][c + 1] = static_cast<uint16_t>(w >> 16);
   }
@@ -283,8 +283,11 @@ int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t 
 using namespace tcl;
 
 extern "C" int tcl_l2norm_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t rows,
-                              int64_t dim, int64_t x_row_stride, void* const* z, int op_format,
-                              float* const* inv_norm, float eps, void* stream) {
+                              int64_t dim, int64_t x_row_stride, void* const* z, int64_t z_row_stride,
+                              int op_format, float* const* inv_norm, float eps, void* stream) {
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 8 == 0, TCL_ERR_BAD_ALIGN,
+              "l2norm: z_row_stride %lld must be >= dim and a multiple of 8", (long long)z_row_stride);
   TCL_REQUIRE(n_tensors >= 1 && n_tensors <= TCL_MAX_TENSORS, TCL_ERR_BAD_ARG, "n_tensors %d", n_tensors);
   TCL_REQUIRE(rows >= 0 && dim >= 8 && dim % 8 == 0, TCL_ERR_BAD_SHAPE,
               "l2norm: dim must be a positive multiple of 8 (got %lld)", (long long)dim);
@@ -299,7 +302,7 @@ extern "C" int tcl_l2norm_fwd(int n_tensors, const void* const* x, int x_dtype, 
     TCL_REQUIRE(aligned_to(x[i], 16) && aligned_to(z[i], 16), TCL_ERR_BAD_ALIGN, "l2norm: pointers must be 16-byte aligned");
     pk.in[i] = x[i]; pk.out[i] = z[i]; pk.aux[i] = inv_norm[i];
   }
-  return launch_fwd<true>(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, op_format, eps,
+  return launch_fwd<true>(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
                           static_cast<cudaStream_t>(stream));
 }
 
@@ -314,12 +317,14 @@ extern "C" int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t 
   if (rows == 0) return TCL_OK;
   PtrPack3 pk{};
   pk.in[0] = x; pk.out[0] = y;
-  return launch_fwd<false>(pk, 1, x_dtype, rows, (int)dim, x_row_stride, op_format, 0.f,
+  return launch_fwd<false>(pk, 1, x_dtype, rows, (int)dim, x_row_stride, dim, op_format, 0.f,
                            static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tcl_transpose_16bit(int n_tensors, const void* const* z, int64_t rows, int64_t dim,
-                                   void* const* zt, int64_t ld_t, void* stream) {
+                                   int64_t z_row_stride, void* const* zt, int64_t ld_t, void* stream) {
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 2 == 0, TCL_ERR_BAD_ALIGN, "transpose: z_row_stride");
   TCL_REQUIRE(n_tensors >= 1 && n_tensors <= TCL_MAX_TENSORS, TCL_ERR_BAD_ARG, "n_tensors %d", n_tensors);
   TCL_REQUIRE(rows >= 0 && dim >= 2 && dim % 2 == 0, TCL_ERR_BAD_SHAPE, "transpose: dim %lld", (long long)dim);
   TCL_REQUIRE(ld_t >= rows && ld_t % 8 == 0, TCL_ERR_BAD_ALIGN, "transpose: ld_t %lld must be >= rows and a multiple of 8", (long long)ld_t);
@@ -333,7 +338,7 @@ extern "C" int tcl_transpose_16bit(int n_tensors, const void* const* z, int64_t 
   dim3 grid(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((dim + 63) / 64), n_tensors);
   {
     ProfScope prof(TCL_K_TRANSPOSE16, static_cast<cudaStream_t>(stream));
-    transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pk, rows, (int)dim, ld_t);
+    transpose16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pk, rows, (int)dim, z_row_stride, ld_t);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;

@@ -327,7 +327,7 @@ extern "C" size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int
 }
 
 extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_self, int64_t n_other,
-                              int64_t dim, int64_t self_offset, int64_t ld_t, int x_dtype,
+                              int64_t dim, int64_t z_row_stride, int64_t self_offset, int64_t ld_t, int x_dtype,
                               int64_t x_row_stride, int op_format, float inv_tau, float eps,
                               void* workspace, size_t workspace_bytes, void* stream) {
   TCL_REQUIRE(n_jobs >= 1 && n_jobs <= TCL_MAX_TENSORS && jobs, TCL_ERR_BAD_ARG, "ntxent_bwd: n_jobs %d", n_jobs);
@@ -340,6 +340,8 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   TCL_REQUIRE(workspace && workspace_bytes >= tcl_ntxent_bwd_workspace_bytes(n_jobs, n_self, dim), TCL_ERR_WORKSPACE, "ntxent_bwd: workspace too small");
   const float c1 = inv_tau * 1.4426950408889634f;
   TCL_REQUIRE(inv_tau > 0.f && 2.f * c1 < 120.f, TCL_ERR_BAD_ARG, "ntxent_bwd: temperature too small (need tau >= 0.025)");
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 8 == 0, TCL_ERR_BAD_ALIGN, "ntxent_bwd: z_row_stride");
   if (int e = require_sm100()) return e;
 
   BwdParams P;
@@ -373,12 +375,12 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     BwdJobDev& J = P.job[j];
     TCL_REQUIRE(src.n_segments >= 1 && src.n_segments <= 2, TCL_ERR_BAD_ARG, "ntxent_bwd: job %d has %d segments", j, src.n_segments);
     TCL_REQUIRE(src.z_self && src.x_self && src.inv_norm && src.dx, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d", j);
-    if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, dim, BW_BM, BW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, z_row_stride, BW_BM, BW_BK)) return e;
     J.n_seg = src.n_segments;
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
       TCL_REQUIRE(sg.z_other && sg.z_other_t && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, dim, use_cluster ? 64 : BW_BN, BW_BK)) return e;
+      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, use_cluster ? 64 : BW_BN, BW_BK)) return e;
       if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, 128, BW_BK)) return e;
       J.seg[s].lse2_self = sg.lse2_self;
       J.seg[s].lse2_other = sg.lse2_other;

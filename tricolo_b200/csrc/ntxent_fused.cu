@@ -67,7 +67,7 @@ extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dt
     z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
     inv[m] = reinterpret_cast<float*>(st8 + L.inv) + static_cast<size_t>(m) * batch;
   }
-  if (int e = tcl_l2norm_fwd(n_tensors, x, x_dtype, batch, dim, x_row_stride, z, op_format, inv, eps, stream)) return e;
+  if (int e = tcl_l2norm_fwd(n_tensors, x, x_dtype, batch, dim, x_row_stride, z, 0, op_format, inv, eps, stream)) return e;
   const void* zrow[TCL_MAX_PAIRS];
   const void* zcol[TCL_MAX_PAIRS];
   for (int p = 0; p < n_pairs; ++p) {
@@ -79,7 +79,7 @@ extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dt
   float* row_sum = reinterpret_cast<float*>(st8 + L.row_sum);
   float* col_sum = reinterpret_cast<float*>(st8 + L.col_sum);
   float* diag2 = reinterpret_cast<float*>(st8 + L.diag2);
-  if (int e = tcl_ntxent_fwd(n_pairs, zrow, zcol, batch, batch, dim, 0, op_format, inv_tau, row_sum, col_sum, diag2,
+  if (int e = tcl_ntxent_fwd(n_pairs, zrow, zcol, batch, batch, dim, 0, 0, op_format, inv_tau, row_sum, col_sum, diag2,
                              workspace, workspace_bytes, stream))
     return e;
   return tcl_ntxent_finalize(n_pairs, batch, batch, 0, inv_tau, alpha, row_sum, col_sum, diag2,
@@ -107,7 +107,7 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
     z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
     zt[m] = ws8 + static_cast<size_t>(m) * dim * ld_t * 2;
   }
-  if (int e = tcl_transpose_16bit(n_tensors, z, batch, dim, zt, ld_t, stream)) return e;
+  if (int e = tcl_transpose_16bit(n_tensors, z, batch, dim, 0, zt, ld_t, stream)) return e;
   const size_t zt_bytes = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256);
   const float* lse_row = reinterpret_cast<const float*>(st8 + L.lse_row);
   const float* lse_col = reinterpret_cast<const float*>(st8 + L.lse_col);
@@ -139,6 +139,6 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
     if (J.n_segments > 0) ++n_jobs;
   }
   if (n_jobs == 0) return TCL_OK;
-  return tcl_ntxent_bwd(n_jobs, jobs, batch, batch, dim, 0, ld_t, x_dtype, x_row_stride, op_format, inv_tau, eps,
+  return tcl_ntxent_bwd(n_jobs, jobs, batch, batch, dim, 0, 0, ld_t, x_dtype, x_row_stride, op_format, inv_tau, eps,
                         ws8 + zt_bytes, workspace_bytes - zt_bytes, stream);
 }

@@ -380,7 +380,7 @@ extern "C" size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, in
 }
 
 extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* const* zcol,
-                              int64_t n_rows, int64_t n_cols, int64_t dim, int64_t row_offset,
+                              int64_t n_rows, int64_t n_cols, int64_t dim, int64_t z_row_stride, int64_t row_offset,
                               int op_format, float inv_tau, float* row_sumexp, float* col_sumexp,
                               float* diag2, void* workspace, size_t workspace_bytes, void* stream) {
   TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "ntxent_fwd: n_pairs %d", n_pairs);
@@ -398,14 +398,16 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
   TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && workspace, TCL_ERR_BAD_ARG, "ntxent_fwd: null pointer");
   TCL_REQUIRE(workspace_bytes >= tcl_ntxent_fwd_workspace_bytes(n_pairs, n_rows, n_cols), TCL_ERR_WORKSPACE,
               "ntxent_fwd: workspace too small");
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 8 == 0, TCL_ERR_BAD_ALIGN, "ntxent_fwd: z_row_stride");
   if (int e = require_sm100()) return e;
 
   FwdParams P;
   memset(&P, 0, sizeof(P));
   for (int p = 0; p < n_pairs; ++p) {
     TCL_REQUIRE(zrow[p] && zcol[p], TCL_ERR_BAD_ARG, "ntxent_fwd: null operand (pair %d)", p);
-    if (int e = make_tmap_2d_16bit(&P.tm_row[p], zrow[p], n_rows, dim, dim, FW_BM, FW_BK)) return e;
-    if (int e = make_tmap_2d_16bit(&P.tm_col[p], zcol[p], n_cols, dim, dim, FW_BN, FW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&P.tm_row[p], zrow[p], n_rows, dim, z_row_stride, FW_BM, FW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&P.tm_col[p], zcol[p], n_cols, dim, z_row_stride, FW_BN, FW_BK)) return e;
   }
   P.n_rows = (int)n_rows; P.n_cols = (int)n_cols; P.row_offset = (int)row_offset;
   P.num_kb = (int)(dim / 64);

@@ -4,9 +4,10 @@ Training — global-negative trimodal InfoNCE (BASELINE.json configs[3]).  The r
 gathers negatives; the semantics here are "the reference loss evaluated on the
 concatenated global batch".  Each rank holds B/W rows of every modality and owns that row block
 of each logit matrix:
-    all-gather   16-bit normalised embeddings                 (W-1)/W * 3*B*D*2 bytes in
+    all-gather   16-bit normalised embeddings, all modalities in ONE call (interleaved rows,
+                 strided TMA operands)                          (W-1)/W * 3*B*D*2 bytes in
     all-reduce   column sum-exp partials, 3 x [B] fp32         (fixed shift -> plain sums)
-    all-gather   row LSEs 3 x [B/W] fp32, all-reduce loss partials
+    all-gather   row LSEs 3 x [B/W] fp32 + loss partials
 The backward is the same directional kernel as on one GPU, run for the local rows of each
 modality against ALL rows of the partner modality, so every local gradient is complete without a
 gradient reduce-scatter (the recompute the kernel does anyway replaces the exchange).
@@ -32,47 +33,62 @@ def _world(group=None):
 
 
 class _GlobalNTXent(torch.autograd.Function):
+    """Three collectives in the forward (one all-gather of all modalities, one all-reduce of the column
+    sums, one all-gather of row LSEs + loss partials); none in the backward."""
+
     @staticmethod
     def forward(ctx, temperature, alpha, op_format, pairs, group, grad_world_scale, *feats):
         world, rank = _world(group)
         inv_tau = 1.0 / float(temperature)
         feats = [f.detach() for f in feats]
+        n, p = len(feats), len(pairs)
         b_loc, dim = feats[0].shape
         b_glob = b_loc * world
         row_offset = rank * b_loc
-        zs, invs, xs = ops.l2norm_fwd(feats, op_format)
-        # all-gather each modality straight into its [B, D] operand (rank-major rows)
-        z_all = []
-        for z in zs:
-            full = torch.empty((b_glob, dim), dtype=z.dtype, device=z.device)
-            dist.all_gather_into_tensor(full, z, group=group)
-            z_all.append(full)
-        zrows = [zs[a] for a, _ in pairs]
-        zcols = [z_all[b] for _, b in pairs]
-        row_sum, col_sum, diag2 = ops.ntxent_fwd(zrows, zcols, row_offset, inv_tau, op_format)
+        dev = feats[0].device
+        dt = ops.L.op_torch_dtype(op_format)
+        # all modalities interleaved per row: [b_loc, n*dim]; modality m = columns [m*dim, (m+1)*dim) with row
+        # stride n*dim, so ONE all-gather yields every [B, dim] operand without a copy
+        z_loc = torch.empty((b_loc, n * dim), dtype=dt, device=dev)
+        z_loc3 = z_loc.view(b_loc, n, dim)
+        _, invs, xs = ops.l2norm_fwd(feats, op_format, out=[z_loc3[:, m] for m in range(n)])
+        z_glob = torch.empty((b_glob, n * dim), dtype=dt, device=dev)
+        dist.all_gather_into_tensor(z_glob, z_loc, group=group)
+        z_glob3 = z_glob.view(b_glob, n, dim)
+        z_all = [z_glob3[:, m] for m in range(n)]
+        z_own = [z[row_offset:row_offset + b_loc] for z in z_all]  # local rows inside the gathered buffer
+        row_sum, col_sum, diag2 = ops.ntxent_fwd([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs],
+                                                 row_offset, inv_tau, op_format)
         dist.all_reduce(col_sum, group=group)
         lse2_row, lse2_col, parts, _ = ops.ntxent_finalize(row_sum, col_sum, diag2, row_offset, inv_tau, alpha,
                                                            want_loss=False)
-        dist.all_reduce(parts, group=group)
-        loss = (alpha * parts[:, 0] + (1.0 - alpha) * parts[:, 1]) / b_glob
-        # row LSEs of every rank (needed when a local column block meets all rows in the backward)
-        lse2_row_all = torch.empty((world * len(pairs), b_loc), dtype=torch.float32, device=lse2_row.device)
-        dist.all_gather_into_tensor(lse2_row_all, lse2_row, group=group)  # [W*P, b_loc], rank-major
-        lse2_row_all = lse2_row_all.view(world, len(pairs), b_loc).permute(1, 0, 2).reshape(len(pairs), b_glob).contiguous()
-        ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale))
-        ctx.save_for_backward(lse2_row_all, lse2_col, *xs, *zs, *invs, *z_all)
+        # row LSEs of every rank (the backward meets all rows when a local column block is "self") and the
+        # loss partials travel in one all-gather
+        pack = torch.cat([lse2_row.reshape(-1), parts.reshape(-1)])
+        packs = torch.empty((world * pack.numel(),), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(packs, pack, group=group)
+        packs = packs.view(world, pack.numel())
+        lse2_row_all = packs[:, :p * b_loc].reshape(world, p, b_loc).permute(1, 0, 2).reshape(p, b_glob).contiguous()
+        parts_sum = packs[:, p * b_loc:].reshape(world, p, 2).sum(dim=0)
+        loss = (alpha * parts_sum[:, 0] + (1.0 - alpha) * parts_sum[:, 1]) / b_glob
+        ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
+        ctx.save_for_backward(lse2_row_all, lse2_col, z_glob, *xs, *invs)
         return loss
 
     @staticmethod
     def backward(ctx, grad_losses):
-        inv_tau, alpha, op_format, pairs, row_offset, b_glob, gscale = ctx.cfg
+        inv_tau, alpha, op_format, pairs, row_offset, b_glob, gscale, n = ctx.cfg
         saved = ctx.saved_tensors
-        lse2_row_all, lse2_col = saved[0], saved[1]
-        n = (len(saved) - 2) // 4
-        xs, zs, invs, z_all = (saved[2:2 + n], saved[2 + n:2 + 2 * n], saved[2 + 2 * n:2 + 3 * n],
-                               saved[2 + 3 * n:])
-        b_loc = zs[0].shape[0]
-        grad_losses = (grad_losses.to(torch.float32) * gscale).contiguous()
+        lse2_row_all, lse2_col, z_glob = saved[0], saved[1], saved[2]
+        xs, invs = saved[3:3 + n], saved[3 + n:3 + 2 * n]
+        b_loc, dim = xs[0].shape
+        z_glob3 = z_glob.view(b_glob, n, dim)
+        z_all = [z_glob3[:, m] for m in range(n)]
+        z_own = [z[row_offset:row_offset + b_loc] for z in z_all]
+        grad_losses = grad_losses.to(torch.float32)
+        if gscale != 1.0:
+            grad_losses = grad_losses * gscale
+        grad_losses = grad_losses.contiguous()
         zts, ld_t = ops.transpose_16bit(z_all)
         jobs, owners = [], []
         sl = slice(row_offset, row_offset + b_loc)
@@ -88,7 +104,7 @@ class _GlobalNTXent(torch.autograd.Function):
                     segs.append(ops.BwdSegmentSpec(z_all[a], zts[a], lse2_col[p, sl], lse2_row_all[p],
                                                    grad_losses[p:p + 1], 1.0 - alpha, alpha))
             if segs:
-                jobs.append(ops.BwdJobSpec(zs[m], xs[m], invs[m], segs))
+                jobs.append(ops.BwdJobSpec(z_own[m], xs[m], invs[m], segs))
                 owners.append(m)
         grads: List = [None] * n
         if jobs:

@@ -26,8 +26,18 @@ def _rows_2d(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def l2norm_fwd(xs: Sequence[torch.Tensor], op_format: int = F16, eps: float = EPS):
-    """K1. Returns ([z 16-bit [rows, dim]], [inv_norm fp32 [rows]]). nt_xent.py:56-57."""
+def _z_stride(zs) -> int:
+    """Common row stride (elements) of a set of 16-bit operand matrices (contiguous or strided views)."""
+    st = zs[0].stride(0)
+    for z in zs:
+        if z.stride(1) != 1 or z.stride(0) != st:
+            raise ValueError("16-bit operand matrices must share one row stride and have unit column stride")
+    return st
+
+
+def l2norm_fwd(xs: Sequence[torch.Tensor], op_format: int = F16, eps: float = EPS, out=None):
+    """K1. Returns ([z 16-bit [rows, dim]], [inv_norm fp32 [rows]]). nt_xent.py:56-57.
+    `out`: optional pre-allocated z views (e.g. column slices of one [rows, M*dim] buffer)."""
     dev = L.require_cuda(*xs)
     xs = [_rows_2d(x) for x in xs]
     rows, dim = xs[0].shape
@@ -37,11 +47,13 @@ def l2norm_fwd(xs: Sequence[torch.Tensor], op_format: int = F16, eps: float = EP
     same_stride = all(x.stride(0) == xs[0].stride(0) for x in xs)
     if not same_stride:
         xs = [x.contiguous() for x in xs]
-    zs = [torch.empty((rows, dim), dtype=L.op_torch_dtype(op_format), device=dev) for _ in xs]
-    invs = [torch.empty((rows,), dtype=torch.float32, device=dev) for _ in xs]
+    zs = out if out is not None else [torch.empty((rows, dim), dtype=L.op_torch_dtype(op_format), device=dev) for _ in xs]
+    inv_all = torch.empty((len(xs), rows), dtype=torch.float32, device=dev)
+    invs = [inv_all[m] for m in range(len(xs))]
     with torch.cuda.device(dev):
         L.check(LIB.tcl_l2norm_fwd(len(xs), L.ptr_array(xs), L.dtype_code(xs[0]), rows, dim, xs[0].stride(0),
-                                   L.ptr_array(zs), op_format, L.ptr_array(invs), eps, L.stream_ptr(dev)))
+                                   L.ptr_array(zs), _z_stride(zs), op_format, L.ptr_array(invs), eps,
+                                   L.stream_ptr(dev)))
     return zs, invs, xs
 
 
@@ -62,7 +74,8 @@ def transpose_16bit(zs: Sequence[torch.Tensor]) -> Tuple[List[torch.Tensor], int
     ld_t = (rows + 7) // 8 * 8
     zts = [torch.empty((dim, ld_t), dtype=z.dtype, device=dev) for z in zs]
     with torch.cuda.device(dev):
-        L.check(LIB.tcl_transpose_16bit(len(zs), L.ptr_array(zs), rows, dim, L.ptr_array(zts), ld_t, L.stream_ptr(dev)))
+        L.check(LIB.tcl_transpose_16bit(len(zs), L.ptr_array(zs), rows, dim, _z_stride(zs), L.ptr_array(zts), ld_t,
+                                        L.stream_ptr(dev)))
     return zts, ld_t
 
 
@@ -79,7 +92,8 @@ def ntxent_fwd(zrows: Sequence[torch.Tensor], zcols: Sequence[torch.Tensor], row
     ws_bytes = LIB.tcl_ntxent_fwd_workspace_bytes(p, n_rows, n_cols)
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        L.check(LIB.tcl_ntxent_fwd(p, L.ptr_array(zrows), L.ptr_array(zcols), n_rows, n_cols, dim, row_offset,
+        L.check(LIB.tcl_ntxent_fwd(p, L.ptr_array(zrows), L.ptr_array(zcols), n_rows, n_cols, dim,
+                                   _z_stride(list(zrows) + list(zcols)), row_offset,
                                    op_format, inv_tau, L.ptr(row_sum), L.ptr(col_sum), L.ptr(diag2), L.ptr(ws),
                                    ws_bytes, L.stream_ptr(dev)))
     return row_sum, col_sum, diag2
@@ -146,7 +160,8 @@ def ntxent_bwd(jobs: Sequence[BwdJobSpec], n_other: int, self_offset: int, ld_t:
     ws_bytes = LIB.tcl_ntxent_bwd_workspace_bytes(len(jobs), n_self, dim)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        L.check(LIB.tcl_ntxent_bwd(len(jobs), arr, n_self, n_other, dim, self_offset, ld_t, L.dtype_code(x0),
+        z_stride = _z_stride([j.z_self for j in jobs] + [s.z_other for j in jobs for s in j.segments])
+        L.check(LIB.tcl_ntxent_bwd(len(jobs), arr, n_self, n_other, dim, z_stride, self_offset, ld_t, L.dtype_code(x0),
                                    x0.stride(0), op_format, inv_tau, eps, L.ptr(ws), ws_bytes, L.stream_ptr(dev)))
     return dxs
 
