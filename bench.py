@@ -290,8 +290,14 @@ def run_ours(args, rank, world, local_rank):
         kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9})
     peak_tf = peaks["tf_sustained"]
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
+    traffic = None
+    try:  # DRAM bytes per launch of the same kernel at the same shapes, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+            traffic = json.load(f).get("ntxent_bwd_kernel") if (world == 1 and batch == 8192) else None
+    except Exception:
+        traffic = None
     roofline = {"kernel": "ntxent_bwd_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (ach / peak_tf) if ach else None, "traffic": None,
+                "frac": (ach / peak_tf) if ach else None, "traffic": traffic,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops_bwd,
                 "whole_step": {"algorithmic_flops": flops_fwd + flops_bwd,

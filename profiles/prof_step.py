@@ -1,5 +1,7 @@
-"""Short driver for ncu captures: a few fwd+bwd steps of the C4 loss and one retrieval block.
-   ncu --set full ... python profiles/prof_step.py [loss|retrieval]"""
+"""Short drivers for ncu captures.
+   ncu ... python profiles/prof_step.py loss [B]        three fwd+bwd steps of the trimodal loss
+   ncu ... python profiles/prof_step.py retrieval       two-kernel form: GEMM -> HBM -> top-k (3 blocks of 8192 x 200k)
+   ncu ... python profiles/prof_step.py fused           fused kernel, 18944 queries x 200k (one CTA per SM)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +20,9 @@ if what == "loss":
 else:
     g = torch.Generator(device=dev).manual_seed(0)
     gal = torch.randn(200000, 512, generator=g, device=dev).bfloat16()
-    text = torch.randn(8192 * 3, 512, generator=g, device=dev).bfloat16()
-    lab = torch.randint(0, 200000, (8192 * 3,), generator=g, device=dev)
-    retrieve(text, gal, lab, 5, block_queries=8192)
+    nq = 8192 * 3 if what == "retrieval" else 148 * 128
+    text = torch.randn(nq, 512, generator=g, device=dev).bfloat16()
+    lab = torch.randint(0, 200000, (nq,), generator=g, device=dev)
+    for _ in range(1 if what == "retrieval" else 2):
+        retrieve(text, gal, lab, 5, block_queries=8192 if what == "retrieval" else None, fused=(what == "fused"))
 torch.cuda.synchronize()

@@ -232,14 +232,20 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(NormBwdParams pr, int64
   for (int it = 0; it < kMaxIter; ++it) {
     const int c = it * 128 + lane * 4;
     if (c < dim) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int s = 0; s < n_split; ++s) {
-        float t[4];
-        load4<float>(jb.gpart + s * split_stride + row * dim + c, t);
-        acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += t[3];
-      }
+      // all split partials are fetched before any is consumed (8 independent 16-byte loads in flight);
+      // the sum order s = 0,1,2,... is fixed, so the result does not depend on the split count's timing
+      float4 part[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        part[s] = s < n_split ? __ldcs(reinterpret_cast<const float4*>(jb.gpart + s * split_stride + row * dim + c))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
       float xv[4];
       load4<T>(x + c, xv);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        acc[0] += part[s].x; acc[1] += part[s].y; acc[2] += part[s].z; acc[3] += part[s].w;
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         g[it][e] = acc[e] * scale;
