@@ -367,6 +367,11 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   // ~20 B/clk DSMEM rate and the N=64 logit MMAs are shared-memory-bound.  Kept behind an opt-in switch.
   static const bool want_cluster = getenv("TRICOLO_B200_BWD_CLUSTER") != nullptr;
   const bool use_cluster = P.n_dhalf == 2 && want_cluster;
+  // Default for dim > 256: the CTA-pair kernel (ntxent_bwd_pair.cu) — both GEMMs as 2-SM MMAs, the logit tile is
+  // recomputed once per (row block, column tile); TRICOLO_B200_BWD_NOPAIR=1 selects the independent-CTA kernel.
+  static const bool no_pair = getenv("TRICOLO_B200_BWD_NOPAIR") != nullptr;
+  const bool use_pair = P.n_dhalf == 2 && !want_cluster && !no_pair;
+  P.idesc_m256 = umma_idesc_f16(256, BW_BN, op_format);
   float* ws = static_cast<float*>(workspace);
   float* scales = ws;  // 64 floats reserved
   float* gbase = ws + 64;
@@ -375,12 +380,12 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     BwdJobDev& J = P.job[j];
     TCL_REQUIRE(src.n_segments >= 1 && src.n_segments <= 2, TCL_ERR_BAD_ARG, "ntxent_bwd: job %d has %d segments", j, src.n_segments);
     TCL_REQUIRE(src.z_self && src.x_self && src.inv_norm && src.dx, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d", j);
-    if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, z_row_stride, BW_BM, BW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, z_row_stride, use_pair ? 64 : BW_BM, BW_BK)) return e;
     J.n_seg = src.n_segments;
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
       TCL_REQUIRE(sg.z_other && sg.z_other_t && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, use_cluster ? 64 : BW_BN, BW_BK)) return e;
+      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, (use_cluster || use_pair) ? 64 : BW_BN, BW_BK)) return e;
       if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, 128, BW_BK)) return e;
       J.seg[s].lse2_self = sg.lse2_self;
       J.seg[s].lse2_other = sg.lse2_other;
@@ -400,7 +405,9 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(n_iblocks, P.n_dhalf * P.n_split, n_jobs);
   prof_begin(TCL_K_NTXENT_BWD, st);
-  if (use_cluster) {
+  if (use_pair) {
+    if (int e = launch_bwd_pair(P, n_iblocks, n_jobs, op_format, st)) return e;
+  } else if (use_cluster) {
     if (int e = launch_bwd_cluster(P, n_iblocks, n_jobs, op_format, st)) return e;
   } else if (op_format == TCL_OP_F16) {
     static int set = 0;

@@ -36,6 +36,7 @@ struct BwdParams {
   float out_scale;  // 1/(tau*n_other)
   uint32_t idesc;   // M=128, N=128
   uint32_t idesc_n64;  // M=128, N=64 (cluster kernel: half logit tile)
+  uint32_t idesc_m256;  // M=256 (CTA pair), N=128 (pair kernel: gradient MMA)
 };
 
 struct BwdSmem {
@@ -58,6 +59,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+// ntxent_bwd_pair.cu
+int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 // ntxent_bwd_cluster.cu
 int launch_bwd_cluster(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 
