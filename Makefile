@@ -17,7 +17,16 @@ $(LIB): $(OBJS)
 	@mkdir -p tricolo_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart shared
 
-clean:
-	rm -rf build $(LIB)
+# wait-time accounting build of the CTA-pair backward (profiles/pair_trace.py)
+TRACE_LEVEL ?= 2
+EXP ?= 0
+TRACE_LIB ?= tricolo_b200/lib/libtricolo_b200_trace.so
+trace:
+	@mkdir -p build_trace
+	for f in $(SRCS); do $(NVCC) $(NVCCFLAGS) -DTCL_PAIR_TRACE=$(TRACE_LEVEL) -DTCL_PAIR_EXP=$(EXP) -c $$f -o build_trace/$$(basename $$f .cu).o 2> /dev/null || exit 1; done
+	$(NVCC) $(ARCH) -shared -o $(TRACE_LIB) build_trace/*.o -cudart shared
 
-.PHONY: all clean
+clean:
+	rm -rf build build_trace $(LIB) tricolo_b200/lib/libtricolo_b200_trace.so
+
+.PHONY: all clean trace

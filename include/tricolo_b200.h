@@ -257,6 +257,9 @@ int tcl_profile_read(int kernel_id, double* total_ms, int64_t* launches);
  * through the 16x256b load shape; out[(warp*2+half)*32*16 + thread*16 + reg].
  * ------------------------------------------------------------------------- */
 int tcl_debug_tmem_probe(uint32_t* out, void* stream);
+/* tcl_debug_pair_trace: cycles the roles of the first CTA pair of the pair backward kernel spent in each wait
+ * (32 counters, see ntxent_bwd_pair.cu; all zero unless the library was built with `make trace`). */
+int tcl_debug_pair_trace(unsigned long long* out32, int reset);
 
 #ifdef __cplusplus
 }

@@ -356,7 +356,6 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   int min_seg = 2;
   for (int j = 0; j < n_jobs; ++j) min_seg = jobs[j].n_segments < min_seg ? jobs[j].n_segments : min_seg;
   if (min_seg < 1) min_seg = 1;
-  P.n_split = bwd_split(n_jobs, n_iblocks, P.n_dhalf, min_seg * P.n_jtiles);
   P.c1 = c1;
   P.out_scale = inv_tau / static_cast<float>(n_other);
   P.idesc = umma_idesc_f16(BW_BM, BW_BN, op_format);
@@ -367,11 +366,15 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   // ~20 B/clk DSMEM rate and the N=64 logit MMAs are shared-memory-bound.  Kept behind an opt-in switch.
   static const bool want_cluster = getenv("TRICOLO_B200_BWD_CLUSTER") != nullptr;
   const bool use_cluster = P.n_dhalf == 2 && want_cluster;
-  // Default for dim > 256: the CTA-pair kernel (ntxent_bwd_pair.cu) — both GEMMs as 2-SM MMAs, the logit tile is
-  // recomputed once per (row block, column tile); TRICOLO_B200_BWD_NOPAIR=1 selects the independent-CTA kernel.
+  // Default for dim > 256: the CTA-pair kernel (ntxent_bwd_pair.cu) — both GEMMs as 2-SM M=256 MMAs, the logit
+  // tile is recomputed once per (row block, column tile); TRICOLO_B200_BWD_NOPAIR=1 selects the independent-CTA kernel.
   static const bool no_pair = getenv("TRICOLO_B200_BWD_NOPAIR") != nullptr;
   const bool use_pair = P.n_dhalf == 2 && !want_cluster && !no_pair;
   P.idesc_m256 = umma_idesc_f16(256, BW_BN, op_format);
+  P.idesc_m256_bmn = P.idesc_m256 | (1u << 16);
+  // the pair kernel walks the column tiles two at a time
+  P.n_split = use_pair ? bwd_split(n_jobs, n_iblocks, 2, (min_seg * P.n_jtiles + 1) / 2)
+                       : bwd_split(n_jobs, n_iblocks, P.n_dhalf, min_seg * P.n_jtiles);
   float* ws = static_cast<float*>(workspace);
   float* scales = ws;  // 64 floats reserved
   float* gbase = ws + 64;
@@ -385,7 +388,7 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
       TCL_REQUIRE(sg.z_other && sg.z_other_t && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, (use_cluster || use_pair) ? 64 : BW_BN, BW_BK)) return e;
+      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, use_cluster ? 64 : BW_BN, BW_BK)) return e;
       if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, 128, BW_BK)) return e;
       J.seg[s].lse2_self = sg.lse2_self;
       J.seg[s].lse2_other = sg.lse2_other;

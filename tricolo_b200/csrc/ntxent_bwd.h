@@ -36,7 +36,8 @@ struct BwdParams {
   float out_scale;  // 1/(tau*n_other)
   uint32_t idesc;   // M=128, N=128
   uint32_t idesc_n64;  // M=128, N=64 (cluster kernel: half logit tile)
-  uint32_t idesc_m256;  // M=256 (CTA pair), N=128 (pair kernel: gradient MMA)
+  uint32_t idesc_m256;      // M=256 (CTA pair), N=128, both operands K-major (pair kernel: logit MMA)
+  uint32_t idesc_m256_bmn;  // same with an MN-major B operand (pair kernel: gradient MMA)
 };
 
 struct BwdSmem {

@@ -1,42 +1,44 @@
-// K3, CTA-pair form (dim > 256): both GEMMs of the backward as 2-SM tcgen05 MMAs (cta_group::2), so the
-// logit recompute is done ONCE per (row block, column tile) instead of once per dim half.
+// K3, CTA-pair form (dim > 256): both GEMMs of the backward as full-rate 2-SM tcgen05 MMAs (cta_group::2,
+// M=256), the logit tile recomputed ONCE per (row block, column tile) instead of once per dim half.
 //
-// A cluster of two CTAs owns 128 "self" rows (64 each) and ALL of dim:
-//   S phase   S[128 x 128] = Zself · Zother_tile^T   2-SM MMA, M=128 (64 rows per CTA), N=128, K=dim.
-//             A = each CTA's 64 resident self rows, B = the other-tile, N-split: each CTA TMA-loads 64 of
-//             its 128 rows.  Per CTA the accumulator is 64 rows x 128 columns, stored as 128 lanes x 64
-//             TMEM columns (tile columns 64..127 sit in lanes 64..127).
-//   epilogue  each CTA turns ITS 64 rows into the 16-bit G tile [64 x 128] and stores it K-major/swizzled
-//             in its own shared memory.
-//   A phase   acc^T[d, i] += Zother^T[d, j] · G[i, j]      2-SM MMA, M=256 (128 dim rows per CTA), N=128
-//             (= the 128 self rows), K=128.  B = G, N-split across the pair: every CTA contributes exactly
-//             the 64 rows it has just produced — the tensor core reads the peer's half from the peer's shared
-//             memory, so NOTHING is exchanged in software.  A = transposed other operand, each CTA loads its
-//             own dim rows.  Two such accumulators per CTA (dim rows [256c + 128 rank, +128), c = 0,1).
-// Executed flop per pair and direction: 2 B^2 D (recompute) + 2 B^2 D (gradient) — the algorithmic count —
-// against 3x that in the independent-CTA kernel (ntxent_bwd.cu), which recomputes per dim half.
+// A cluster of two CTAs (adjacent in x) owns 128 "self" rows and ALL of dim.  One step = two column tiles:
+//   S phase   S^T[256 j x 128 i] = Zother[2 tiles] · Zself^T      2-SM MMA, M=256, N=128, K=dim.
+//             A = the other-operand tile of each CTA (CTA h streams tile 2u+h), B = the self block, N-split:
+//             each CTA keeps 64 of the 128 self rows resident.  Per CTA the accumulator is S^T of ITS tile:
+//             128 lanes (j) x 128 TMEM columns (i).
+//             (M=128 over two SMs — 64 rows per SM — runs the tensor cores at half rate, measured: 1.02 ms for
+//             the whole backward, no better than the independent-CTA kernel; mapping j to M avoids it.)
+//   epilogue  thread = column j of the logits.  It turns its S values into the 16-bit gradient weights G[i, j]
+//             and stores them as the B operand of the gradient MMA: rows = K index j, 128 bytes = 64 self rows i
+//             (MN-major, 128-byte swizzle).  That operand is N-split by self-row halves across the pair, so the
+//             half with i < 64 goes to CTA 0's shared memory and the half with i >= 64 to CTA 1's: of the two
+//             warps per lane quarter one writes locally, the other through DSMEM (16 KB per step and direction).
+//   A phase   acc^T[d, i] += Zother^T[d, j] · G[i, j]     2-SM MMA, M=256 (128 dim rows per CTA), N=128, K=256
+//             (the step's two tiles).  Two accumulators per CTA: dim rows [256c + 128 rank, +128), c = 0,1.
+// Executed flop per pair and direction: 2 B^2 D (recompute) + 2 B^2 D (gradient) = the algorithmic count, against
+// 3x the gradient term in the independent-CTA kernel (ntxent_bwd.cu).
 //
-// Only the leader CTA (cluster rank 0) issues MMAs.  Barriers: TMA loads of both CTAs complete on the
-// leader's `full` barriers; tcgen05.commit multicasts to both CTAs' `empty`, `s_full`, `g_empty`, `acc_full`;
-// epilogue warps of both CTAs arrive on the leader's `s_empty` / `g_full` (remote arrives from the peer).
+// Only the leader CTA (cluster rank 0) issues MMAs.  TMA loads of both CTAs complete on the leader's `full`
+// barriers; tcgen05.commit multicasts to both CTAs' `empty`, `s_full`, `g_empty`, `acc_full`; the epilogue warps
+// of both CTAs arrive on the leader's `s_empty` / `g_full` (remote arrives from the peer).
 #include "ntxent_bwd.h"
 #include "../../include/tricolo_b200.h"
 
 namespace tcl {
 
-static constexpr int BP_STAGES = 6;           // 16 KB ring slots
-static constexpr int BP_NBUF = 3;             // logit (TMEM) and G (smem) buffers: the logit MMAs run two tiles ahead of the
-                                              // gradient MMAs, which gives the epilogue two tile times to turn S into G
-static constexpr int BP_SLOT = 16384;
-static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA
+static constexpr int BP_STAGES = 3;    // ring slots
+static constexpr int BP_BLK = 16384;   // one TMA box: 128 rows x 64 K elements
+static constexpr int BP_SLOT = 2 * BP_BLK;
+static constexpr int BP_GBUF = 32768;  // one step of G: 256 K rows x 128 bytes
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // same offset in the even (leader) CTA of the pair
 
 struct PairSmem {
-  static constexpr uint32_t x_off = 0;  // num_kb * 8 KB  (64 self rows)
-  static constexpr uint32_t g_off(int num_kb) { return num_kb * 8192; }                 // BP_NBUF buffers x 16 KB
-  static constexpr uint32_t ring_off(int num_kb) { return g_off(num_kb) + BP_NBUF * 16384; }
+  static constexpr uint32_t x_off = 0;                                                   // num_kb * 8 KB: 64 self rows
+  static constexpr uint32_t g_off(int num_kb) { return num_kb * 8192; }                  // 2 buffers x 32 KB
+  static constexpr uint32_t ring_off(int num_kb) { return g_off(num_kb) + 2 * BP_GBUF; }
   static constexpr uint32_t bar_off(int num_kb) { return ring_off(num_kb) + BP_STAGES * BP_SLOT; }
-  static constexpr uint32_t bj_off(int num_kb) { return bar_off(num_kb) + 256; }  // 2 x 128 floats
-  static constexpr uint32_t total(int num_kb) { return bj_off(num_kb) + 1024 + 1024; }
+  static constexpr uint32_t col_off(int num_kb) { return bar_off(num_kb) + 256; }        // [lse_i | wo_i][128] floats
+  static constexpr uint32_t total(int num_kb) { return col_off(num_kb) + 1024 + 1024; }
 };
 
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_result_addr, uint32_t ncols) {
@@ -76,6 +78,29 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtenso
       : "memory");
 }
 
+// Optional wait-time accounting of the first cluster (make trace): cycles each role spends in each wait.
+__device__ unsigned long long g_pair_trace[32];
+#ifdef TCL_PAIR_TRACE
+#define TR_DECL unsigned long long tr_t0 = 0; const bool tr_on = blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0; (void)tr_t0;
+#endif
+#if defined(TCL_PAIR_TRACE) && TCL_PAIR_TRACE >= 2
+#define TR_BEGIN() do { if (tr_on) tr_t0 = clock64(); } while (0)
+#define TR_END(slot) do { if (tr_on) atomicAdd(&g_pair_trace[(slot) + 16 * (blockIdx.x & 1)], clock64() - tr_t0); } while (0)
+#else
+#ifndef TCL_PAIR_TRACE
+#define TR_DECL
+#endif
+#define TR_BEGIN() do {} while (0)
+#define TR_END(slot) do {} while (0)
+#endif
+// Timing experiments (never in the product build): TCL_PAIR_EXP 1 = MMA thread ignores the `full` barriers,
+// 2 = also no ring traffic at all (no TMA loads, no commits to `empty`), 3 = also no epilogue handshakes.
+#ifndef TCL_PAIR_EXP
+#define TCL_PAIR_EXP 0
+#endif
+// slots (+16 for the peer CTA): 0 producer empty-wait, 1 mma s_empty, 2 mma full (S), 3 mma g_full, 4 mma full (A),
+// 5 mma total, 12 mma issue (S), 13 commits, 14 mma issue (A), 6 epi s_full wait, 7 epi g_empty wait, 8 epi tmem-ld, 9 epi compute+stores, 10 epi fence+arrive, 11 epi total
+
 template <int kOp>
 __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -91,29 +116,32 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __
   auto empty_bar = [&](int s) { return bars + 8u * (BP_STAGES + s); };
   const uint32_t x_full_bar = bars + 8u * (2 * BP_STAGES);
   auto s_full_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 1 + b); };
-  auto s_empty_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 1 + BP_NBUF + b); };
-  auto g_full_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 1 + 2 * BP_NBUF + b); };
-  auto g_empty_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 1 + 3 * BP_NBUF + b); };
-  const uint32_t acc_full_bar = bars + 8u * (2 * BP_STAGES + 1 + 4 * BP_NBUF);
-  const uint32_t tmem_slot = bars + 8u * (2 * BP_STAGES + 2 + 4 * BP_NBUF);
+  auto s_empty_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 3 + b); };
+  auto g_full_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 5 + b); };
+  auto g_empty_bar = [&](int b) { return bars + 8u * (2 * BP_STAGES + 7 + b); };
+  const uint32_t acc_full_bar = bars + 8u * (2 * BP_STAGES + 9);
+  const uint32_t tmem_slot = bars + 8u * (2 * BP_STAGES + 10);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      base_ptr + PairSmem::bar_off(num_kb) + 8u * (2 * BP_STAGES + 2 + 4 * BP_NBUF));
-  float* bj = reinterpret_cast<float*>(base_ptr + PairSmem::bj_off(num_kb));  // [2][128]
+      base_ptr + PairSmem::bar_off(num_kb) + 8u * (2 * BP_STAGES + 10));
+  float* colc = reinterpret_cast<float*>(base_ptr + PairSmem::col_off(num_kb));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TR_DECL
   const uint32_t crank = cluster_ctarank();  // 0 = leader
   const bool leader = crank == 0;
   const int ib = blockIdx.x >> 1;  // the pair = two CTAs adjacent in x (cluster dims (2,1,1))
   const int split = blockIdx.y;
   const BwdJobDev& J = P.job[blockIdx.z];
-  const int i0 = ib * BW_BM;                          // first self row of the pair
-  const int i0_own = i0 + static_cast<int>(crank) * 64;  // first self row of this CTA
-  const int n_chunk = (P.dim + 255) / 256;            // accumulators per CTA (dim rows [256c + 128 rank, +128))
+  const int i0 = ib * BW_BM;                             // first self row of the pair
+  const int i0_own = i0 + static_cast<int>(crank) * 64;  // first of the 64 self rows resident in this CTA
+  const int n_chunk = (P.dim + 255) / 256;               // accumulators per CTA (dim rows [256c + 128 rank, +128))
   const int total_tiles = J.n_seg * P.n_jtiles;
-  const int t_begin = static_cast<int>((static_cast<int64_t>(total_tiles) * split) / P.n_split);
-  const int t_end = static_cast<int>((static_cast<int64_t>(total_tiles) * (split + 1)) / P.n_split);
-  const int n_tiles = t_end - t_begin;
-  const int n_sslot = (num_kb + 1) / 2;  // ring slots per logit tile: two 8 KB K-blocks per 16 KB slot
+  const int total_steps = (total_tiles + 1) / 2;
+  const int u_begin = static_cast<int>((static_cast<int64_t>(total_steps) * split) / P.n_split);
+  const int u_end = static_cast<int>((static_cast<int64_t>(total_steps) * (split + 1)) / P.n_split);
+  const int n_steps = u_end - u_begin;
+  // tile of CTA h in step u: 2u + h (one past the end in the last step of an odd tile count: contributes nothing)
+  auto tile_of = [&](int u, int h) { return 2 * (u_begin + u) + h; };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&J.tm_self);
@@ -126,7 +154,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __
       mbar_init(empty_bar(s), 1);  // one multicast commit
     }
     mbar_init(x_full_bar, 1);
-    for (int b = 0; b < BP_NBUF; ++b) {
+    for (int b = 0; b < 2; ++b) {
       mbar_init(s_full_bar(b), 1);
       mbar_init(s_empty_bar(b), 2 * BW_EPI_WARPS);  // leader's: epilogue warps of both CTAs
       mbar_init(g_full_bar(b), 2 * BW_EPI_WARPS);   // leader's
@@ -144,11 +172,13 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tmem_acc = tmem + BP_NBUF * 64;  // logit buffers: 3 x 64 columns; accumulators behind them (2 x 128)
+  const uint32_t tmem_acc = tmem + 256;  // logit buffers: columns [0,128) and [128,256); accumulators [256,512)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (elect_one() && n_tiles > 0) {
+    // Ring slots hold TWO 16 KB operand blocks (8 MMAs per full/empty handshake): the per-slot wait + commit
+    // latency of the single MMA thread is what keeps 64-cycle MMAs off the tensor-core floor.
+    if (elect_one() && n_steps > 0) {
       const uint32_t x_full_leader = x_full_bar & kPeerBitMask;
       if (leader) mbar_arrive_expect_tx(x_full_bar, 2 * num_kb * 8192);
       for (int kb = 0; kb < num_kb; ++kb)
@@ -157,105 +187,158 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __
       auto acquire = [&](uint32_t pair_bytes) -> int {
         const int s = it % BP_STAGES;
         const uint32_t ph = (it / BP_STAGES) & 1;
-        mbar_wait_cluster(empty_bar(s), ph ^ 1);
+        TR_BEGIN();
+        mbar_wait(empty_bar(s), ph ^ 1);
+        TR_END(0);
         if (leader) mbar_arrive_expect_tx(full_bar(s), pair_bytes);
         ++it;
         return s;
       };
-      auto load_s = [&](int t) {  // this CTA's 64 rows of the other-tile (N half), two K-blocks per slot
-        const int tt = t_begin + t;
-        const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
-        const int j0 = (tt % P.n_jtiles) * BW_BN + static_cast<int>(crank) * 64;
-        for (int st = 0; st < n_sslot; ++st) {
-          const int nk = (2 * st + 1 < num_kb) ? 2 : 1;
-          const int s = acquire(2 * nk * 8192);
-          for (int u = 0; u < nk; ++u)
-            tma_load_2d_2sm(ring + s * BP_SLOT + u * 8192, &sg.tm_other, full_bar(s) & kPeerBitMask,
-                            (2 * st + u) * BW_BK, j0);
+      auto load_s = [&](int u) {  // A operand of the logit MMA: this CTA's tile of the other operand, all of K
+        const int t_own = tile_of(u, static_cast<int>(crank));
+        const bool own_ok = t_own < total_tiles;
+        const bool peer_ok = tile_of(u, static_cast<int>(crank) ^ 1) < total_tiles;
+        for (int kb = 0; kb < num_kb; kb += 2) {
+          const int nk = kb + 1 < num_kb ? 2 : 1;
+          const int s = acquire(static_cast<uint32_t>(nk) * ((own_ok ? BP_BLK : 0) + (peer_ok ? BP_BLK : 0)));
+          if (own_ok) {
+            const BwdSegDev& sg = J.seg[t_own / P.n_jtiles];
+            for (int k2 = 0; k2 < nk; ++k2)
+              tma_load_2d_2sm(ring + s * BP_SLOT + k2 * BP_BLK, &sg.tm_other, full_bar(s) & kPeerBitMask,
+                              (kb + k2) * BW_BK, (t_own % P.n_jtiles) * BW_BN);
+          }
         }
       };
-      auto load_a = [&](int t) {  // transposed other operand: this CTA's 128 dim rows of each accumulator chunk
-        const int tt = t_begin + t;
-        const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
-        const int j0 = (tt % P.n_jtiles) * BW_BN;
-        for (int kb2 = 0; kb2 < 2; ++kb2)
-          for (int c = 0; c < n_chunk; ++c) {
-            const int s = acquire(2 * BP_SLOT);
-            tma_load_2d_2sm(ring + s * BP_SLOT, &sg.tm_other_t, full_bar(s) & kPeerBitMask, j0 + kb2 * BW_BK,
-                            c * 256 + static_cast<int>(crank) * 128);
+      auto load_a = [&](int u) {  // A operand of the gradient MMA: transposed other operand, this CTA's 128 dim rows
+        for (int h = 0; h < 2; ++h) {
+          const int tt = tile_of(u, h);
+          if (tt >= total_tiles) break;  // both CTAs and the MMA issuer skip the missing tile identically
+          const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
+          const int j0 = (tt % P.n_jtiles) * BW_BN;
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            const int s = acquire(static_cast<uint32_t>(n_chunk) * 2 * BP_BLK);
+            for (int c = 0; c < n_chunk; ++c)
+              tma_load_2d_2sm(ring + s * BP_SLOT + c * BP_BLK, &sg.tm_other_t, full_bar(s) & kPeerBitMask,
+                              j0 + kb2 * BW_BK, c * 256 + static_cast<int>(crank) * 128);
           }
+        }
       };
-      // same order as the MMA issuer consumes: S(0), S(1), [S(t+2), A(t)] ...
-      load_s(0);
-      if (n_tiles > 1) load_s(1);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 2 < n_tiles) load_s(t + 2);
-        load_a(t);
+#if TCL_PAIR_EXP == 4
+      // second issuing thread: all gradient-shaped MMAs, no synchronisation at all (issue-rate experiment)
+      if (leader) {
+        const unsigned long long t0 = clock64();
+        for (int u = 0; u < n_steps; ++u)
+          for (int g8 = 0; g8 < 4; ++g8)
+            for (int c = 0; c < n_chunk; ++c) {
+              const uint64_t ad = umma_desc_k_sw128(ring + c * BP_BLK);
+              const uint64_t bd = umma_desc_k_sw128(g_smem + g8 * 8192);
+#pragma unroll
+              for (int kk = 0; kk < BW_BK / 16; ++kk)
+                tc_mma_f16_2sm(tmem_acc + c * 128, ad + 2 * kk, bd + 128 * kk, P.idesc_m256_bmn, 1);
+            }
+        tc_commit_2sm(acc_full_bar, 0x3);
+        if (tr_on) atomicAdd(&g_pair_trace[4], clock64() - t0);
       }
+#elif TCL_PAIR_EXP < 2
+      load_s(0);
+      for (int u = 0; u < n_steps; ++u) {
+        if (u + 1 < n_steps) load_s(u + 1);
+        load_a(u);
+      }
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && elect_one() && n_tiles > 0) {
-      mbar_wait_cluster(x_full_bar, 0);
+    if (leader && elect_one() && n_steps > 0) {
+      mbar_wait(x_full_bar, 0);
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long tr_mma0 = clock64();
+#endif
       int it = 0;
-      auto issue_s = [&](int t) {
-        const int b = t % BP_NBUF;
-        mbar_wait_cluster(s_empty_bar(b), ((t / BP_NBUF) & 1) ^ 1);
+      auto issue_s = [&](int u) {
+        const int b = u & 1;
+        TR_BEGIN();
+        if (TCL_PAIR_EXP < 3) mbar_wait(s_empty_bar(b), ((u >> 1) & 1) ^ 1);
+        TR_END(1);
         tc_fence_after();
-        for (int st = 0; st < n_sslot; ++st, ++it) {
+        for (int kb = 0; kb < num_kb; kb += 2, ++it) {
           const int s = it % BP_STAGES;
           const uint32_t ph = (it / BP_STAGES) & 1;
-          mbar_wait_cluster(full_bar(s), ph);
+          const int nk = kb + 1 < num_kb ? 2 : 1;
+          TR_BEGIN();
+          if (TCL_PAIR_EXP < 1) mbar_wait(full_bar(s), ph);
+          TR_END(2);
           tc_fence_after();
-          const int nk = (2 * st + 1 < num_kb) ? 2 : 1;
-          for (int u = 0; u < nk; ++u) {
-            const int kb = 2 * st + u;
-            const uint64_t ad = umma_desc_k_sw128(x_smem + kb * 8192);
-            const uint64_t bd = umma_desc_k_sw128(ring + s * BP_SLOT + u * 8192);
+          TR_BEGIN();
+          for (int k2 = 0; k2 < nk; ++k2) {
+            const uint64_t ad = umma_desc_k_sw128(ring + s * BP_SLOT + k2 * BP_BLK);  // 128 other rows per CTA (M = 256)
+            const uint64_t bd = umma_desc_k_sw128(x_smem + (kb + k2) * 8192);         // 64 self rows per CTA (N = 128)
 #pragma unroll
             for (int kk = 0; kk < BW_BK / 16; ++kk)
-              tc_mma_f16_2sm(tmem + b * 64, ad + 2 * kk, bd + 2 * kk, P.idesc, (kb | kk) != 0);  // M=128 (pair), N=128
+              tc_mma_f16_2sm(tmem + b * 128, ad + 2 * kk, bd + 2 * kk, P.idesc_m256, (kb | k2 | kk) != 0);
           }
-          tc_commit_2sm(empty_bar(s), 0x3);
+          TR_END(12);
+          TR_BEGIN();
+          if (TCL_PAIR_EXP < 2) tc_commit_2sm(empty_bar(s), 0x3);
+          TR_END(13);
         }
-        tc_commit_2sm(s_full_bar(b), 0x3);
+        if (TCL_PAIR_EXP < 3) tc_commit_2sm(s_full_bar(b), 0x3);
       };
       issue_s(0);
-      if (n_tiles > 1) issue_s(1);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 2 < n_tiles) issue_s(t + 2);
-        const int gb = t % BP_NBUF;
-        mbar_wait_cluster(g_full_bar(gb), (t / BP_NBUF) & 1);
+      for (int u = 0; u < n_steps; ++u) {
+        if (u + 1 < n_steps) issue_s(u + 1);
+        if (TCL_PAIR_EXP == 4) continue;
+        const int gb = u & 1;
+        TR_BEGIN();
+        if (TCL_PAIR_EXP < 3) mbar_wait_cluster(g_full_bar(gb), (u >> 1) & 1);  // acquires the peer's generic-proxy (DSMEM) stores
+        TR_END(3);
         tc_fence_after();
-        for (int kb2 = 0; kb2 < 2; ++kb2) {
-          for (int c = 0; c < n_chunk; ++c, ++it) {
+        for (int h = 0; h < 2; ++h) {
+          if (tile_of(u, h) >= total_tiles) break;
+          for (int kb2 = 0; kb2 < 2; ++kb2, ++it) {
+            // B = K rows h*128 + kb2*64 .. +63 of this step's G buffer: MN-major, 128 bytes per K row, so one
+            // UMMA_K (16 K rows) advances the start address by 2048 bytes
+            const uint32_t gk = g_smem + gb * BP_GBUF + (h * 128 + kb2 * 64) * 128;
             const int s = it % BP_STAGES;
             const uint32_t ph = (it / BP_STAGES) & 1;
-            mbar_wait_cluster(full_bar(s), ph);
+            TR_BEGIN();
+            if (TCL_PAIR_EXP < 1) mbar_wait(full_bar(s), ph);
+            TR_END(4);
             tc_fence_after();
-            const uint64_t ad = umma_desc_k_sw128(ring + s * BP_SLOT);                          // 128 dim rows per CTA
-            const uint64_t bd = umma_desc_k_sw128(g_smem + gb * 16384 + kb2 * 8192);            // 64 G rows per CTA
+            TR_BEGIN();
+            for (int c = 0; c < n_chunk; ++c) {
+              const uint64_t ad = umma_desc_k_sw128(ring + s * BP_SLOT + c * BP_BLK);  // 128 dim rows per CTA (M = 256)
+              const uint64_t bd = umma_desc_k_sw128(gk);  // same descriptor fields; B is MN-major in the idesc
 #pragma unroll
-            for (int kk = 0; kk < BW_BK / 16; ++kk)
-              tc_mma_f16_2sm(tmem_acc + c * 128, ad + 2 * kk, bd + 2 * kk, P.idesc_m256, (t | kb2 | kk) != 0);  // M=256, N=128
-            tc_commit_2sm(empty_bar(s), 0x3);
+              for (int kk = 0; kk < BW_BK / 16; ++kk)
+                tc_mma_f16_2sm(tmem_acc + c * 128, ad + 2 * kk, bd + 128 * kk, P.idesc_m256_bmn,
+                               (u | h | kb2 | kk) != 0);
+            }
+            TR_END(14);
+            TR_BEGIN();
+            if (TCL_PAIR_EXP < 2) tc_commit_2sm(empty_bar(s), 0x3);
+            TR_END(13);
           }
         }
-        tc_commit_2sm(g_empty_bar(gb), 0x3);
+        if (TCL_PAIR_EXP < 3) tc_commit_2sm(g_empty_bar(gb), 0x3);
       }
-      tc_commit_2sm(acc_full_bar, 0x3);
+      if (TCL_PAIR_EXP != 4) tc_commit_2sm(acc_full_bar, 0x3);
+#ifdef TCL_PAIR_TRACE
+      if (tr_on) {
+        atomicAdd(&g_pair_trace[5], clock64() - tr_mma0);
+        atomicAdd(&g_pair_trace[15], static_cast<unsigned long long>(n_steps));
+      }
+#endif
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs)
-    // 2-SM M=128 accumulator of one CTA: TMEM lane L holds self row (L % 64); tile columns (L / 64) * 64 + [0,64)
-    // sit in the buffer's 64 TMEM columns.  Two warps per lane quarter split those 64 columns.
+    // Accumulator of this CTA: S^T of its own tile, TMEM lane = column j of the logits, TMEM column = self row i.
+    // Two warps per lane quarter; each handles 32 self rows of BOTH row halves: first the half that belongs to the
+    // peer's G buffer (its DSMEM stores then drain while the second half is computed), then the local half.
     const int q = warp & 3;
-    const int ch = (warp - 2) >> 2;                 // 32-column half of the 64 TMEM columns
-    const int tl = q * 32 + lane;                   // TMEM lane
-    const int r = tl & 63;                          // self row inside this CTA's 64
-    const int chalf = tl >> 6;                      // which 64-column half of the tile (== G K-block)
-    const int et = threadIdx.x - 64;                // 0..255
-    const int grow = i0_own + r;                    // local self row index
+    const int ch = (warp - 2) >> 2;
+    const int jl = q * 32 + lane;     // tile-local column j == TMEM lane
+    const int et = threadIdx.x - 64;  // 0..255
     float gs[2] = {0.f, 0.f};
     float gmax = 0.f;
     for (int s = 0; s < J.n_seg; ++s) {
@@ -265,95 +348,117 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __
     const float inv_gmax = gmax > 0.f ? 1.f / gmax : 0.f;
     if (blockIdx.x == 0 && blockIdx.y == 0 && et == 0) *J.scale_out = gmax * P.out_scale;  // one CTA per job
 
-    auto load_bj = [&](int t) -> float {
-      if (et >= 128 || t >= n_tiles) return 0.f;
-      const int tt = t_begin + t;
-      const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
-      const int j = (tt % P.n_jtiles) * BW_BN + et;
-      return j < P.n_other ? ex2_approx(P.c1 - sg.lse2_other[j]) : 0.f;
-    };
-    if (et < 128 && n_tiles > 0) bj[et] = load_bj(0);
     int cur_seg = -1;
-    float lse_i = 0.f, ws = 0.f, wo_i = 0.f, rr = 0.f;
+    uint8_t* g_local_ptr = base_ptr + PairSmem::g_off(num_kb);
+    const uint32_t g_peer = map_to_peer(g_smem, crank ^ 1u);
     const uint32_t s_empty_leader0 = map_to_peer(s_empty_bar(0), 0);  // barriers are 8 bytes apart
     const uint32_t g_full_leader0 = map_to_peer(g_full_bar(0), 0);
+    const int krow = static_cast<int>(crank) * 128 + jl;  // K row of this thread inside a step's G buffer
+    const int col_far = static_cast<int>(crank ^ 1u) * 64 + ch * 32;  // first self row (pair-local) of the far part
+    const int col_near = static_cast<int>(crank) * 64 + ch * 32;
 
-    for (int t = 0; t < n_tiles; ++t) {
-      const int tt = t_begin + t;
-      const int si = tt / P.n_jtiles;
-      const int j0 = (tt % P.n_jtiles) * BW_BN;
-      const int b = t % BP_NBUF;
-      const uint32_t bpar = (t / BP_NBUF) & 1;
-      if (si != cur_seg) {
-        const BwdSegDev& sg = J.seg[si];
+    for (int u = 0; u < (TCL_PAIR_EXP < 3 ? n_steps : 0); ++u) {
+      const int tt = tile_of(u, static_cast<int>(crank));
+      const bool tile_ok = tt < total_tiles;
+      const int si = tile_ok ? tt / P.n_jtiles : (cur_seg < 0 ? 0 : cur_seg);
+      const BwdSegDev& sg = J.seg[si];
+      const int j0 = tile_ok ? (tt % P.n_jtiles) * BW_BN : 0;
+      const int b = u & 1;
+      const uint32_t bpar = (u >> 1) & 1;
+      const float rr = si == 0 ? gs[0] * inv_gmax : gs[1] * inv_gmax;
+      const float ws = rr * sg.w_self;
+      if (si != cur_seg) {  // uniform over the CTA: per-self-row constants of the segment, one row per thread
         cur_seg = si;
-        rr = gs[si] * inv_gmax;
-        lse_i = grow < P.n_self ? sg.lse2_self[grow] : 0.f;
-        ws = rr * sg.w_self;
-        wo_i = rr * sg.w_other * ex2_approx(lse_i - P.c1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous segment's constants
+        if (et < 128) {
+          const int gi = i0 + et;
+          const float l = gi < P.n_self ? sg.lse2_self[gi] : 0.f;
+          colc[et] = l;
+          colc[128 + et] = rr * sg.w_other * ex2_approx(l - P.c1);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const float bj_next = load_bj(t + 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int ccol0 = chalf * 64 + ch * 32;  // first tile column of this thread's 32
-      const float* bjt = bj + (t & 1) * 128 + ccol0;
-      const int dl = P.self_offset + grow - j0 - ccol0;  // column of the positive inside our 32 (if any)
+      const int j = j0 + jl;
+      const float bj = (tile_ok && j < P.n_other) ? ex2_approx(P.c1 - sg.lse2_other[j]) : 0.f;
+      const int dpos = j - P.self_offset - i0;  // pair-local self row of this column's positive (if in [0,128))
+      const uint32_t off_row = static_cast<uint32_t>(b * BP_GBUF + krow * 128);
 
-      mbar_wait_cluster(s_full_bar(b), bpar);
+      TR_BEGIN();
+      mbar_wait(s_full_bar(b), bpar);
+      TR_END(6);
+      TR_BEGIN();
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_addr(tmem + b * 64, q * 32, ch * 32), v);
+      uint32_t vf[32], vn[32];
+      tmem_ld_32x32b_x32(tmem_addr(tmem + b * 128, q * 32, col_far), vf);
+      tmem_ld_32x32b_x32(tmem_addr(tmem + b * 128, q * 32, col_near), vn);
       tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {  // logit buffer drained: tell the leader's MMA thread
-        if (leader) mbar_arrive(s_empty_bar(b)); else mbar_arrive_remote(s_empty_leader0 + 8u * b);
+      if (lane == 0) {  // logit buffer drained: tell the leader's MMA thread (orders TMEM reads only: relaxed)
+        if (leader) mbar_arrive(s_empty_bar(b)); else mbar_arrive_remote_relaxed(s_empty_leader0 + 8u * b);
       }
-      uint32_t pk[16];
+      TR_END(8);
+      // G buffer (u & 1) is free once the gradient MMAs of step u-2 have completed (they read both CTAs' halves)
+      TR_BEGIN();
+      mbar_wait(g_empty_bar(b), bpar ^ 1);
+      TR_END(7);
+      TR_BEGIN();
+      // B operand of the gradient MMA, MN-major: 16-byte chunk c of K row k lives at chunk position (c ^ (k & 7))
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), P.c1, -lse_i));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), P.c1, -lse_i));
-        const float g0 = fmaf(p0, fmaf(wo_i, bjt[e], ws), (e == dl) ? -rr : 0.f);
-        const float g1 = fmaf(p1, fmaf(wo_i, bjt[e + 1], ws), (e + 1 == dl) ? -rr : 0.f);
-        pk[e >> 1] = pack2<kOp>(g0, g1);
+      for (int part = 0; part < 2; ++part) {
+        const int col0 = part == 0 ? col_far : col_near;
+        const float* lse_i = colc + col0;
+        const float* wo_i = colc + 128 + col0;
+        const int dl = dpos - col0;
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float s0 = __uint_as_float(part == 0 ? vf[e] : vn[e]);
+          const float s1 = __uint_as_float(part == 0 ? vf[e + 1] : vn[e + 1]);
+          const float p0 = ex2_approx(fmaf(s0, P.c1, -lse_i[e]));
+          const float p1 = ex2_approx(fmaf(s1, P.c1, -lse_i[e + 1]));
+          const float g0 = fmaf(p0, fmaf(wo_i[e], bj, ws), (e == dl) ? -rr : 0.f);
+          const float g1 = fmaf(p1, fmaf(wo_i[e + 1], bj, ws), (e + 1 == dl) ? -rr : 0.f);
+          pk[e >> 1] = tile_ok ? pack2<kOp>(g0, g1) : 0u;
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t off = off_row + (((ch * 4 + c4) ^ (krow & 7)) << 4);
+          if (part == 0)
+            st_cluster_v4(g_peer + off, pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+          else
+            *reinterpret_cast<uint4*>(g_local_ptr + off) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+        }
       }
-      // G buffer (t % 3) is free once the gradient MMAs of tile t-3 have completed (both CTAs' halves were read)
-      const int gb = b;
-      mbar_wait_cluster(g_empty_bar(gb), bpar ^ 1);
-      // K-major swizzled B operand: K-block = chalf, row r (of 64), 16-byte chunks ch*4 .. ch*4+3
-      uint8_t* grow_ptr = base_ptr + PairSmem::g_off(num_kb) + gb * 16384 + chalf * 8192 + r * 128;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4)
-        *reinterpret_cast<uint4*>(grow_ptr + (((ch * 4 + c4) ^ (r & 7)) << 4)) =
-            make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
-      fence_proxy_async_smem();  // generic-proxy stores -> async proxy (the pair's tensor cores read this buffer)
+      TR_END(9);
+      TR_BEGIN();
+      fence_proxy_async_all();  // generic-proxy stores (local and DSMEM) -> async proxy (tensor cores of both SMs)
       __syncwarp();
       if (lane == 0) {
-        if (leader) mbar_arrive(g_full_bar(gb)); else mbar_arrive_remote(g_full_leader0 + 8u * gb);
+        if (leader) mbar_arrive(g_full_bar(b)); else mbar_arrive_remote(g_full_leader0 + 8u * b);
       }
-      if (et < 128 && t + 1 < n_tiles) bj[((t + 1) & 1) * 128 + et] = bj_next;
+      TR_END(10);
     }
 
-    if (n_tiles > 0) {
-      mbar_wait_cluster(acc_full_bar, 0);
+    if (n_steps > 0) {
+      mbar_wait(acc_full_bar, 0);
       tc_fence_after();
     }
     // accumulator read-out: the accumulator is transposed (TMEM lane = dim row within this CTA's 128 of chunk c,
     // TMEM column = self row), so for a fixed register index the 32 lanes of a warp hold 32 consecutive dim
     // entries of ONE gradient row: every store instruction writes 128 contiguous bytes, no staging needed.
     for (int c = 0; c < n_chunk; ++c) {
-      const int d_base = c * 256 + static_cast<int>(crank) * 128 + q * 32;  // dim index of this warp's lane 0
+      const int d = c * 256 + static_cast<int>(crank) * 128 + q * 32 + lane;
 #pragma unroll 1
       for (int cb = ch * 2; cb < ch * 2 + 2; ++cb) {  // this warp's two 32-row blocks of the 128 self rows
         uint32_t v[32];
-        if (n_tiles > 0) {
+        if (n_steps > 0) {
           tmem_ld_32x32b_x32(tmem_addr(tmem_acc + c * 128, q * 32, cb * 32), v);
           tc_wait_ld();
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0u;
         }
-        const int d = d_base + lane;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int srow = i0 + cb * 32 + e;
@@ -369,6 +474,21 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_pair_kernel(const __
   if (warp == 1) tmem_dealloc_2sm(tmem, 512);
 }
 
+}  // namespace tcl
+
+extern "C" int tcl_debug_pair_trace(unsigned long long* out32, int reset) {
+  using namespace tcl;
+  TCL_CHECK_CUDA(cudaDeviceSynchronize());
+  if (out32) TCL_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_pair_trace, sizeof(unsigned long long) * 32));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    TCL_CHECK_CUDA(cudaMemcpyToSymbol(g_pair_trace, z, sizeof(z)));
+  }
+  return TCL_OK;
+}
+
+namespace tcl {
+
 int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st) {
   const int smem = static_cast<int>(PairSmem::total(P.num_kb));
   cudaLaunchConfig_t cfg{};
@@ -377,7 +497,7 @@ int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].id = cudaLaunchAttributeClusterDimension;  // the CTA pair of a 2-SM MMA must be adjacent in x
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
@@ -389,15 +509,7 @@ int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format
       TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_pair_kernel<TCL_OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = smem;
     }
-    {
-      cudaError_t le = cudaLaunchKernelEx(&cfg, ntxent_bwd_pair_kernel<TCL_OP_F16>, P);
-      if (le != cudaSuccess) {
-        int ncl = -1;
-        cudaError_t qe = cudaOccupancyMaxActiveClusters(&ncl, ntxent_bwd_pair_kernel<TCL_OP_F16>, &cfg);
-        return set_error(TCL_ERR_CUDA_BASE + (int)le, "pair kernel launch: %s (grid %u,%u,%u smem %d; max active clusters %d, query %s)",
-                         cudaGetErrorString(le), cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, smem, ncl, cudaGetErrorString(qe));
-      }
-    }
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_bwd_pair_kernel<TCL_OP_F16>, P));
   } else {
     static int set = 0;
     if (set < smem) {
