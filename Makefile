@@ -21,9 +21,10 @@ $(LIB): $(OBJS)
 TRACE_LEVEL ?= 2
 EXP ?= 0
 TRACE_LIB ?= tricolo_b200/lib/libtricolo_b200_trace.so
+TRACE_DEFS ?=
 trace:
 	@mkdir -p build_trace
-	for f in $(SRCS); do $(NVCC) $(NVCCFLAGS) -DTCL_PAIR_TRACE=$(TRACE_LEVEL) -DTCL_PAIR_EXP=$(EXP) -c $$f -o build_trace/$$(basename $$f .cu).o 2> /dev/null || exit 1; done
+	for f in $(SRCS); do $(NVCC) $(NVCCFLAGS) -DTCL_PAIR_TRACE=$(TRACE_LEVEL) -DTCL_PAIR_EXP=$(EXP) $(TRACE_DEFS) -c $$f -o build_trace/$$(basename $$f .cu).o 2> /dev/null || exit 1; done
 	$(NVCC) $(ARCH) -shared -o $(TRACE_LIB) build_trace/*.o -cudart shared
 
 clean:

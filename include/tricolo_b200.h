@@ -260,6 +260,10 @@ int tcl_debug_tmem_probe(uint32_t* out, void* stream);
 /* tcl_debug_pair_trace: cycles the roles of the first CTA pair of the pair backward kernel spent in each wait
  * (32 counters, see ntxent_bwd_pair.cu; all zero unless the library was built with `make trace`). */
 int tcl_debug_pair_trace(unsigned long long* out32, int reset);
+/* tcl_debug_pc_trace: the same for the first cluster of the producer/consumer backward kernel (ntxent_bwd_pc.cu). */
+int tcl_debug_pc_trace(unsigned long long* out32, int reset);
+/* tcl_debug_max_clusters: cudaOccupancyMaxActiveClusters for the producer/consumer kernel's footprint. */
+int tcl_debug_max_clusters(int cluster_size, int* out);
 
 #ifdef __cplusplus
 }

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0u;
         }
-        if (grow < P.n_self) {
+        if (grow < P.n_self && d0 + cc * 32 < P.dim) {  // dim % 128 != 0: the last chunk is partly outside dim
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
             *reinterpret_cast<float4*>(gout + cc * 32 + e) =
@@ -350,6 +350,7 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   memset(&N, 0, sizeof(N));
   P.n_self = (int)n_self; P.n_other = (int)n_other; P.self_offset = (int)self_offset; P.dim = (int)dim;
   P.num_kb = (int)(dim / 64);
+  P.z_row_stride = z_row_stride;
   P.n_jtiles = (int)((n_other + BW_BN - 1) / BW_BN);
   P.n_dhalf = (int)((dim + BW_DH - 1) / BW_DH);
   const int n_iblocks = (int)((n_self + BW_BM - 1) / BW_BM);
@@ -360,18 +361,24 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   P.out_scale = inv_tau / static_cast<float>(n_other);
   P.idesc = umma_idesc_f16(BW_BM, BW_BN, op_format);
   P.idesc_n64 = umma_idesc_f16(BW_BM, 64, op_format);
-  // dim > 256: the two dim-half CTAs can run as a 2-CTA cluster that shares the logit recompute through
-  // DSMEM (ntxent_bwd_cluster.cu, 8 instead of 12 B^2 D executed).  Correct, but measured SLOWER on B200
-  // (1.22 ms vs 1.00 ms at B=8192x3): the 16 KB/tile G exchange sits on the per-tile critical path at the
-  // ~20 B/clk DSMEM rate and the N=64 logit MMAs are shared-memory-bound.  Kept behind an opt-in switch.
-  static const bool want_cluster = getenv("TRICOLO_B200_BWD_CLUSTER") != nullptr;
-  const bool use_cluster = P.n_dhalf == 2 && want_cluster;
-  // Default for dim > 256: the CTA-pair kernel (ntxent_bwd_pair.cu) — both GEMMs as 2-SM M=256 MMAs, the logit
-  // tile is recomputed once per (row block, column tile); TRICOLO_B200_BWD_NOPAIR=1 selects the independent-CTA kernel.
-  static const bool no_pair = getenv("TRICOLO_B200_BWD_NOPAIR") != nullptr;
-  const bool use_pair = P.n_dhalf == 2 && !want_cluster && !no_pair;
+  // dim > 256 has four implementations, all behind the same ABI (TRICOLO_B200_BWD=pc|pair|cluster|indep):
+  //  pc      (default) producer/consumer 2-CTA cluster, ntxent_bwd_pc.cu: logit recompute on one SM, gradient GEMM
+  //          with a full-dim accumulator on the other; 8 B^2 D executed per pair.
+  //  pair    ntxent_bwd_pair.cu: both GEMMs as 2-SM M=256 MMAs, G halves exchanged both ways through DSMEM.
+  //  cluster ntxent_bwd_cluster.cu: the two dim-half CTAs share the logit recompute through DSMEM (N=64 MMAs);
+  //          correct but slower than `indep` (1.22 ms vs 1.00 ms at B=8192x3).
+  //  indep   the kernel above: one CTA per dim half, logits recomputed per half (12 B^2 D executed).
+  static const char* mode_env = getenv("TRICOLO_B200_BWD");
+  static const bool want_cluster = getenv("TRICOLO_B200_BWD_CLUSTER") != nullptr || (mode_env && !strcmp(mode_env, "cluster"));
+  static const bool want_indep = getenv("TRICOLO_B200_BWD_NOPAIR") != nullptr || (mode_env && !strcmp(mode_env, "indep"));
+  static const bool want_pair = mode_env && !strcmp(mode_env, "pair");
+  const bool wide = P.n_dhalf == 2;
+  const bool use_cluster = wide && want_cluster;
+  const bool use_pair = wide && !use_cluster && want_pair;
+  const bool use_pc = wide && !use_cluster && !use_pair && !want_indep;
   P.idesc_m256 = umma_idesc_f16(256, BW_BN, op_format);
   P.idesc_m256_bmn = P.idesc_m256 | (1u << 16);
+  P.idesc_n256 = umma_idesc_f16(BW_BM, 256, op_format);
   // the pair kernel walks the column tiles two at a time
   P.n_split = use_pair ? bwd_split(n_jobs, n_iblocks, 2, (min_seg * P.n_jtiles + 1) / 2)
                        : bwd_split(n_jobs, n_iblocks, P.n_dhalf, min_seg * P.n_jtiles);
@@ -385,11 +392,12 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     TCL_REQUIRE(src.z_self && src.x_self && src.inv_norm && src.dx, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d", j);
     if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, z_row_stride, use_pair ? 64 : BW_BM, BW_BK)) return e;
     J.n_seg = src.n_segments;
+    J.z_self = static_cast<const uint16_t*>(src.z_self);
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
       TCL_REQUIRE(sg.z_other && sg.z_other_t && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
       if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, use_cluster ? 64 : BW_BN, BW_BK)) return e;
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, 128, BW_BK)) return e;
+      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, use_pc ? 256 : 128, BW_BK)) return e;
       J.seg[s].lse2_self = sg.lse2_self;
       J.seg[s].lse2_other = sg.lse2_other;
       J.seg[s].grad_scale = sg.grad_scale;
@@ -408,7 +416,9 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(n_iblocks, P.n_dhalf * P.n_split, n_jobs);
   prof_begin(TCL_K_NTXENT_BWD, st);
-  if (use_pair) {
+  if (use_pc) {
+    if (int e = launch_bwd_pc(P, n_iblocks, n_jobs, op_format, st)) return e;
+  } else if (use_pair) {
     if (int e = launch_bwd_pair(P, n_iblocks, n_jobs, op_format, st)) return e;
   } else if (use_cluster) {
     if (int e = launch_bwd_cluster(P, n_iblocks, n_jobs, op_format, st)) return e;

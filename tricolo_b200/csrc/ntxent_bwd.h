@@ -15,7 +15,7 @@ static constexpr int BW_DH = 256;  // dim columns per CTA
 
 struct BwdSegDev {
   CUtensorMap tm_other;    // [n_other, dim]   box {64, 128} (cluster kernel: {64, 64})
-  CUtensorMap tm_other_t;  // [dim, n_other]   box {64, 128}
+  CUtensorMap tm_other_t;  // [dim, n_other]   box {64, 128} (producer/consumer kernel: {64, 256})
   const float* lse2_self;
   const float* lse2_other;
   const float* grad_scale;
@@ -24,6 +24,7 @@ struct BwdSegDev {
 struct BwdJobDev {
   CUtensorMap tm_self;  // [n_self, dim] box {64, 128}
   BwdSegDev seg[2];
+  const uint16_t* z_self;  // raw pointer of the self operand (producer/consumer kernel: loaded into TMEM)
   float* gpart;      // [n_split][n_self][dim]
   float* scale_out;  // device scalar consumed by the normalise backward
   int n_seg;
@@ -32,12 +33,14 @@ struct BwdParams {
   BwdJobDev job[TCL_MAX_TENSORS];
   int n_self, n_other, self_offset, dim;
   int num_kb, n_jtiles, n_split, n_dhalf;
+  int64_t z_row_stride;  // elements
   float c1;         // log2(e)/tau
   float out_scale;  // 1/(tau*n_other)
   uint32_t idesc;   // M=128, N=128
   uint32_t idesc_n64;  // M=128, N=64 (cluster kernel: half logit tile)
   uint32_t idesc_m256;      // M=256 (CTA pair), N=128, both operands K-major (pair kernel: logit MMA)
   uint32_t idesc_m256_bmn;  // same with an MN-major B operand (pair kernel: gradient MMA)
+  uint32_t idesc_n256;      // M=128, N=256 (producer/consumer kernel: gradient MMA)
 };
 
 struct BwdSmem {
@@ -62,6 +65,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // ntxent_bwd_pair.cu
 int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
+// ntxent_bwd_pc.cu
+int launch_bwd_pc(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 // ntxent_bwd_cluster.cu
 int launch_bwd_cluster(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 

@@ -1,0 +1,557 @@
+// K3, producer/consumer form (dim > 256): the backward of tricolo/loss/nt_xent.py:55-74 with the logit
+// recompute and the gradient GEMM on DIFFERENT SMs of a 2-CTA cluster.
+//
+// Why: the fp32 gradient accumulator of 128 self rows x dim 512 fills all 512 TMEM columns of an SM, so a single
+// CTA cannot hold it next to the logit buffers (ntxent_bwd.cu splits dim and recomputes the logits twice; the
+// pair kernel exchanges G both ways on the per-tile critical path).  Here the two roles get one SM each:
+//   producer CTA (cluster rank 0)   S = Zself[128 rows] · Zother[tile]^T into two 128-column TMEM buffers.  The
+//                                   self block is the A operand and stays resident IN TMEM (128 lanes x dim/2
+//                                   columns, written once by tcgen05.st), so shared memory holds only the
+//                                   operand ring and the G staging slots.  The epilogue warps turn S into the
+//                                   16-bit gradient weights G' (same formula as ntxent_bwd.cu), store them in
+//                                   the K-major swizzled operand layout into a local staging slot, and one
+//                                   thread per 16 KB K-block pushes it into the consumer's shared memory with
+//                                   a bulk DSMEM copy (cp.async.bulk.shared::cluster) that completes on the
+//                                   consumer's mbarrier.  (Direct st.shared::cluster stores were measured at
+//                                   ~6 B/clk for this access pattern: 5600 cycles per 32 KB tile.)
+//   consumer CTA (cluster rank 1)   acc[128 rows x dim] += G'[128 x 128] · Zother[tile]  with the whole 512-column
+//                                   TMEM as accumulator: M=128, N=256 MMAs, A = a G slot, B = the transposed
+//                                   operand streamed by its own TMA ring.
+// Both SMs run 2·128·128·dim flop per tile: the work is balanced, nothing is recomputed twice (8 B^2 D executed
+// per pair, the count of a recompute backward) and the 32 KB/tile G hand-over is one-way and three slots deep,
+// i.e. off the critical path.  Hand-shakes: producer -> consumer MMA thread: the copies' complete_tx on g_full[slot]
+// (armed with arrive.expect_tx by the consumer itself: a remote release-arrive cost ~1800 cycles per tile); consumer -> producer: tcgen05.commit multicast onto the producer's g_empty[slot]
+// once the MMAs that read the slot have completed (which also frees the staging slot of the same index).
+#include "ntxent_bwd.h"
+#include "../../include/tricolo_b200.h"
+
+namespace tcl {
+
+#ifndef TCL_PC_PSTAGES
+#define TCL_PC_PSTAGES 4
+#endif
+// Timing experiments (never in the product build): TCL_PC_EXP 1 = the producer's ring is never loaded or waited for
+// (logit MMAs on stale shared memory), 2 = the same for the consumer's ring as well.
+#ifndef TCL_PC_EXP
+#define TCL_PC_EXP 0
+#endif
+static constexpr int PC_PSTAGES = TCL_PC_PSTAGES;  // producer ring: slots of two 16 KB K-blocks of the other operand
+static constexpr int PC_CSTAGES = 4;     // consumer ring: slots of {64 K x 256 dim rows} of the transposed operand
+static constexpr int PC_SLOT = 32768;
+static constexpr int PC_GSLOTS = 3;      // G tiles in flight (128 rows x 128 K, two K-blocks of 16 KB)
+static constexpr int PC_SBUFS = 2;       // logit buffers in the producer's TMEM (columns 0..255; the self block: 256..)
+static constexpr int PC_XCOL = 256;      // first TMEM column of the resident self block
+static constexpr int PC_EPI_WARPS = 16;  // two groups of 8: group g handles the tiles t = g (mod 2) (logit buffer g)
+static constexpr int PC_THREADS = 64 + PC_EPI_WARPS * 32;
+
+struct PcSmem {
+  // producer: [G staging 3 x 32 KB][ring 3 x 32 KB];  consumer: [G 3 x 32 KB][ring 4 x 32 KB]
+  static constexpr uint32_t p_stage_off = 0;
+  static constexpr uint32_t p_ring_off = PC_GSLOTS * PC_SLOT;
+  static constexpr uint32_t c_g_off = 0;
+  static constexpr uint32_t c_ring_off = PC_GSLOTS * PC_SLOT;
+  static constexpr uint32_t buf_bytes(int) {
+    return (PC_GSLOTS + (PC_CSTAGES > PC_PSTAGES ? PC_CSTAGES : PC_PSTAGES)) * PC_SLOT;
+  }
+  static constexpr uint32_t bar_off(int num_kb) { return buf_bytes(num_kb); }   // same offset in both CTAs
+  static constexpr uint32_t bj_off(int num_kb) { return bar_off(num_kb) + 512; }  // [2 groups][128] floats
+  static constexpr uint32_t total(int num_kb) { return bj_off(num_kb) + 1024 + 1024; }
+};
+static_assert(PcSmem::total(8) <= 232448, "producer/consumer backward: shared memory budget");
+
+// Optional wait-time accounting of the first cluster (make trace; profiles/pc_trace.py): cycles per role and wait.
+// slots: 0 P-tma p_empty | 1 P-mma s_empty, 2 P-mma p_full, 3 P-mma total | 4 P-epi s_full, 5 P-epi tmem-ld,
+// 6 P-epi math, 7 P-epi g_empty, 8 P-epi stores, 9 P-epi fence+arrive, 10 P-epi total, 11 P-epi bar.sync |
+// 16 C-tma c_empty | 17 C-mma g_full, 18 C-mma c_full, 19 C-mma total | 20 C-epi read-out | 31 tiles
+__device__ unsigned long long g_pc_trace[32];
+#ifdef TCL_PAIR_TRACE
+#define PT_DECL unsigned long long pt_t0 = 0; const bool pt_on = blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) <= 2); (void)pt_t0;
+#define PT_BEGIN() do { if (pt_on) pt_t0 = clock64(); } while (0)
+#define PT_END(slot) do { if (pt_on) { const unsigned long long pt_t1 = clock64(); atomicAdd(&g_pc_trace[slot], pt_t1 - pt_t0); pt_t0 = pt_t1; } } while (0)
+#else
+#define PT_DECL
+#define PT_BEGIN() do {} while (0)
+#define PT_END(slot) do {} while (0)
+#endif
+
+template <int kOp>
+__global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const int num_kb = P.num_kb;
+  const uint32_t bars = base + PcSmem::bar_off(num_kb);
+  auto p_full = [&](int s) { return bars + 8u * (40 + s); };
+  auto p_empty = [&](int s) { return bars + 8u * (32 + s); };
+  const uint32_t x_full_bar = bars + 8u * 6;  // the self block is in TMEM (one arrive per epilogue warp)
+  auto s_full = [&](int b) { return bars + 8u * (7 + b); };
+  auto s_empty = [&](int b) { return bars + 8u * (11 + b); };
+  auto g_empty = [&](int g) { return bars + 8u * (15 + g); };  // lives in the PRODUCER's shared memory
+  auto c_full = [&](int s) { return bars + 8u * (18 + s); };
+  auto c_empty = [&](int s) { return bars + 8u * (22 + s); };
+  auto g_full = [&](int g) { return bars + 8u * (26 + g); };   // lives in the CONSUMER's shared memory
+  const uint32_t acc_full_bar = bars + 8u * 29;
+  const uint32_t tmem_slot = bars + 8u * 30;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + PcSmem::bar_off(num_kb) + 8u * 30);
+  float* bj_all = reinterpret_cast<float*>(base_ptr + PcSmem::bj_off(num_kb));  // [2 groups][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool is_producer = crank == 0;
+  PT_DECL
+  const int ib = blockIdx.x >> 1;  // the cluster = two CTAs adjacent in x
+  const int split = blockIdx.y;
+  const BwdJobDev& J = P.job[blockIdx.z];
+  const int i0 = ib * BW_BM;
+  const int n_chunk = (P.dim + 255) / 256;  // 256-column accumulator chunks of the consumer
+  const int total_tiles = J.n_seg * P.n_jtiles;
+  const int t_begin = static_cast<int>((static_cast<int64_t>(total_tiles) * split) / P.n_split);
+  const int t_end = static_cast<int>((static_cast<int64_t>(total_tiles) * (split + 1)) / P.n_split);
+  const int n_tiles = t_end - t_begin;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&J.tm_self);
+    for (int s = 0; s < J.n_seg; ++s) {
+      tma_prefetch_desc(&J.seg[s].tm_other);
+      tma_prefetch_desc(&J.seg[s].tm_other_t);
+    }
+    for (int s = 0; s < PC_PSTAGES; ++s) {
+      mbar_init(p_full(s), 1);
+      mbar_init(p_empty(s), 1);
+    }
+    mbar_init(x_full_bar, PC_EPI_WARPS);
+    for (int b = 0; b < PC_SBUFS; ++b) {
+      mbar_init(s_full(b), 1);
+      mbar_init(s_empty(b), PC_EPI_WARPS / 2);  // the eight warps of the group that owns the buffer
+    }
+    for (int g = 0; g < PC_GSLOTS; ++g) {
+      mbar_init(g_empty(g), 1);           // one multicast commit from the consumer's MMA thread
+      mbar_init(g_full(g), 1);             // armed (arrive.expect_tx 32 KB) by the consumer's MMA thread; the bytes
+                                           // come from the producer's two bulk copies per tile
+    }
+    for (int s = 0; s < PC_CSTAGES; ++s) {
+      mbar_init(c_full(s), 1);
+      mbar_init(c_empty(s), 1);
+    }
+    mbar_init(acc_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (is_producer) {
+    const uint32_t stage = base + PcSmem::p_stage_off;
+    const uint32_t ring = base + PcSmem::p_ring_off;
+    const uint32_t tmem_x = tmem + PC_XCOL;
+    if (warp == 0) {
+      // -------------------------------------------------------------- producer: TMA warp
+      if (TCL_PC_EXP < 1 && elect_one() && n_tiles > 0) {
+        int it = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+          const int tt = t_begin + t;
+          const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
+          const int j0 = (tt % P.n_jtiles) * BW_BN;
+          for (int kb = 0; kb < num_kb; kb += 2, ++it) {
+            const int nk = kb + 1 < num_kb ? 2 : 1;
+            const int s = it % PC_PSTAGES;
+            PT_BEGIN();
+            mbar_wait(p_empty(s), ((it / PC_PSTAGES) & 1) ^ 1);
+            PT_END(0);
+            mbar_arrive_expect_tx(p_full(s), nk * BW_KB_BYTES);
+            for (int k2 = 0; k2 < nk; ++k2)
+              tma_load_2d(ring + s * PC_SLOT + k2 * BW_KB_BYTES, &sg.tm_other, p_full(s), (kb + k2) * BW_BK, j0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // -------------------------------------------------------------- producer: logit MMAs (A from TMEM)
+      if (elect_one() && n_tiles > 0) {
+        mbar_wait(x_full_bar, 0);
+        tc_fence_after();
+        int it = 0;
+#ifdef TCL_PAIR_TRACE
+        const unsigned long long pt_m0 = clock64();
+#endif
+        for (int t = 0; t < n_tiles; ++t) {
+          const int b = t % PC_SBUFS;
+          PT_BEGIN();
+          mbar_wait(s_empty(b), ((t / PC_SBUFS) & 1) ^ 1);
+          PT_END(1);
+          tc_fence_after();
+          for (int kb = 0; kb < num_kb; kb += 2, ++it) {
+            const int nk = kb + 1 < num_kb ? 2 : 1;
+            const int s = it % PC_PSTAGES;
+            PT_BEGIN();
+            if (TCL_PC_EXP < 1) mbar_wait(p_full(s), (it / PC_PSTAGES) & 1);
+            PT_END(2);
+            tc_fence_after();
+            for (int k2 = 0; k2 < nk; ++k2) {
+              const uint32_t ax = tmem_x + (kb + k2) * (BW_BK / 2);  // 32 columns per K-block of 64
+              const uint64_t bd = umma_desc_k_sw128(ring + s * PC_SLOT + k2 * BW_KB_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BW_BK / 16; ++kk)
+                tc_mma_f16_ts(tmem + b * BW_BN, ax + 8 * kk, bd + 2 * kk, P.idesc, (kb | k2 | kk) != 0);
+            }
+            if (TCL_PC_EXP < 1) tc_commit(p_empty(s));
+          }
+          tc_commit(s_full(b));
+        }
+#ifdef TCL_PAIR_TRACE
+        if (pt_on) { atomicAdd(&g_pc_trace[3], clock64() - pt_m0); atomicAdd(&g_pc_trace[31], (unsigned long long)n_tiles); }
+#endif
+      }
+    } else {
+      // -------------------------------------------------------------- producer: G epilogue (2 groups x 8 warps)
+      // Group gi owns logit buffer gi and the tiles t = gi, gi+2, ...: each group has two tile periods for its
+      // serial chain (wait, TMEM load, math, staging stores, hand-over), so the chain's latencies stay hidden.
+      const int ew = warp - 2;
+      const int gi = ew >> 3;          // group
+      const int q = warp & 3;          // TMEM lane quarter
+      const int ch = (ew >> 2) & 1;    // column half of the logit tile == K-block of the G operand
+      const int r = q * 32 + lane;     // tile-local row == TMEM lane
+      const int gt = (ew & 7) * 32 + lane;  // thread index inside the group, 0..255
+      const int grow = i0 + r;
+      const int bar_grp = 1 + gi;           // named barriers: 1,2 = group; 3..6 = (group, K-block)
+      const int bar_kb = 3 + 2 * gi + ch;
+      float* bj = bj_all + gi * 128;
+      // self block -> TMEM: row = lane, 16-bit element k -> column k/2; this thread: two K-blocks of its row
+      if (n_tiles > 0) {
+        const uint16_t* zrow = J.z_self + static_cast<int64_t>(grow) * P.z_row_stride;
+        const int c0 = (gi * 2 + ch) * 2;
+#pragma unroll 1
+        for (int c32 = c0; c32 < c0 + 2; ++c32) {  // 32 columns = 64 elements = one K-block
+          if (c32 >= num_kb) break;
+          uint32_t xv[32];
+          if (grow < P.n_self) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint4 u = *reinterpret_cast<const uint4*>(zrow + c32 * 64 + e * 8);
+              xv[4 * e] = u.x; xv[4 * e + 1] = u.y; xv[4 * e + 2] = u.z; xv[4 * e + 3] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) xv[e] = 0u;
+          }
+          tmem_st_32x32b_x32(tmem_addr(tmem_x, q * 32, c32 * 32), xv);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_full_bar);
+      }
+      float gs[2] = {0.f, 0.f};
+      float gmax = 0.f;
+      for (int s = 0; s < J.n_seg; ++s) {
+        gs[s] = J.seg[s].grad_scale ? *J.seg[s].grad_scale : 1.f;
+        gmax = fmaxf(gmax, fabsf(gs[s]));
+      }
+      const float inv_gmax = gmax > 0.f ? 1.f / gmax : 0.f;
+      if (blockIdx.x == 0 && blockIdx.y == 0 && ew == 0 && lane == 0) *J.scale_out = gmax * P.out_scale;
+
+      // tile walk of this group: (segment, column tile) of tile t, advanced by two tiles per iteration
+      int si = (t_begin + gi) / P.n_jtiles;
+      int jt = (t_begin + gi) % P.n_jtiles;
+      auto advance2 = [&]() {
+        jt += 2;
+        if (jt >= P.n_jtiles) { jt -= P.n_jtiles; ++si; }
+      };
+      // per-column factors 2^(c1 - lse_other_j): the global load is issued one iteration ahead and consumed
+      // (ex2 + shared-memory store) at the top of the next one, so its latency is off the loop's path
+      auto load_lse = [&](int seg, int jtile, bool valid) -> float {
+        if (gt >= 128 || !valid) return 1e30f;
+        const int j = jtile * BW_BN + gt;
+        return j < P.n_other ? J.seg[seg].lse2_other[j] : 1e30f;  // 2^(c1 - 1e30) = 0
+      };
+      float lse_col = load_lse(si, jt, gi < n_tiles);
+      int cur_seg = -1;
+      float lse_i = 0.f, ws = 0.f, wo_i = 0.f, rr = 0.f;
+      const uint32_t g_peer = map_to_peer(base + PcSmem::c_g_off, 1u);  // G slots in the consumer's shared memory
+      const uint32_t g_full_peer0 = map_to_peer(g_full(0), 1u);
+      const uint32_t row_off = static_cast<uint32_t>(ch * BW_KB_BYTES + r * 128);
+      uint8_t* stage_ptr = base_ptr + PcSmem::p_stage_off;
+      const uint32_t s_addr = tmem_addr(tmem + gi * BW_BN, q * 32, ch * 64);
+      int g = gi % PC_GSLOTS;  // G slot of tile t (t mod PC_GSLOTS)
+      uint32_t s_par = 0;
+
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long pt_e0 = clock64();
+#endif
+      for (int t = gi; t < n_tiles; t += 2) {
+        if (si != cur_seg) {
+          const BwdSegDev& sg = J.seg[si];
+          cur_seg = si;
+          rr = gs[si] * inv_gmax;
+          lse_i = grow < P.n_self ? sg.lse2_self[grow] : 0.f;
+          ws = rr * sg.w_self;
+          wo_i = rr * sg.w_other * ex2_approx(lse_i - P.c1);
+        }
+        const int j0 = jt * BW_BN;
+        if (gt < 128) bj[gt] = ex2_approx(P.c1 - lse_col);
+        // next tile of this group: prefetch its column constants
+        int si_n = si, jt_n = jt + 2;
+        if (jt_n >= P.n_jtiles) { jt_n -= P.n_jtiles; ++si_n; }
+        lse_col = load_lse(si_n, jt_n, t + 2 < n_tiles);
+        PT_BEGIN();
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_grp) : "memory");  // bj visible to the group
+        PT_END(11);
+        const int dcol = P.self_offset + grow - j0 - ch * 64;  // column of the positive inside this thread's 64
+        const bool has_diag = (P.self_offset + i0 < j0 + BW_BN) && (P.self_offset + i0 + BW_BM > j0);  // CTA-uniform
+
+        mbar_wait(s_full(gi), s_par);
+        s_par ^= 1;
+        PT_END(4);
+        tc_fence_after();
+        uint32_t pk[2][16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(s_addr + h * 32, v);
+          tc_wait_ld();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty(gi));  // logits are in registers: the TMEM buffer can be refilled
+          }
+          const float4* bj4 = reinterpret_cast<const float4*>(bj + ch * 64 + h * 32);
+          if (!has_diag) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 bb = bj4[e >> 2];
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), P.c1, -lse_i));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), P.c1, -lse_i));
+              const float p2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), P.c1, -lse_i));
+              const float p3 = ex2_approx(fmaf(__uint_as_float(v[e + 3]), P.c1, -lse_i));
+              pk[h][e >> 1] = pack2<kOp>(p0 * fmaf(wo_i, bb.x, ws), p1 * fmaf(wo_i, bb.y, ws));
+              pk[h][(e >> 1) + 1] = pack2<kOp>(p2 * fmaf(wo_i, bb.z, ws), p3 * fmaf(wo_i, bb.w, ws));
+            }
+          } else {
+            const int dl = dcol - h * 32;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 bb = bj4[e >> 2];
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), P.c1, -lse_i));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), P.c1, -lse_i));
+              const float p2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), P.c1, -lse_i));
+              const float p3 = ex2_approx(fmaf(__uint_as_float(v[e + 3]), P.c1, -lse_i));
+              const float g0 = fmaf(p0, fmaf(wo_i, bb.x, ws), (e == dl) ? -rr : 0.f);
+              const float g1 = fmaf(p1, fmaf(wo_i, bb.y, ws), (e + 1 == dl) ? -rr : 0.f);
+              const float g2 = fmaf(p2, fmaf(wo_i, bb.z, ws), (e + 2 == dl) ? -rr : 0.f);
+              const float g3 = fmaf(p3, fmaf(wo_i, bb.w, ws), (e + 3 == dl) ? -rr : 0.f);
+              pk[h][e >> 1] = pack2<kOp>(g0, g1);
+              pk[h][(e >> 1) + 1] = pack2<kOp>(g2, g3);
+            }
+          }
+        }
+        PT_END(6);
+        // staging slot g (and the consumer's slot g) is free once the consumer's MMAs of tile t - PC_GSLOTS completed
+        mbar_wait(g_empty(g), (static_cast<uint32_t>(t / PC_GSLOTS) & 1u) ^ 1u);
+        PT_END(7);
+        // K-major, 128-byte-swizzled operand tile: row r, 16-byte chunk c16 -> c16 ^ (r & 7)
+        uint8_t* gk = stage_ptr + g * PC_SLOT + row_off;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int c16 = h * 4 + c4;
+            *reinterpret_cast<uint4*>(gk + ((c16 ^ (r & 7)) << 4)) =
+                make_uint4(pk[h][4 * c4], pk[h][4 * c4 + 1], pk[h][4 * c4 + 2], pk[h][4 * c4 + 3]);
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> async proxy (the bulk copy reads them)
+        PT_END(8);
+        // the four warps of this K-block are done (also: everyone has read bj): one thread ships 16 KB to the consumer
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_kb) : "memory");
+        if (q == 0 && lane == 0) {
+          const uint32_t off = static_cast<uint32_t>(g * PC_SLOT + ch * BW_KB_BYTES);
+          bulk_copy_to_cluster(g_peer + off, stage + off, BW_KB_BYTES, g_full_peer0 + 8u * g);
+        }
+        PT_END(9);
+        // both K-block halves of the group have passed their barrier before bj is rewritten: the writers (gt < 128,
+        // i.e. K-block half 0 of the group) only need the readers of half 1 -> one more group barrier
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_grp) : "memory");
+        g = (g + 2) % PC_GSLOTS;
+        advance2();
+      }
+#ifdef TCL_PAIR_TRACE
+      if (pt_on) atomicAdd(&g_pc_trace[10], clock64() - pt_e0);
+#endif
+    }
+  } else {
+    const uint32_t g_smem = base + PcSmem::c_g_off;
+    const uint32_t ring = base + PcSmem::c_ring_off;
+    if (warp == 0) {
+      // -------------------------------------------------------------- consumer: TMA warp
+      if (TCL_PC_EXP < 2 && elect_one() && n_tiles > 0) {
+        int it = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+          const int tt = t_begin + t;
+          const BwdSegDev& sg = J.seg[tt / P.n_jtiles];
+          const int j0 = (tt % P.n_jtiles) * BW_BN;
+          for (int kb2 = 0; kb2 < 2; ++kb2)
+            for (int c = 0; c < n_chunk; ++c, ++it) {
+              const int s = it % PC_CSTAGES;
+              PT_BEGIN();
+              mbar_wait(c_empty(s), ((it / PC_CSTAGES) & 1) ^ 1);
+              PT_END(16);
+              mbar_arrive_expect_tx(c_full(s), PC_SLOT);
+              tma_load_2d(ring + s * PC_SLOT, &sg.tm_other_t, c_full(s), j0 + kb2 * BW_BK, c * 256);
+            }
+        }
+      }
+    } else if (warp == 1) {
+      // -------------------------------------------------------------- consumer: gradient MMAs
+      if (elect_one() && n_tiles > 0) {
+        int it = 0;
+        for (int g = 0; g < PC_GSLOTS; ++g) mbar_arrive_expect_tx(g_full(g), PC_SLOT);  // arm the first round
+#ifdef TCL_PAIR_TRACE
+        const unsigned long long pt_m0 = clock64();
+#endif
+        for (int t = 0; t < n_tiles; ++t) {
+          const int g = t % PC_GSLOTS;
+          PT_BEGIN();
+          mbar_wait(g_full(g), (t / PC_GSLOTS) & 1);  // both bulk copies of the producer have landed
+          PT_END(17);
+          // arm the next round of this slot: its bytes cannot be sent before the g_empty commit below
+          mbar_arrive_expect_tx(g_full(g), PC_SLOT);
+          tc_fence_after();
+          for (int kb2 = 0; kb2 < 2; ++kb2)
+            for (int c = 0; c < n_chunk; ++c, ++it) {
+              const int s = it % PC_CSTAGES;
+              PT_BEGIN();
+              if (TCL_PC_EXP < 2) mbar_wait(c_full(s), (it / PC_CSTAGES) & 1);
+              PT_END(18);
+              tc_fence_after();
+              const uint64_t ad = umma_desc_k_sw128(g_smem + g * PC_SLOT + kb2 * BW_KB_BYTES);
+              const uint64_t bd = umma_desc_k_sw128(ring + s * PC_SLOT);
+#pragma unroll
+              for (int kk = 0; kk < BW_BK / 16; ++kk)
+                tc_mma_f16(tmem + c * 256, ad + 2 * kk, bd + 2 * kk, P.idesc_n256, (t | kb2 | kk) != 0);
+              if (TCL_PC_EXP < 2) tc_commit(c_empty(s));
+            }
+          tc_commit_multicast(g_empty(g), 0x1);  // slot g consumed: tell the producer (cluster rank 0)
+        }
+        tc_commit(acc_full_bar);
+#ifdef TCL_PAIR_TRACE
+        if (pt_on) atomicAdd(&g_pc_trace[19], clock64() - pt_m0);
+#endif
+      }
+    } else {
+      // -------------------------------------------------------------- consumer: accumulator read-out (16 warps)
+      const int ew = warp - 2;
+      const int q = warp & 3;
+      const int cq = ew >> 2;  // 128-column quarter of the accumulator
+      const int r = q * 32 + lane;
+      const int grow = i0 + r;
+      if (n_tiles > 0) {
+        mbar_wait(acc_full_bar, 0);
+        tc_fence_after();
+      }
+      PT_BEGIN();
+      float* gout = J.gpart + (static_cast<int64_t>(split) * P.n_self + grow) * P.dim;
+#pragma unroll 1
+      for (int cc = cq * 4; cc < cq * 4 + 4; ++cc) {
+        if (cc * 32 >= P.dim) break;
+        uint32_t v[32];
+        if (n_tiles > 0) {
+          tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, cc * 32), v);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+        if (grow < P.n_self) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(gout + cc * 32 + e) =
+                make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                            __uint_as_float(v[e + 3]));
+        }
+      }
+      PT_END(20);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves while the other may still signal its barriers / write its memory
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tcl
+
+extern "C" int tcl_debug_pc_trace(unsigned long long* out32, int reset) {
+  using namespace tcl;
+  TCL_CHECK_CUDA(cudaDeviceSynchronize());
+  if (out32) TCL_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_pc_trace, sizeof(unsigned long long) * 32));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    TCL_CHECK_CUDA(cudaMemcpyToSymbol(g_pc_trace, z, sizeof(z)));
+  }
+  return TCL_OK;
+}
+
+// how many clusters of `cluster_size` CTAs of this kernel's footprint the device can hold at once
+extern "C" int tcl_debug_max_clusters(int cluster_size, int* out) {
+  using namespace tcl;
+  const int smem = static_cast<int>(PcSmem::total(8));
+  TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_pc_kernel<TCL_OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (cluster_size > 8)
+    TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_pc_kernel<TCL_OP_F16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cluster_size * 64, 1, 1);
+  cfg.blockDim = dim3(PC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCL_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, ntxent_bwd_pc_kernel<TCL_OP_F16>, &cfg));
+  return TCL_OK;
+}
+
+namespace tcl {
+
+int launch_bwd_pc(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st) {
+  const int smem = static_cast<int>(PcSmem::total(P.num_kb));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_iblocks, P.n_split, n_jobs);
+  cfg.blockDim = dim3(PC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (op_format == TCL_OP_F16) {
+    static int set = 0;
+    if (set < smem) {
+      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_pc_kernel<TCL_OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      set = smem;
+    }
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_bwd_pc_kernel<TCL_OP_F16>, P));
+  } else {
+    static int set = 0;
+    if (set < smem) {
+      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_pc_kernel<TCL_OP_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      set = smem;
+    }
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_bwd_pc_kernel<TCL_OP_BF16>, P));
+  }
+  return TCL_OK;
+}
+
+}  // namespace tcl
