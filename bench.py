@@ -59,7 +59,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.1):
+    def __init__(self, index: int, period_s: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period_s, [], set(), None
         self._stop_evt = threading.Event()
@@ -284,19 +284,23 @@ def run_ours(args, rank, world, local_rank):
     if "ntxent_fwd" in kern:
         kern["ntxent_fwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_fwd, "ntxent_fwd")})
     if "ntxent_bwd" in kern:
+        # executed flop of the gradient kernel per algorithmic flop: the producer/consumer and pair kernels recompute
+        # the logits once per direction (2x), the independent-CTA kernel once per dim half (3x)
+        bwd_mode = os.environ.get("TRICOLO_B200_BWD", "pc")
+        exec_factor = 3.0 if bwd_mode == "indep" or os.environ.get("TRICOLO_B200_BWD_NOPAIR") else 2.0
         kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
-                                   "executed_tflops": tf(flops_bwd * 3.0, "ntxent_bwd")})
+                                   "executed_tflops": tf(flops_bwd * exec_factor, "ntxent_bwd"), "mode": bwd_mode})
     if "l2norm_fwd" in kern:
         kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9})
     peak_tf = peaks["tf_sustained"]
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
     traffic = None
     try:  # DRAM bytes per launch of the same kernel at the same shapes, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
-            traffic = json.load(f).get("ntxent_bwd_kernel") if (world == 1 and batch == 8192) else None
+        with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as f:
+            traffic = json.load(f).get("ntxent_bwd_pc_kernel") if (world == 1 and batch == 8192) else None
     except Exception:
         traffic = None
-    roofline = {"kernel": "ntxent_bwd_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline = {"kernel": "ntxent_bwd_pc_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (ach / peak_tf) if ach else None, "traffic": traffic,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops_bwd,

@@ -122,7 +122,8 @@ int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row
  * ------------------------------------------------------------------------- */
 typedef struct {
   const void* z_other;     /* [n_other, dim] 16-bit */
-  const void* z_other_t;   /* [dim, ld_t]   16-bit (tcl_transpose_16bit) */
+  const void* z_other_t;   /* [dim, ld_t]   16-bit (tcl_transpose_16bit); may be NULL when
+                              tcl_ntxent_bwd_needs_transpose(dim) == 0 */
   const float* lse2_self;  /* [n_self]  */
   const float* lse2_other; /* [n_other] */
   const float* grad_scale; /* device scalar dL/d(loss of this pair); NULL = 1 */
@@ -141,6 +142,9 @@ typedef struct {
 } tcl_bwd_job;
 
 size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int64_t dim);
+/* 1 if tcl_ntxent_bwd needs the transposed copies z_other_t / ld_t for this dim (the kernels for dim <= 256 and the
+ * non-default kernels selected by TRICOLO_B200_BWD), 0 if it reads the row-major operands only. */
+int tcl_ntxent_bwd_needs_transpose(int64_t dim);
 int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int64_t n_other,
                    int64_t dim, int64_t z_row_stride, int64_t self_offset, int64_t ld_t, int x_dtype,
                    int64_t x_row_stride, int op_format, float inv_tau, float eps,

@@ -345,6 +345,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for an MN-major operand tile stored as [K rows][64 x 16-bit] = 128-byte rows of 64 consecutive M/N elements,
+// 128-byte swizzle (a TMA box {64 elements, K rows} of a row-major [K, MN] tensor):
+//   stride byte offset  = distance between groups of 8 K rows (8 x 128 B = 1024)
+//   leading byte offset = distance between consecutive 64-element groups along M/N (`mn_group_bytes`)
+// Advancing by one UMMA_K (16 K rows) adds 2048 >> 4 = 128 to the start-address field.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t mn_group_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((mn_group_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major:
 //   bits  4-5   D format   (1 = F32)
 //   bits  7-9   A format   (0 = F16, 1 = BF16)

@@ -297,6 +297,18 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+enum class BwdMode { Pc, Pair, Cluster, Indep };
+static BwdMode bwd_mode() {  // read once: TRICOLO_B200_BWD=pc|pair|cluster|indep (legacy switches still honoured)
+  static const BwdMode m = [] {
+    const char* e = getenv("TRICOLO_B200_BWD");
+    if (getenv("TRICOLO_B200_BWD_CLUSTER") || (e && !strcmp(e, "cluster"))) return BwdMode::Cluster;
+    if (getenv("TRICOLO_B200_BWD_NOPAIR") || (e && !strcmp(e, "indep"))) return BwdMode::Indep;
+    if (e && !strcmp(e, "pair")) return BwdMode::Pair;
+    return BwdMode::Pc;
+  }();
+  return m;
+}
+
 static constexpr int kBwdMaxSplit = 8;
 static int bwd_split(int n_jobs, int n_iblocks, int n_dhalf, int min_tiles) {
   // One CTA per SM (224 KB shared memory): pick the split of the tile range that wastes the least
@@ -326,6 +338,11 @@ extern "C" size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int
   return static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self * dim * sizeof(float) + 256;
 }
 
+extern "C" int tcl_ntxent_bwd_needs_transpose(int64_t dim) {
+  // only the producer/consumer kernel (dim > 256, default) reads the row-major operand directly
+  return (dim > BW_DH && bwd_mode() == BwdMode::Pc) ? 0 : 1;
+}
+
 extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_self, int64_t n_other,
                               int64_t dim, int64_t z_row_stride, int64_t self_offset, int64_t ld_t, int x_dtype,
                               int64_t x_row_stride, int op_format, float inv_tau, float eps,
@@ -335,7 +352,8 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   TCL_REQUIRE(dim >= 64 && dim % 64 == 0 && dim <= 512, TCL_ERR_BAD_SHAPE,
               "ntxent_bwd: dim must be a multiple of 64 in [64, 512] (got %lld)", (long long)dim);
   TCL_REQUIRE(self_offset >= 0 && self_offset + n_self <= n_other, TCL_ERR_BAD_SHAPE, "ntxent_bwd: self rows outside the global batch");
-  TCL_REQUIRE(ld_t >= n_other && ld_t % 8 == 0, TCL_ERR_BAD_ALIGN, "ntxent_bwd: ld_t must be >= n_other and a multiple of 8");
+  const bool need_t = tcl_ntxent_bwd_needs_transpose(dim) != 0;
+  TCL_REQUIRE(!need_t || (ld_t >= n_other && ld_t % 8 == 0), TCL_ERR_BAD_ALIGN, "ntxent_bwd: ld_t must be >= n_other and a multiple of 8");
   TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
   TCL_REQUIRE(workspace && workspace_bytes >= tcl_ntxent_bwd_workspace_bytes(n_jobs, n_self, dim), TCL_ERR_WORKSPACE, "ntxent_bwd: workspace too small");
   const float c1 = inv_tau * 1.4426950408889634f;
@@ -368,17 +386,15 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   //  cluster ntxent_bwd_cluster.cu: the two dim-half CTAs share the logit recompute through DSMEM (N=64 MMAs);
   //          correct but slower than `indep` (1.22 ms vs 1.00 ms at B=8192x3).
   //  indep   the kernel above: one CTA per dim half, logits recomputed per half (12 B^2 D executed).
-  static const char* mode_env = getenv("TRICOLO_B200_BWD");
-  static const bool want_cluster = getenv("TRICOLO_B200_BWD_CLUSTER") != nullptr || (mode_env && !strcmp(mode_env, "cluster"));
-  static const bool want_indep = getenv("TRICOLO_B200_BWD_NOPAIR") != nullptr || (mode_env && !strcmp(mode_env, "indep"));
-  static const bool want_pair = mode_env && !strcmp(mode_env, "pair");
+  const BwdMode mode = bwd_mode();
+  const bool want_cluster = mode == BwdMode::Cluster, want_indep = mode == BwdMode::Indep, want_pair = mode == BwdMode::Pair;
   const bool wide = P.n_dhalf == 2;
   const bool use_cluster = wide && want_cluster;
   const bool use_pair = wide && !use_cluster && want_pair;
   const bool use_pc = wide && !use_cluster && !use_pair && !want_indep;
   P.idesc_m256 = umma_idesc_f16(256, BW_BN, op_format);
   P.idesc_m256_bmn = P.idesc_m256 | (1u << 16);
-  P.idesc_n256 = umma_idesc_f16(BW_BM, 256, op_format);
+  P.idesc_n256 = umma_idesc_f16(BW_BM, 256, op_format) | (1u << 16);  // B operand MN-major
   // the pair kernel walks the column tiles two at a time
   P.n_split = use_pair ? bwd_split(n_jobs, n_iblocks, 2, (min_seg * P.n_jtiles + 1) / 2)
                        : bwd_split(n_jobs, n_iblocks, P.n_dhalf, min_seg * P.n_jtiles);
@@ -395,9 +411,13 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     J.z_self = static_cast<const uint16_t*>(src.z_self);
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
-      TCL_REQUIRE(sg.z_other && sg.z_other_t && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
+      TCL_REQUIRE(sg.z_other && (sg.z_other_t || !need_t) && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
       if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, use_cluster ? 64 : BW_BN, BW_BK)) return e;
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, use_pc ? 256 : 128, BW_BK)) return e;
+      if (use_pc) {  // the gradient GEMM reads the row-major operand itself (MN-major B): boxes {64 dim, 64 rows}
+        if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other, n_other, dim, z_row_stride, 64, 64)) return e;
+      } else {
+        if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other_t, dim, n_other, ld_t, 128, BW_BK)) return e;
+      }
       J.seg[s].lse2_self = sg.lse2_self;
       J.seg[s].lse2_other = sg.lse2_other;
       J.seg[s].grad_scale = sg.grad_scale;

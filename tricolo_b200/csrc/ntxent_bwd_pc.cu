@@ -15,8 +15,9 @@
 //                                   consumer's mbarrier.  (Direct st.shared::cluster stores were measured at
 //                                   ~6 B/clk for this access pattern: 5600 cycles per 32 KB tile.)
 //   consumer CTA (cluster rank 1)   acc[128 rows x dim] += G'[128 x 128] · Zother[tile]  with the whole 512-column
-//                                   TMEM as accumulator: M=128, N=256 MMAs, A = a G slot, B = the transposed
-//                                   operand streamed by its own TMA ring.
+//                                   TMEM as accumulator: M=128, N=256 MMAs, A = a G slot, B = the other operand
+//                                   in MN-major form (TMA boxes {64 dim, 64 rows} of the row-major tensor, so
+//                                   no transposed copy is needed) streamed by its own TMA ring.
 // Both SMs run 2·128·128·dim flop per tile: the work is balanced, nothing is recomputed twice (8 B^2 D executed
 // per pair, the count of a recompute backward) and the 32 KB/tile G hand-over is one-way and three slots deep,
 // i.e. off the critical path.  Hand-shakes: producer -> consumer MMA thread: the copies' complete_tx on g_full[slot]
@@ -36,7 +37,7 @@ namespace tcl {
 #define TCL_PC_EXP 0
 #endif
 static constexpr int PC_PSTAGES = TCL_PC_PSTAGES;  // producer ring: slots of two 16 KB K-blocks of the other operand
-static constexpr int PC_CSTAGES = 4;     // consumer ring: slots of {64 K x 256 dim rows} of the transposed operand
+static constexpr int PC_CSTAGES = 4;     // consumer ring: slots of 4 boxes {64 dim x 64 other rows} (N = 256, K = 64)
 static constexpr int PC_SLOT = 32768;
 static constexpr int PC_GSLOTS = 3;      // G tiles in flight (128 rows x 128 K, two K-blocks of 16 KB)
 static constexpr int PC_SBUFS = 2;       // logit buffers in the producer's TMEM (columns 0..255; the self block: 256..)
@@ -403,7 +404,11 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
               mbar_wait(c_empty(s), ((it / PC_CSTAGES) & 1) ^ 1);
               PT_END(16);
               mbar_arrive_expect_tx(c_full(s), PC_SLOT);
-              tma_load_2d(ring + s * PC_SLOT, &sg.tm_other_t, c_full(s), j0 + kb2 * BW_BK, c * 256);
+              // four boxes {64 dim columns, 64 other rows}: the B operand in MN-major form (N = dim, K = other
+              // rows), read straight from the row-major operand: no transposed copy
+              for (int a = 0; a < 4; ++a)
+                tma_load_2d(ring + s * PC_SLOT + a * 8192, &sg.tm_other_t, c_full(s), c * 256 + a * 64,
+                            j0 + kb2 * BW_BK);
             }
         }
       }
@@ -431,10 +436,10 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
               PT_END(18);
               tc_fence_after();
               const uint64_t ad = umma_desc_k_sw128(g_smem + g * PC_SLOT + kb2 * BW_KB_BYTES);
-              const uint64_t bd = umma_desc_k_sw128(ring + s * PC_SLOT);
+              const uint64_t bd = umma_desc_mn_sw128(ring + s * PC_SLOT, 8192);
 #pragma unroll
               for (int kk = 0; kk < BW_BK / 16; ++kk)
-                tc_mma_f16(tmem + c * 256, ad + 2 * kk, bd + 2 * kk, P.idesc_n256, (t | kb2 | kk) != 0);
+                tc_mma_f16(tmem + c * 256, ad + 2 * kk, bd + 128 * kk, P.idesc_n256, (t | kb2 | kk) != 0);
               if (TCL_PC_EXP < 2) tc_commit(c_empty(s));
             }
           tc_commit_multicast(g_empty(g), 0x1);  // slot g consumed: tell the producer (cluster rank 0)

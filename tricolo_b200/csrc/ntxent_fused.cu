@@ -107,7 +107,10 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
     z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
     zt[m] = ws8 + static_cast<size_t>(m) * dim * ld_t * 2;
   }
-  if (int e = tcl_transpose_16bit(n_tensors, z, batch, dim, 0, zt, ld_t, stream)) return e;
+  const bool need_t = tcl_ntxent_bwd_needs_transpose(dim) != 0;
+  if (need_t) {
+    if (int e = tcl_transpose_16bit(n_tensors, z, batch, dim, 0, zt, ld_t, stream)) return e;
+  }
   const size_t zt_bytes = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256);
   const float* lse_row = reinterpret_cast<const float*>(st8 + L.lse_row);
   const float* lse_col = reinterpret_cast<const float*>(st8 + L.lse_col);
@@ -129,7 +132,7 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
       const bool is_row = pair_row[p] == m;  // self is the pair's first argument: row softmax weight alpha
       const int o = is_row ? pair_col[p] : pair_row[p];
       S.z_other = z[o];
-      S.z_other_t = zt[o];
+      S.z_other_t = need_t ? zt[o] : nullptr;
       S.lse2_self = (is_row ? lse_row : lse_col) + static_cast<size_t>(p) * batch;
       S.lse2_other = (is_row ? lse_col : lse_row) + static_cast<size_t>(p) * batch;
       S.grad_scale = grad_losses + p;

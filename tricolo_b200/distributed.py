@@ -89,7 +89,7 @@ class _GlobalNTXent(torch.autograd.Function):
         if gscale != 1.0:
             grad_losses = grad_losses * gscale
         grad_losses = grad_losses.contiguous()
-        zts, ld_t = ops.transpose_16bit(z_all)
+        zts, ld_t = ops.transpose_for_bwd(z_all)  # none for the default dim-512 kernel
         jobs, owners = [], []
         sl = slice(row_offset, row_offset + b_loc)
         for m in range(n):

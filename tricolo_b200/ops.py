@@ -67,6 +67,19 @@ def cast_16bit(x: torch.Tensor, op_format: int = BF16) -> torch.Tensor:
     return y
 
 
+def bwd_needs_transpose(dim: int) -> bool:
+    """Whether tcl_ntxent_bwd wants the transposed operand copies for this dim (the default kernel for
+    dim > 256 reads the row-major operands directly)."""
+    return bool(LIB.tcl_ntxent_bwd_needs_transpose(int(dim)))
+
+
+def transpose_for_bwd(zs: Sequence[torch.Tensor]) -> Tuple[List[Optional[torch.Tensor]], int]:
+    """The transposed copies tcl_ntxent_bwd needs for these operands: ([None, ...], 0) when it needs none."""
+    if not bwd_needs_transpose(zs[0].shape[1]):
+        return [None] * len(zs), 0
+    return transpose_16bit(zs)
+
+
 def transpose_16bit(zs: Sequence[torch.Tensor]) -> Tuple[List[torch.Tensor], int]:
     """[rows, dim] -> [dim, ld_t] (ld_t = rows rounded up to 8)."""
     dev = L.require_cuda(*zs)
@@ -151,7 +164,7 @@ def ntxent_bwd(jobs: Sequence[BwdJobSpec], n_other: int, self_offset: int, ld_t:
         for s, sg in enumerate(job.segments):
             a = arr[j].seg[s]
             a.z_other = sg.z_other.data_ptr()
-            a.z_other_t = sg.z_other_t.data_ptr()
+            a.z_other_t = 0 if sg.z_other_t is None else sg.z_other_t.data_ptr()
             a.lse2_self = sg.lse2_self.data_ptr()
             a.lse2_other = sg.lse2_other.data_ptr()
             a.grad_scale = 0 if sg.grad_scale is None else sg.grad_scale.data_ptr()
