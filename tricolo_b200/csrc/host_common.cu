@@ -84,4 +84,22 @@ int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64
   return TCL_OK;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     uint32_t box_cols) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  TCL_REQUIRE(fn != nullptr, TCL_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  TCL_REQUIRE(aligned_to(base, 16) && (cols * 4) % 16 == 0, TCL_ERR_BAD_ALIGN, "TMA fp32 tensor: 16-byte alignment");
+  TCL_REQUIRE(box_cols * 4 == 128, TCL_ERR_BAD_ARG, "128-byte swizzle needs a 32-element fp32 inner box");
+  TCL_REQUIRE(box_rows >= 1 && box_rows <= 256, TCL_ERR_BAD_ARG, "box rows out of range");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TCL_REQUIRE(r == CUDA_SUCCESS, TCL_ERR_DRIVER, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+  return TCL_OK;
+}
+
 }  // namespace tcl

@@ -37,6 +37,16 @@ int require_sm100();
 // are zero-filled (ragged edge tiles rely on this).
 int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+// The same for a dense fp32 [rows, cols] tensor (TMA stores of accumulator tiles): 32-element inner box.
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     uint32_t box_cols);
+
+// Persistent gradient kernel (ntxent_bwd_pc.cu): tile range [lo, hi) of range c out of n over `total` tiles, and the
+// range a tile belongs to.
+__host__ __device__ inline int64_t pc_range_lo(int64_t total, int c, int n) { return total * c / n; }
+__host__ __device__ inline int pc_range_of(int64_t total, int64_t t, int n) {
+  return static_cast<int>(((t + 1) * n - 1) / total);
+}
 
 // normalise backward (l2norm.cu), launched by tcl_ntxent_bwd after the gradient GEMM
 struct NormBwdJob {
@@ -48,6 +58,13 @@ struct NormBwdJob {
 };
 struct NormBwdParams {
   NormBwdJob job[3];
+  // partial layout [slot][split_rows][dim]; split_rows = 0 means `rows`.  n_clusters > 0: the partial count of a
+  // 128-row unit follows from the persistent gradient kernel's tile ranges (ntxent_bwd.h: pc_range_of).
+  int64_t split_rows;
+  int64_t total_tiles;
+  int64_t job_tile_base[3];
+  int unit_tiles[3];
+  int n_clusters;
 };
 // sim_gemm_resident.cu: retrieval GEMM with the query block resident (dim % 64 == 0, dim <= 512)
 int launch_sim_gemm_resident(const void* q, const void* g, int64_t n_q, int64_t n_g, int64_t dim, int op_format,

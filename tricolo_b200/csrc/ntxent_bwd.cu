@@ -309,7 +309,6 @@ static BwdMode bwd_mode() {  // read once: TRICOLO_B200_BWD=pc|pair|cluster|inde
   return m;
 }
 
-static constexpr int kBwdMaxSplit = 8;
 static int bwd_split(int n_jobs, int n_iblocks, int n_dhalf, int min_tiles) {
   // One CTA per SM (224 KB shared memory): pick the split of the tile range that wastes the least
   // of the last wave; every extra split costs one more fp32 partial of the gradient, so a larger
@@ -335,7 +334,8 @@ using namespace tcl;
 
 extern "C" size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int64_t dim) {
   if (n_jobs < 1 || n_self < 1 || dim < 1) return 0;
-  return static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self * dim * sizeof(float) + 256;
+  const int64_t n_self_pad = (n_self + BW_BM - 1) / BW_BM * BW_BM;  // the persistent kernel stores whole 128-row units
+  return static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self_pad * dim * sizeof(float) + 256;
 }
 
 extern "C" int tcl_ntxent_bwd_needs_transpose(int64_t dim) {
@@ -372,6 +372,8 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   P.n_jtiles = (int)((n_other + BW_BN - 1) / BW_BN);
   P.n_dhalf = (int)((dim + BW_DH - 1) / BW_DH);
   const int n_iblocks = (int)((n_self + BW_BM - 1) / BW_BM);
+  P.n_iblocks = n_iblocks;
+  P.n_self_pad = n_iblocks * BW_BM;
   int min_seg = 2;
   for (int j = 0; j < n_jobs; ++j) min_seg = jobs[j].n_segments < min_seg ? jobs[j].n_segments : min_seg;
   if (min_seg < 1) min_seg = 1;
@@ -424,20 +426,35 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
       J.seg[s].w_self = sg.w_self;
       J.seg[s].w_other = sg.w_other;
     }
-    J.gpart = gbase + static_cast<size_t>(j) * kBwdMaxSplit * n_self * dim;
+    J.gpart = gbase + static_cast<size_t>(j) * kBwdMaxSplit * P.n_self_pad * dim;
     J.scale_out = scales + j;
+    P.unit_tiles[j] = src.n_segments * P.n_jtiles;
+    P.job_tile_base[j + 1] = P.job_tile_base[j] + static_cast<int64_t>(n_iblocks) * P.unit_tiles[j];
+    if (use_pc)
+      if (int e = make_tmap_2d_f32(&P.tm_gpart[j], J.gpart, static_cast<uint64_t>(kBwdMaxSplit) * P.n_self_pad, dim, 32, 32)) return e;
     N.job[j].x = src.x_self;
     N.job[j].inv_norm = src.inv_norm;
     N.job[j].gpart = J.gpart;
     N.job[j].scale = J.scale_out;
     N.job[j].dx = src.dx;
   }
+  for (int j = n_jobs; j < TCL_MAX_TENSORS; ++j) P.job_tile_base[j + 1] = P.job_tile_base[n_jobs];
   const int smem = (int)BwdSmem::total(P.num_kb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(n_iblocks, P.n_dhalf * P.n_split, n_jobs);
   prof_begin(TCL_K_NTXENT_BWD, st);
   if (use_pc) {
-    if (int e = launch_bwd_pc(P, n_iblocks, n_jobs, op_format, st)) return e;
+    int n_clusters = 0;
+    if (int e = launch_bwd_pc(P, n_jobs, op_format, &n_clusters, st)) return e;
+    // partial count per 128-row unit follows from the tile ranges (ntxent_bwd.h: pc_range_of)
+    N.n_clusters = n_clusters;
+    N.split_rows = P.n_self_pad;
+    N.total_tiles = P.job_tile_base[TCL_MAX_TENSORS];
+    for (int j = 0; j < TCL_MAX_TENSORS; ++j) {
+      N.job_tile_base[j] = P.job_tile_base[j];
+      N.unit_tiles[j] = P.unit_tiles[j];
+    }
+    P.n_split = kBwdMaxSplit;
   } else if (use_pair) {
     if (int e = launch_bwd_pair(P, n_iblocks, n_jobs, op_format, st)) return e;
   } else if (use_cluster) {

@@ -12,6 +12,8 @@ static constexpr int BW_EPI_WARPS = 8;  // two per TMEM lane quarter
 static constexpr int BW_EPI_THREADS = BW_EPI_WARPS * 32;
 static constexpr int BW_THREADS = 64 + BW_EPI_THREADS;
 static constexpr int BW_DH = 256;  // dim columns per CTA
+static constexpr int kBwdMaxSplit = 8;  // fp32 gradient partials per 128-row unit the workspace provides for
+
 
 struct BwdSegDev {
   CUtensorMap tm_other;    // [n_other, dim]   box {64, 128} (cluster kernel: {64, 64})
@@ -41,6 +43,12 @@ struct BwdParams {
   uint32_t idesc_m256;      // M=256 (CTA pair), N=128, both operands K-major (pair kernel: logit MMA)
   uint32_t idesc_m256_bmn;  // same with an MN-major B operand (pair kernel: gradient MMA)
   uint32_t idesc_n256;      // M=128, N=256 (producer/consumer kernel: gradient MMA)
+  // persistent producer/consumer kernel: the flat tile sequence (job-major, then 128-row unit, then tile) is cut
+  // into n_clusters equal contiguous ranges; a unit cut by a range boundary leaves one partial per piece
+  CUtensorMap tm_gpart[TCL_MAX_TENSORS];  // [kBwdMaxSplit * n_self_pad, dim] f32, box {32 cols, 32 rows}, 128-B swizzle
+  int64_t job_tile_base[TCL_MAX_TENSORS + 1];
+  int unit_tiles[TCL_MAX_TENSORS];  // n_seg * n_jtiles
+  int n_iblocks, n_self_pad;
 };
 
 struct BwdSmem {
@@ -65,8 +73,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // ntxent_bwd_pair.cu
 int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
-// ntxent_bwd_pc.cu
-int launch_bwd_pc(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
+// ntxent_bwd_pc.cu: persistent; *n_clusters_out = the number of tile ranges it used (<= pc_max_pieces() per unit)
+int launch_bwd_pc(const BwdParams& P, int n_jobs, int op_format, int* n_clusters_out, cudaStream_t st);
 // ntxent_bwd_cluster.cu
 int launch_bwd_cluster(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 
