@@ -266,6 +266,8 @@ int tcl_debug_tmem_probe(uint32_t* out, void* stream);
 int tcl_debug_pair_trace(unsigned long long* out32, int reset);
 /* tcl_debug_pc_trace: the same for the first cluster of the producer/consumer backward kernel (ntxent_bwd_pc.cu). */
 int tcl_debug_pc_trace(unsigned long long* out32, int reset);
+/* tcl_debug_fwd_trace: the same for the first cluster of the CTA-pair forward kernel (ntxent_fwd.cu). */
+int tcl_debug_fwd_trace(unsigned long long* out32, int reset);
 /* tcl_debug_max_clusters: cudaOccupancyMaxActiveClusters for the producer/consumer kernel's footprint. */
 int tcl_debug_max_clusters(int cluster_size, int* out);
 

@@ -31,6 +31,8 @@
 // `cluster - cluster_of(first tile of the unit)`; the producer already works on the next piece meanwhile (its
 // hand-over is three G slots deep).  No wave quantisation, 3-4 drains per SM pair instead of 8 at B = 8192, and the
 // normalise backward reads 1-2 partials per row instead of 3.
+#include <stdlib.h>
+
 #include "ntxent_bwd.h"
 #include "../../include/tricolo_b200.h"
 
@@ -630,6 +632,10 @@ static int launch_bwd_pc_t(const BwdParams& P, int n_jobs, int* n_clusters_out, 
   for (int j = 0; j < n_jobs; ++j) t_max = P.unit_tiles[j] > t_max ? P.unit_tiles[j] : t_max;
   // a unit of T tiles is cut into at most ceil(T / range) + 1 pieces; the workspace holds kBwdMaxSplit partials
   int64_t n = resident[dev];
+  if (const char* e = getenv("TRICOLO_B200_PC_CLUSTERS")) {  // experiments: fewer tile ranges than resident clusters
+    const int v = atoi(e);
+    if (v >= 1 && v < n) n = v;
+  }
   if (n > total) n = total;
   const int64_t cap = (kBwdMaxSplit - 1) * total / t_max;  // range >= T / (kBwdMaxSplit - 1)
   if (n > cap) n = cap;

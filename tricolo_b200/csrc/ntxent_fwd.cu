@@ -38,6 +38,10 @@ struct FwdParams {
   int num_kb, n_jtiles, n_jsplit, n_iblocks;
   float c1;
   uint32_t idesc;
+  // CTA-pair kernel: M = 256 instruction descriptor, raw row-operand pointers (the row block goes to TMEM)
+  uint32_t idesc_pair;
+  const void* z_row[TCL_MAX_PAIRS];
+  int64_t z_row_stride;
 };
 
 // shared memory map (offsets from the 1024-aligned base)
@@ -97,6 +101,74 @@ __device__ __forceinline__ void fwd_tile_epilogue(uint32_t tmem_acc, int q, int 
           cs[cl * 8 + g * 2 + e] += e0 + e1;
         }
       }
+    }
+  }
+}
+
+// column sums of one tile: butterfly over the 8 row groups of the quad layout, then over the four lane quarters
+// through shared memory; one partial per (row block, column)
+__device__ __forceinline__ void fwd_col_sums(const float (&cs)[16], float* colbuf, int buf, int bar_id, int q, int ch,
+                                             int lane, int p, int et, int j0, int pair, int ib, const FwdParams& P) {
+  // column sums: butterfly over the 8 row groups (lane bits 4,3,2): 16 -> 8 -> 4 -> 2 values
+  float a8[8], a4[4], a2[2];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = hi ? cs[i] : cs[i + 8];
+      const float keep = hi ? cs[i + 8] : cs[i];
+      a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? a8[i] : a8[i + 4];
+      const float keep = hi ? a8[i + 4] : a8[i];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? a4[i] : a4[i + 2];
+      const float keep = hi ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  // this thread now owns cidx = bit4*8 + bit3*4 + bit2*2 + i  (cl = cidx>>3, g = (cidx>>1)&3, e = cidx&1)
+  float* cb = colbuf + buf * 512 + q * 128;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + i;
+    const int cl = cidx >> 3, g = (cidx >> 1) & 3, e = cidx & 1;
+    cb[(2 * ch + cl) * 32 + g * 8 + 2 * p + e] = a2[i];
+  }
+  asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+  if (et < 128) {
+    const float* c0 = colbuf + buf * 512;
+    const float tot = c0[et] + c0[128 + et] + c0[256 + et] + c0[384 + et];
+    if (j0 + et < P.n_cols && ib < P.n_iblocks)  // (the pair kernel pads an odd block count with an empty block)
+      P.col_part[(static_cast<int64_t>(pair) * P.n_iblocks + ib) * P.n_cols + j0 + et] = tot;
+  }
+}
+
+// row sums: reduce over the 4 column-pair lanes, then one store per row and column half
+__device__ __forceinline__ void fwd_row_sums(float (&rs)[4], int q, int ch, int ql, int p, int i0, int js, int pair,
+                                             const FwdParams& P) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+    rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+  }
+  if (p == 0) {
+    float* rp = P.row_part + (static_cast<int64_t>(pair) * (2 * P.n_jsplit) + 2 * js + ch) * P.n_rows;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = i0 + q * 32 + (r >> 1) * 16 + ql + (r & 1) * 8;
+      if (row < P.n_rows) rp[row] = rs[r];
     }
   }
 }
@@ -220,70 +292,273 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(b));
 
-      // column sums: butterfly over the 8 row groups (lane bits 4,3,2): 16 -> 8 -> 4 -> 2 values
-      float a8[8], a4[4], a2[2];
-      {
-        const bool hi = (lane & 16) != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float send = hi ? cs[i] : cs[i + 8];
-          const float keep = hi ? cs[i + 8] : cs[i];
-          a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-      }
-      {
-        const bool hi = (lane & 8) != 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = hi ? a8[i] : a8[i + 4];
-          const float keep = hi ? a8[i + 4] : a8[i];
-          a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-      }
-      {
-        const bool hi = (lane & 4) != 0;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float send = hi ? a4[i] : a4[i + 2];
-          const float keep = hi ? a4[i + 2] : a4[i];
-          a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-      }
-      // this thread now owns cidx = bit4*8 + bit3*4 + bit2*2 + i  (cl = cidx>>3, g = (cidx>>1)&3, e = cidx&1)
-      float* cb = colbuf + (t & 1) * 512 + q * 128;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + i;
-        const int cl = cidx >> 3, g = (cidx >> 1) & 3, e = cidx & 1;
-        cb[(2 * ch + cl) * 32 + g * 8 + 2 * p + e] = a2[i];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et < 128) {
-        const float* c0 = colbuf + (t & 1) * 512;
-        const float tot = c0[et] + c0[128 + et] + c0[256 + et] + c0[384 + et];
-        if (j0 + et < P.n_cols)
-          P.col_part[(static_cast<int64_t>(pair) * P.n_iblocks + ib) * P.n_cols + j0 + et] = tot;
-      }
+      fwd_col_sums(cs, colbuf, t & 1, 1, q, ch, lane, p, et, j0, pair, ib, P);
     }
-    // row sums: reduce over the 4 column-pair lanes, then one store per row and column half
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
-      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
-    }
-    if (p == 0) {
-      float* rp = P.row_part + (static_cast<int64_t>(pair) * (2 * P.n_jsplit) + 2 * js + ch) * P.n_rows;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = i0 + q * 32 + (r >> 1) * 16 + ql + (r & 1) * 8;
-        if (row < P.n_rows) rp[row] = rs[r];
-      }
-    }
+    fwd_row_sums(rs, q, ch, ql, p, i0, js, pair, P);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair form (TRICOLO_B200_FWD=pair|single): two adjacent row blocks share one column sweep through TMA MULTICAST.
+// Why: with one CTA per row block every SM ingests the whole 128 KB column tile per 2048 MMA cycles; the two SMs of
+// a TPC then sit on a shared ingest limit of ~85 B/clk (measured on the backward: ~3100 cycles per tile whatever the
+// number of active SMs, profiles/r1c_*).  Here each CTA of a 2-CTA cluster loads HALF of every K-block (64 of the 128
+// tile rows) and multicasts it into both CTAs' ring slots, so a TPC fetches each tile once.  The MMAs stay 1-SM
+// (cta_group::1, M = N = 128: a 2-SM M=256/N=128 version issued at ~111 cycles per MMA instead of 64 and was slower,
+// profiles/r1c_fwd_pair_trace.log).  The row block is the A operand and lives in TMEM (128 lanes x dim/2 columns,
+// written once with tcgen05.st), so shared memory holds only the ring (6 slots of two 16 KB K-blocks) and its read
+// traffic is the B operand alone.  A ring slot is refilled once BOTH CTAs' MMAs have consumed it: every MMA thread
+// commits (multicast) onto the `empty` barrier of both CTAs (count 2).
+static constexpr int F2_STAGES = 6;
+static constexpr int F2_SLOT = 32768;   // two K-blocks of 128 rows x 128 bytes
+static constexpr int F2_XCOL = 256;     // first TMEM column of the resident row block
+static constexpr int F2_EPI_WARPS = 16; // two groups of 8: group g owns logit buffer g and the tiles t = g (mod 2)
+static constexpr int F2_THREADS = 64 + F2_EPI_WARPS * 32;
+
+struct Fwd2Smem {
+  static constexpr uint32_t ring_off = 0;
+  static constexpr uint32_t bar_off = F2_STAGES * F2_SLOT;
+  static constexpr uint32_t colbuf_off = bar_off + 256;                     // [4][4 quarters][128] floats
+  static constexpr uint32_t rowbuf_off = colbuf_off + 4 * 4 * 128 * 4;      // [2 column halves][128] floats
+  static constexpr uint32_t total = rowbuf_off + 2 * 128 * 4 + 1024;
+};
+static_assert(Fwd2Smem::total <= 232448, "pair forward: shared memory budget");
+
+// Optional wait-time accounting of the first cluster (make trace; profiles/fwd_trace.py).  Slots: MMA thread of CTA 0
+// 0 x_full, 1 tmem_empty, 2 full, 3 total, 4 tiles | TMA thread 5 empty (CTA 0), 6 empty (CTA 1) | epilogue warp 2:
+// 7 tmem_full (CTA 0), 8 loads+math (both), 9 column sums (both), 10 total (CTA 0), 11 tmem_full (CTA 1),
+// 12 prologue (both), 13 total (CTA 1)
+__device__ unsigned long long g_f2_trace[32];
+#ifdef TCL_PAIR_TRACE
+#define FT_DECL unsigned long long ft_t0 = 0; const bool ft_on = blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) <= 2); (void)ft_t0;
+#define FT_BEGIN() do { if (ft_on) ft_t0 = clock64(); } while (0)
+#define FT_END(slot) do { if (ft_on) { const unsigned long long ft_t1 = clock64(); atomicAdd(&g_f2_trace[slot], ft_t1 - ft_t0); ft_t0 = ft_t1; } } while (0)
+#else
+#define FT_DECL
+#define FT_BEGIN() do {} while (0)
+#define FT_END(slot) do {} while (0)
+#endif
+
+__global__ void __launch_bounds__(F2_THREADS, 1) ntxent_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const int num_kb = P.num_kb;
+  const uint32_t ring = base + Fwd2Smem::ring_off;
+  const uint32_t bars = base + Fwd2Smem::bar_off;
+  auto full_bar = [&](int s) { return bars + 8u * s; };                   // own TMA thread arms it; bytes from both CTAs
+  auto empty_bar = [&](int s) { return bars + 8u * (F2_STAGES + s); };    // count 2: the MMA threads of both CTAs
+  const uint32_t x_full_bar = bars + 8u * (2 * F2_STAGES);
+  auto tmem_full_bar = [&](int b) { return bars + 8u * (2 * F2_STAGES + 1 + b); };
+  auto tmem_empty_bar = [&](int b) { return bars + 8u * (2 * F2_STAGES + 3 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * F2_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + Fwd2Smem::bar_off + 8u * (2 * F2_STAGES + 5));
+  float* colbuf = reinterpret_cast<float*>(base_ptr + Fwd2Smem::colbuf_off);  // [4][4][128]
+  float* rowbuf = reinterpret_cast<float*>(base_ptr + Fwd2Smem::rowbuf_off);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  FT_DECL
+  const int ib = blockIdx.x, js = blockIdx.y, pair = blockIdx.z;  // cluster = two CTAs adjacent in x
+  const int i0 = ib * FW_BM;
+  const int t_begin = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * js) / P.n_jsplit);
+  const int t_end = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * (js + 1)) / P.n_jsplit);
+  const int n_tiles = t_end - t_begin;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&P.tm_col[pair]);
+    tma_prefetch_desc(&P.tm_row[pair]);
+    for (int s = 0; s < F2_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 2);
+    }
+    mbar_init(x_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), F2_EPI_WARPS / 2);  // the eight warps of the group that owns the buffer
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tmem_x = tmem + F2_XCOL;
+
+  // Prologue: the row block travels global -> ring slots (TMA, 16 KB K-blocks) -> registers -> TMEM.  (Per-thread row
+  // loads straight from global took ~12k cycles per CTA: 32 distinct lines per load instruction.)  The ring proper
+  // starts after the cluster barrier: until then the peer must not multicast into the slots used as staging.
+  FT_BEGIN();
+  if (warp == 0 && elect_one()) {
+    mbar_arrive_expect_tx(x_full_bar, num_kb * FW_KB_BYTES);
+    for (int kb = 0; kb < num_kb; ++kb)
+      tma_load_2d(ring + kb * FW_KB_BYTES, &P.tm_row[pair], x_full_bar, kb * FW_BK, i0);
+  }
+  if (warp >= 2) {
+    const int ew = warp - 2;
+    const int r = (warp & 3) * 32 + lane;           // row == TMEM lane
+    const int c0 = ((ew >> 3) * 2 + ((ew >> 2) & 1)) * 2;  // this thread: K-blocks c0, c0 + 1 of its row
+    mbar_wait(x_full_bar, 0);
+#pragma unroll 1
+    for (int c32 = c0; c32 < c0 + 2; ++c32) {
+      if (c32 >= num_kb) break;
+      const uint8_t* rowp = base_ptr + Fwd2Smem::ring_off + c32 * FW_KB_BYTES + r * 128;
+      uint32_t xv[32];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {  // 16-byte chunk e of the row sits at chunk position e ^ (r & 7)
+        const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((e ^ (r & 7)) << 4));
+        xv[4 * e] = u.x; xv[4 * e + 1] = u.y; xv[4 * e + 2] = u.z; xv[4 * e + 3] = u.w;
+      }
+      tmem_st_32x32b_x32(tmem_addr(tmem_x, (warp & 3) * 32, c32 * 32), xv);
+    }
+    tc_wait_st();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // row blocks are in TMEM, the staging slots are free in both CTAs, all barriers exist
+  tc_fence_after();
+  FT_END(12);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // this CTA's half of every K-block (tile rows 64 * rank .. + 64), multicast into both CTAs' slots
+      uint32_t it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int j0 = (t_begin + t) * FW_BN + static_cast<int>(crank) * 64;
+        for (int kb = 0; kb < num_kb; kb += 2, ++it) {
+          const int nk = kb + 1 < num_kb ? 2 : 1;
+          const int s = it % F2_STAGES;
+          FT_BEGIN();
+          mbar_wait_cluster(empty_bar(s), ((it / F2_STAGES) & 1) ^ 1);  // slot s is free in BOTH CTAs
+          FT_END(crank == 0 ? 5 : 6);
+          mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(nk) * FW_KB_BYTES);  // both halves of nk K-blocks
+          for (int k2 = 0; k2 < nk; ++k2)
+            tma_load_2d_multicast(ring + s * F2_SLOT + k2 * FW_KB_BYTES + crank * 8192u, &P.tm_col[pair], full_bar(s),
+                                  (kb + k2) * FW_BK, j0, 0x3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one() && n_tiles > 0) {
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long ft_m0 = clock64();
+#endif
+      uint32_t it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int b = t & 1;
+        FT_BEGIN();
+        mbar_wait(tmem_empty_bar(b), ((t >> 1) & 1) ^ 1);
+        FT_END(1);
+        tc_fence_after();
+        const uint32_t acc = tmem + b * FW_BN;
+        for (int kb = 0; kb < num_kb; kb += 2, ++it) {
+          const int nk = kb + 1 < num_kb ? 2 : 1;
+          const int s = it % F2_STAGES;
+          FT_BEGIN();
+          mbar_wait(full_bar(s), (it / F2_STAGES) & 1);
+          FT_END(2);
+          tc_fence_after();
+          for (int k2 = 0; k2 < nk; ++k2) {
+            const uint32_t ax = tmem_x + (kb + k2) * (FW_BK / 2);  // 32 columns per K-block of 64
+            const uint64_t bd = umma_desc_k_sw128(ring + s * F2_SLOT + k2 * FW_KB_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < FW_BK / 16; ++kk)
+              tc_mma_f16_ts(acc, ax + 8 * kk, bd + 2 * kk, P.idesc, (kb | k2 | kk) != 0);
+          }
+          tc_commit_multicast(empty_bar(s), 0x3);  // this CTA is done with slot s: tell both TMA threads
+        }
+        tc_commit(tmem_full_bar(b));
+      }
+#ifdef TCL_PAIR_TRACE
+      if (ft_on) { atomicAdd(&g_f2_trace[3], clock64() - ft_m0); atomicAdd(&g_f2_trace[4], (unsigned long long)n_tiles); }
+#endif
+    }
+  } else {
+    const int ew = warp - 2;
+    const int gi = ew >> 3;           // group: logit buffer gi, tiles t = gi (mod 2)
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int ch = (ew >> 2) & 1;     // column half of the tile (64 columns)
+    const int et = (ew & 7) * 32 + lane;  // 0..255 inside the group
+    const int ql = lane >> 2, p = lane & 3;
+#ifdef TCL_PAIR_TRACE
+    const unsigned long long ft_e0 = clock64();
+#endif
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    float cs[16];
+    float* diag_out = P.diag2 + static_cast<int64_t>(pair) * P.n_rows + i0;
+    const bool row_edge = i0 + FW_BM > P.n_rows;
+    for (int t = gi; t < n_tiles; t += 2) {
+      const int j0 = (t_begin + t) * FW_BN;
+      FT_BEGIN();
+      mbar_wait(tmem_full_bar(gi), (t >> 1) & 1);
+      FT_END(crank == 0 ? 7 : 11);
+      tc_fence_after();
+      const int diag_delta = P.row_offset + i0 - j0;
+      const bool has_diag = diag_delta > -FW_BN && diag_delta < FW_BM;
+      const bool masked = row_edge || (j0 + FW_BN > P.n_cols);
+      if (masked)
+        fwd_tile_epilogue<true>(tmem + gi * FW_BN, q, ch, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
+                                diag_delta, has_diag, diag_out);
+      else
+        fwd_tile_epilogue<false>(tmem + gi * FW_BN, q, ch, lane, P.c1, rs, cs, i0, j0, P.n_rows, P.n_cols,
+                                 diag_delta, has_diag, diag_out);
+      FT_END(8);
+      // this warp's part of the logit buffer is in registers -> release it to the MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(gi));
+      // the group's column-sum buffers alternate between its consecutive tiles
+      fwd_col_sums(cs, colbuf, gi * 2 + ((t >> 1) & 1), 1 + gi, q, ch, lane, p, et, j0, pair, ib, P);
+      FT_END(9);
+    }
+#ifdef TCL_PAIR_TRACE
+    if (ft_on) atomicAdd(&g_f2_trace[crank == 0 ? 10 : 13], clock64() - ft_e0);
+#endif
+    // row sums: over the 4 column-pair lanes, then group 1 hands its sums to group 0 through shared memory
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+    }
+    if (gi == 1 && p == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) rowbuf[ch * 128 + q * 32 + (r >> 1) * 16 + ql + (r & 1) * 8] = rs[r];
+    }
+    asm volatile("bar.sync 3, 512;" ::: "memory");
+    if (gi == 0 && p == 0) {
+      float* rp = P.row_part + (static_cast<int64_t>(pair) * (2 * P.n_jsplit) + 2 * js + ch) * P.n_rows;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int rl = q * 32 + (r >> 1) * 16 + ql + (r & 1) * 8;
+        if (i0 + rl < P.n_rows) rp[i0 + rl] = rs[r] + rowbuf[ch * 128 + rl];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves while the other may still multicast into its memory / signal its barriers
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+}  // namespace tcl
+extern "C" int tcl_debug_fwd_trace(unsigned long long* out32, int reset) {
+  using namespace tcl;
+  TCL_CHECK_CUDA(cudaDeviceSynchronize());
+  if (out32) TCL_CHECK_CUDA(cudaMemcpyFromSymbol(out32, g_f2_trace, sizeof(unsigned long long) * 32));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    TCL_CHECK_CUDA(cudaMemcpyToSymbol(g_f2_trace, z, sizeof(z)));
+  }
+  return TCL_OK;
+}
+namespace tcl {
 
 // fixed-order reduction of the partial buffers
 __global__ void fwd_reduce_kernel(const float* __restrict__ row_part, const float* __restrict__ col_part,
@@ -404,11 +679,23 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
 
   FwdParams P;
   memset(&P, 0, sizeof(P));
+  // The multicast CTA-pair kernel is the default for large batches (>= 2048 rows: 0.188 vs 0.195 ms at 8192 x 3
+  // pairs); below that the one-CTA-per-row-block kernel's shorter prologue wins.  TRICOLO_B200_FWD=single|pair forces one.
+  static const int fwd_mode = [] {
+    const char* e = getenv("TRICOLO_B200_FWD");
+    return e && !strcmp(e, "single") ? 1 : (e && !strcmp(e, "pair") ? 2 : 0);
+  }();
+  const bool use_pair = fwd_mode == 2 || (fwd_mode == 0 && n_rows >= 2048);
   for (int p = 0; p < n_pairs; ++p) {
     TCL_REQUIRE(zrow[p] && zcol[p], TCL_ERR_BAD_ARG, "ntxent_fwd: null operand (pair %d)", p);
+    TCL_REQUIRE(aligned_to(zrow[p], 16), TCL_ERR_BAD_ALIGN, "ntxent_fwd: operands must be 16-byte aligned");
     if (int e = make_tmap_2d_16bit(&P.tm_row[p], zrow[p], n_rows, dim, z_row_stride, FW_BM, FW_BK)) return e;
-    if (int e = make_tmap_2d_16bit(&P.tm_col[p], zcol[p], n_cols, dim, z_row_stride, FW_BN, FW_BK)) return e;
+    // pair kernel: each CTA loads its 64-row half of a column tile
+    if (int e = make_tmap_2d_16bit(&P.tm_col[p], zcol[p], n_cols, dim, z_row_stride, use_pair ? 64 : FW_BN, FW_BK)) return e;
+    P.z_row[p] = zrow[p];
   }
+  P.z_row_stride = z_row_stride;
+  P.idesc_pair = umma_idesc_f16(256, FW_BN, op_format);
   P.n_rows = (int)n_rows; P.n_cols = (int)n_cols; P.row_offset = (int)row_offset;
   P.num_kb = (int)(dim / 64);
   P.n_iblocks = (int)((n_rows + FW_BM - 1) / FW_BM);
@@ -420,15 +707,36 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
   P.col_part = P.row_part + static_cast<size_t>(n_pairs) * 2 * P.n_jsplit * n_rows;
   P.diag2 = diag2;
 
-  const int smem = (int)FwdSmem::total(P.num_kb);
-  static int smem_set = 0;
-  if (smem_set < smem) {
-    TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(P.n_iblocks, P.n_jsplit, n_pairs);
-  {
+  if (use_pair) {
+    const int smem = (int)Fwd2Smem::total;
+    static bool smem_set = false;
+    if (!smem_set) {
+      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      smem_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * ((P.n_iblocks + 1) / 2), P.n_jsplit, n_pairs);
+    cfg.blockDim = dim3(F2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(TCL_K_NTXENT_FWD, st);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_fwd_pair_kernel, P));
+  } else {
+    const int smem = (int)FwdSmem::total(P.num_kb);
+    static int smem_set = 0;
+    if (smem_set < smem) {
+      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      smem_set = smem;
+    }
+    dim3 grid(P.n_iblocks, P.n_jsplit, n_pairs);
     ProfScope prof(TCL_K_NTXENT_FWD, st);
     ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);
   }
