@@ -409,3 +409,55 @@ def test_fused_sharded_matches_unsharded(tb):
         cv.append(v); ci.append(i); nb = nb + b
     mv, mi = ops.topk_merge(torch.stack(cv), torch.stack(ci))
     assert torch.equal(mi, idx) and torch.equal(mv, val) and torch.equal(nb + 1, rank)
+
+
+@pytest.mark.parametrize("b_glob,world,interleaved", [(4096, 2, True), (2500, 1, False), (4224, 2, False)])
+def test_rank_emulation_offsets_match_unsharded(tb, b_glob, world, interleaved):
+    """The sharded form's kernel calls (row_offset / self_offset, rows per rank >= 2048 -> CTA-pair forward and
+    persistent backward with cut units, ragged 128-row blocks, modality-interleaved operand rows as in
+    tricolo_b200/distributed.py) replayed rank by rank on ONE GPU must reproduce the unsharded loss and gradients."""
+    ops = tb.ops
+    F16 = 0
+    g = torch.Generator().manual_seed(21)
+    base = torch.randn(b_glob, 512, generator=g)
+    f = [(base + 0.5 * torch.randn(b_glob, 512, generator=g)).bfloat16().float().cuda() for _ in range(3)]
+    dev = [x.clone().requires_grad_(True) for x in f]
+    losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA)
+    losses.sum().backward()
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    inv_tau = 1.0 / TAU
+    b_loc = b_glob // world
+    if interleaved:
+        zbuf = torch.empty((b_glob, 3 * 512), dtype=torch.float16, device="cuda")
+        outs = [zbuf.view(b_glob, 3, 512)[:, m] for m in range(3)]
+        z_all, invs, xs = ops.l2norm_fwd(f, F16, out=outs)
+    else:
+        z_all, invs, xs = ops.l2norm_fwd(f, F16)
+    fw = []
+    for r in range(world):
+        sl = slice(r * b_loc, (r + 1) * b_loc)
+        fw.append(ops.ntxent_fwd([z_all[a][sl] for a, _ in pairs], [z_all[b] for _, b in pairs], r * b_loc, inv_tau, F16))
+    col_sum = sum(x[1] for x in fw)
+    fin = [ops.ntxent_finalize(fw[r][0], col_sum, fw[r][2], r * b_loc, inv_tau, ALPHA, want_loss=False) for r in range(world)]
+    lse2_row_all = torch.cat([x[0] for x in fin], dim=1).contiguous()
+    lse2_col = fin[0][1]
+    parts = sum(x[2] for x in fin)
+    loss = (ALPHA * parts[:, 0] + (1.0 - ALPHA) * parts[:, 1]) / b_glob
+    assert torch.allclose(loss, losses.detach(), rtol=1e-5)
+    ones = torch.ones((3,), dtype=torch.float32, device="cuda")
+    zts, ld_t = ops.transpose_for_bwd(z_all)
+    for r in range(world):
+        sl = slice(r * b_loc, (r + 1) * b_loc)
+        jobs = []
+        for m in range(3):
+            segs = []
+            for p, (a, b) in enumerate(pairs):
+                if m == a:
+                    segs.append(ops.BwdSegmentSpec(z_all[b], zts[b], lse2_row_all[p, sl], lse2_col[p], ones[p:p + 1], ALPHA, 1.0 - ALPHA))
+                elif m == b:
+                    segs.append(ops.BwdSegmentSpec(z_all[a], zts[a], lse2_col[p, sl], lse2_row_all[p], ones[p:p + 1], 1.0 - ALPHA, ALPHA))
+            jobs.append(ops.BwdJobSpec(z_all[m][sl], xs[m][sl], invs[m][sl], segs))
+        dxs = ops.ntxent_bwd(jobs, b_glob, r * b_loc, ld_t, inv_tau, F16)
+        for m in range(3):
+            ref = dev[m].grad[sl]
+            assert torch.allclose(dxs[m], ref, rtol=1e-4, atol=1e-5 * ref.abs().max().item()), (r, m)
