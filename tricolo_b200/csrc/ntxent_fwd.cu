@@ -620,21 +620,20 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
 }
 
 static int fwd_split(int n_pairs, int n_iblocks, int n_jtiles) {
-  // One CTA per SM: choose the split of the column sweep that fills whole waves of 148 SMs best.
-  // Small problems (fewer CTAs than SMs) split down to one tile per CTA for latency; large ones keep
-  // >= 8 tiles per CTA so the resident row block (128 KB) is amortised.
+  // One CTA per SM.  Cost model of a split s of the column sweep: waves(s) x (prologue + tiles per CTA), the
+  // prologue (row block into shared memory / TMEM, pipeline fill) being worth about two tiles.  Small problems end up
+  // with one tile per CTA (latency), large ones with the split that fills whole waves of 148 SMs.
   const int ctas = n_pairs * n_iblocks;
-  const int min_tiles = ctas >= kNumSMsB200 ? 8 : 1;
-  int max_split = n_jtiles / min_tiles > 0 ? n_jtiles / min_tiles : 1;
-  if (max_split > 64) max_split = 64;
+  const double prologue = 2.0;
   int best = 1;
-  double best_eff = 0.0;
+  double best_cost = 0.0;
+  const int max_split = n_jtiles < 64 ? n_jtiles : 64;
   for (int s = 1; s <= max_split; ++s) {
     const int total = ctas * s;
     const int waves = (total + kNumSMsB200 - 1) / kNumSMsB200;
-    const double eff = static_cast<double>(total) / (static_cast<double>(waves) * kNumSMsB200);
-    if (eff > best_eff + 0.02) {
-      best_eff = eff;
+    const double cost = waves * (prologue + static_cast<double>((n_jtiles + s - 1) / s));
+    if (s == 1 || cost < best_cost * 0.98) {
+      best_cost = cost;
       best = s;
     }
   }

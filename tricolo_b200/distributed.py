@@ -33,8 +33,8 @@ def _world(group=None):
 
 
 class _GlobalNTXent(torch.autograd.Function):
-    """Three collectives in the forward (one all-gather of all modalities, one all-reduce of the column
-    sums, one all-gather of row LSEs + loss partials); none in the backward."""
+    """Two collectives in the forward (one all-gather of all modalities, one all-reduce of the sum-exp
+    statistics); none in the backward."""
 
     @staticmethod
     def forward(ctx, temperature, alpha, op_format, pairs, group, grad_world_scale, *feats):
@@ -59,18 +59,16 @@ class _GlobalNTXent(torch.autograd.Function):
         z_own = [z[row_offset:row_offset + b_loc] for z in z_all]  # local rows inside the gathered buffer
         row_sum, col_sum, diag2 = ops.ntxent_fwd([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs],
                                                  row_offset, inv_tau, op_format)
-        dist.all_reduce(col_sum, group=group)
-        lse2_row, lse2_col, parts, _ = ops.ntxent_finalize(row_sum, col_sum, diag2, row_offset, inv_tau, alpha,
-                                                           want_loss=False)
-        # row LSEs of every rank (the backward meets all rows when a local column block is "self") and the
-        # loss partials travel in one all-gather
-        pack = torch.cat([lse2_row.reshape(-1), parts.reshape(-1)])
-        packs = torch.empty((world * pack.numel(),), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(packs, pack, group=group)
-        packs = packs.view(world, pack.numel())
-        lse2_row_all = packs[:, :p * b_loc].reshape(world, p, b_loc).permute(1, 0, 2).reshape(p, b_glob).contiguous()
-        parts_sum = packs[:, p * b_loc:].reshape(world, p, 2).sum(dim=0)
-        loss = (alpha * parts_sum[:, 0] + (1.0 - alpha) * parts_sum[:, 1]) / b_glob
+        # ONE all-reduce carries the column sum-exp partials and, each rank writing only its own row range of a zeroed
+        # buffer, every rank's row sums and positives: afterwards every rank finalises ALL rows itself (row LSEs of
+        # all ranks are needed by the backward when a local column block is "self"), no second exchange
+        stats = torch.zeros((3, p, b_glob), dtype=torch.float32, device=dev)
+        stats[0].copy_(col_sum)
+        stats[1, :, row_offset:row_offset + b_loc].copy_(row_sum)
+        stats[2, :, row_offset:row_offset + b_loc].copy_(diag2)
+        dist.all_reduce(stats, group=group)
+        lse2_row_all, lse2_col, _, loss = ops.ntxent_finalize(stats[1], stats[0], stats[2], 0, inv_tau, alpha,
+                                                              want_loss=True)
         ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
         ctx.save_for_backward(lse2_row_all, lse2_col, z_glob, *xs, *invs)
         return loss
