@@ -578,20 +578,24 @@ __global__ void fwd_reduce_kernel(const float* __restrict__ row_part, const floa
   }
 }
 
-// lse + loss; one block per pair, fixed-order tree so the result is reproducible
+// lse + loss; one cluster of FIN_CTAS blocks per pair, fixed-order trees (inside a block, then over the blocks in
+// rank order through distributed shared memory) so the result is reproducible and needs no global scratch
+static constexpr int FIN_CTAS = 8;
 __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
     int n_rows, int n_cols, int row_offset, float c1, float alpha, const float* __restrict__ row_sum,
     const float* __restrict__ col_sum, const float* __restrict__ diag2, float* __restrict__ lse2_row,
     float* __restrict__ lse2_col, float* __restrict__ loss_parts, float* __restrict__ loss) {
-  const int pair = blockIdx.x;
+  const int pair = blockIdx.y;
+  const int crank = static_cast<int>(cluster_ctarank());
   const float* rs = row_sum + static_cast<int64_t>(pair) * n_rows;
   const float* cs = col_sum + static_cast<int64_t>(pair) * n_cols;
   const float* dg = diag2 + static_cast<int64_t>(pair) * n_rows;
   float* lr = lse2_row + static_cast<int64_t>(pair) * n_rows;
   float* lc = lse2_col + static_cast<int64_t>(pair) * n_cols;
-  for (int j = threadIdx.x; j < n_cols; j += blockDim.x) lc[j] = log2f(cs[j]) + c1;
+  const int tid = crank * blockDim.x + threadIdx.x, nth = FIN_CTAS * blockDim.x;
+  for (int j = tid; j < n_cols; j += nth) lc[j] = log2f(cs[j]) + c1;
   double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+  for (int i = tid; i < n_rows; i += nth) {
     const float l = log2f(rs[i]) + c1;
     lr[i] = l;
     a += static_cast<double>(l - dg[i]);
@@ -599,6 +603,7 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
     if (j < n_cols) b += static_cast<double>((log2f(cs[j]) + c1) - dg[i]);
   }
   __shared__ double sa[1024], sb[1024];
+  __shared__ double part[2 * FIN_CTAS];  // rank 0's copy collects the block sums
   sa[threadIdx.x] = a;
   sb[threadIdx.x] = b;
   __syncthreads();
@@ -610,8 +615,19 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    const uint32_t dst = map_to_peer(smem_u32(part), 0u) + 16u * crank;
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst), "d"(sa[0]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst + 8u), "d"(sb[0]) : "memory");
+  }
+  cluster_sync_all();
+  if (crank == 0 && threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int r = 0; r < FIN_CTAS; ++r) {
+      ta += part[2 * r];
+      tb += part[2 * r + 1];
+    }
     const double ln2 = 0.69314718055994530942;
-    const double pa = sa[0] * ln2, pb = sb[0] * ln2;
+    const double pa = ta * ln2, pb = tb * ln2;
     loss_parts[pair * 2 + 0] = static_cast<float>(pa);
     loss_parts[pair * 2 + 1] = static_cast<float>(pb);
     if (loss != nullptr)
@@ -761,8 +777,22 @@ extern "C" int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, 
   const float c1 = inv_tau * 1.4426950408889634f;
   {
     ProfScope prof(TCL_K_FWD_FINALIZE, static_cast<cudaStream_t>(stream));
-    fwd_finalize_kernel<<<n_pairs, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-        (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss);
+    const int nmax = (int)(n_rows > n_cols ? n_rows : n_cols);
+    int threads = 32;
+    while (threads < 1024 && threads * FIN_CTAS < nmax) threads <<= 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(FIN_CTAS, n_pairs, 1);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FIN_CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_finalize_kernel, (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha,
+                                      row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss));
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
