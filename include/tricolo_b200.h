@@ -72,6 +72,16 @@ int tcl_l2norm_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, i
 int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t x_row_stride,
                    void* y, int op_format, void* stream);
 
+/* Gallery build of the device-resident evaluation hand-off: replaces the host loops of
+ * TriCoLoNet._collate_output (tricolo_net.py:125-158: shape = zeros + image + voxel, fp32) and the
+ * first-occurrence de-duplication of construct_embeddings_matrix (eval_retrieval.py:49-56):
+ *   out16[g, :] = round16( src[0][index[g], :] (+ src[1][index[g], :]) )      g < n_out
+ * The sum is formed in fp32 in the reference's order.  n_src in {1, 2}; all sources share dtype,
+ * shape [n_src_rows, dim] and row stride; index values must lie in [0, n_src_rows). dim % 8 == 0. */
+int tcl_gather_sum_cast16(int n_src, const void* const* src_host_ptrs, int src_dtype, int64_t n_src_rows,
+                          int64_t dim, int64_t src_row_stride, const int64_t* index, int64_t n_out,
+                          void* out16, int op_format, void* stream);
+
 /* [rows, dim] 16-bit -> [dim, ld_t] 16-bit (ld_t >= rows, ld_t % 8 == 0); operand
  * layout of the gradient GEMM in tcl_ntxent_bwd. */
 int tcl_transpose_16bit(int n_tensors, const void* const* z_host_ptrs, int64_t rows, int64_t dim,
@@ -249,7 +259,8 @@ enum {
   TCL_K_GATHER_GT = 10,
   TCL_K_TOPK_MERGE = 11,
   TCL_K_SIM_TOPK_FUSED = 12,
-  TCL_K_COUNT = 13
+  TCL_K_GATHER_SUM = 13,
+  TCL_K_COUNT = 14
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);

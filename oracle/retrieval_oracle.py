@@ -149,3 +149,36 @@ def make_integer_kat(seed=42, n_shapes=50, dim=16, captions=3):
             te[flip] = rng.integers(-1, 2, 4)
             tuples.append((None, "c", f"m{s}", te, shape[s]))
     return tuples
+
+
+def make_val_batches(seed=11, n_shapes=300, n_items=2000, dim=128, batch=192, noise=14.0):
+    """Validation-epoch shaped input of tricolo_net.py:78-88: a list of (data_dict, output_dict) batches with
+    text / image / voxel features (float32 numpy), model ids with repeats and categories.  image and voxel lie on a
+    1/64 grid so that image + voxel (tricolo_net.py:135-139) is exact in bf16 as well as in fp32; text is bf16-exact."""
+    rng = np.random.default_rng(seed)
+    img = np.clip(np.round(rng.standard_normal((n_shapes, dim)) * 16) / 64, -1.5, 1.5).astype(np.float32)
+    vox = np.clip(np.round(rng.standard_normal((n_shapes, dim)) * 16) / 64, -1.5, 1.5).astype(np.float32)
+    shape = img + vox
+    owner = rng.permutation(np.concatenate([np.arange(n_shapes), rng.integers(0, n_shapes, n_items - n_shapes)]))
+    batches = []
+    for s in range(0, n_items, batch):
+        own = owner[s:s + batch]
+        te = shape[own] + noise * rng.standard_normal((len(own), dim)).astype(np.float32) / np.sqrt(dim)
+        te = bf16_round(te.astype(np.float32))
+        data = {"model_id": [f"m{int(o):04d}" for o in own], "category": [f"c{int(o) % 3}" for o in own]}
+        out = {"text_features": te, "image_features": img[own].copy(), "voxel_features": vox[own].copy()}
+        batches.append((data, out))
+    return batches
+
+
+def make_self_retrieval(seed=5, n=500, dim=64):
+    """fit == query input of the self-retrieval branch (eval_retrieval.py:84-98), bf16-exact."""
+    rng = np.random.default_rng(seed)
+    return bf16_round(rng.standard_normal((n, dim)).astype(np.float32))
+
+
+def topk_margin(sim, k):
+    """Per row: the smallest gap between consecutive values among the k+1 largest (fp64); rows whose margin
+    exceeds the fp32 rounding of the GPU's similarities must reproduce the reference's order exactly."""
+    part = -np.sort(-sim, axis=1)[:, :k + 1]
+    return np.min(-np.diff(part, axis=1), axis=1)

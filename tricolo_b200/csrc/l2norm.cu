@@ -159,6 +159,47 @@ static int launch_fwd(const PtrPack3& pk, int n_tensors, int x_dtype, int64_t ro
   return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
 }
 
+// ---------------------------------------------------------------------------
+// Gallery build: out16[g] = round16(src0[index[g]] (+ src1[index[g]])), one warp per output row
+// ---------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) gather_sum_cast_kernel(PtrPack3 pk, int n_src, int64_t n_src_rows, int dim,
+                                                              int64_t x_stride, const int64_t* __restrict__ index,
+                                                              int64_t n_out, TOut* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (g >= n_out) return;
+  const int64_t r = index[g];
+  if (r < 0 || r >= n_src_rows) return;  // validated on the host side of the ABI's callers; never read out of range
+  const TIn* a = static_cast<const TIn*>(pk.in[0]) + r * x_stride;
+  const TIn* b = n_src > 1 ? static_cast<const TIn*>(pk.in[1]) + r * x_stride : nullptr;
+  TOut* o = out + g * dim;
+  for (int c = lane * 4; c < dim; c += 128) {
+    float va[4], vb[4] = {0.f, 0.f, 0.f, 0.f};
+    load4<TIn>(a + c, va);
+    if (b) load4<TIn>(b + c, vb);
+    // reference order: zeros, += image, += voxel  (0 + x is exact)
+    float s[4] = {(0.f + va[0]) + vb[0], (0.f + va[1]) + vb[1], (0.f + va[2]) + vb[2], (0.f + va[3]) + vb[3]};
+    if (!b) { s[0] = va[0]; s[1] = va[1]; s[2] = va[2]; s[3] = va[3]; }
+    store4<TOut>(o + c, s);
+  }
+}
+
+template <typename TIn>
+static int launch_gather_sum(const PtrPack3& pk, int n_src, int64_t n_src_rows, int dim, int64_t stride,
+                             const int64_t* index, int64_t n_out, void* out, int op_format, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((n_out + 7) / 8));
+  ProfScope prof(TCL_K_GATHER_SUM, st);
+  if (op_format == TCL_OP_F16)
+    gather_sum_cast_kernel<TIn, __half><<<grid, 256, 0, st>>>(pk, n_src, n_src_rows, dim, stride, index, n_out,
+                                                              static_cast<__half*>(out));
+  else
+    gather_sum_cast_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pk, n_src, n_src_rows, dim, stride, index, n_out,
+                                                                     static_cast<__nv_bfloat16*>(out));
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
 static size_t dtype_size(int dt) {
   return dt == TCL_DT_F32 ? 4 : dt == TCL_DT_F64 ? 8 : 2;
 }
@@ -331,6 +372,31 @@ extern "C" int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t 
   pk.in[0] = x; pk.out[0] = y;
   return launch_fwd<false>(pk, 1, x_dtype, rows, (int)dim, x_row_stride, dim, op_format, 0.f,
                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tcl_gather_sum_cast16(int n_src, const void* const* src, int src_dtype, int64_t n_src_rows, int64_t dim,
+                                     int64_t src_row_stride, const int64_t* index, int64_t n_out, void* out16,
+                                     int op_format, void* stream) {
+  TCL_REQUIRE(n_src == 1 || n_src == 2, TCL_ERR_BAD_ARG, "gather_sum: n_src %d", n_src);
+  TCL_REQUIRE(n_src_rows >= 1 && n_out >= 0 && dim >= 8 && dim % 8 == 0, TCL_ERR_BAD_SHAPE, "gather_sum: sizes");
+  TCL_REQUIRE(src && index && out16 && aligned_to(out16, 16), TCL_ERR_BAD_ALIGN, "gather_sum: null or misaligned pointer");
+  TCL_REQUIRE(src_row_stride >= dim && (src_row_stride * dtype_size(src_dtype)) % 16 == 0, TCL_ERR_BAD_ALIGN, "gather_sum: row stride");
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  if (int e = require_sm100()) return e;
+  if (n_out == 0) return TCL_OK;
+  PtrPack3 pk{};
+  for (int i = 0; i < n_src; ++i) {
+    TCL_REQUIRE(src[i] && aligned_to(src[i], 16), TCL_ERR_BAD_ALIGN, "gather_sum: source %d null or misaligned", i);
+    pk.in[i] = src[i];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (src_dtype) {
+    case TCL_DT_F32: return launch_gather_sum<float>(pk, n_src, n_src_rows, (int)dim, src_row_stride, index, n_out, out16, op_format, st);
+    case TCL_DT_F64: return launch_gather_sum<double>(pk, n_src, n_src_rows, (int)dim, src_row_stride, index, n_out, out16, op_format, st);
+    case TCL_DT_F16: return launch_gather_sum<__half>(pk, n_src, n_src_rows, (int)dim, src_row_stride, index, n_out, out16, op_format, st);
+    case TCL_DT_BF16: return launch_gather_sum<__nv_bfloat16>(pk, n_src, n_src_rows, (int)dim, src_row_stride, index, n_out, out16, op_format, st);
+  }
+  return set_error(TCL_ERR_BAD_ARG, "unknown src_dtype %d", src_dtype);
 }
 
 extern "C" int tcl_transpose_16bit(int n_tensors, const void* const* z, int64_t rows, int64_t dim,

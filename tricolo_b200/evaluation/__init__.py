@@ -8,3 +8,4 @@ from .eval_retrieval import (  # noqa: F401
     retrieve,
     metrics_from_ranks,
 )
+from .accumulator import RetrievalAccumulator, save_predictions  # noqa: F401,E402

@@ -112,22 +112,44 @@ def _flip_distances_like_reference(val: np.ndarray, block: Optional[int]) -> np.
     return out
 
 
+def _drop_self(indices: np.ndarray, n_neighbors: int, block: Optional[int]) -> np.ndarray:
+    """Self-retrieval post-pass of eval_retrieval.py:84-98 on the k+1 nearest neighbours: a row that contains its own
+    index (block-relative row number + range_start, :87/:118) loses that entry, any other row keeps its first k."""
+    n_q = indices.shape[0]
+    final = np.zeros((n_q, n_neighbors), dtype=int)
+    for s in range(0, n_q, block or n_q):
+        blk = indices[s:s + (block or n_q)]
+        own = np.arange(s, s + blk.shape[0]).reshape(-1, 1)
+        has_self = np.equal(own, blk)
+        for r in range(blk.shape[0]):
+            if has_self[r].any():
+                final[s + r] = np.delete(blk[r], np.nonzero(has_self[r])[0])[:n_neighbors]
+            else:
+                final[s + r] = blk[r, :n_neighbors]
+    return final
+
+
 def compute_nearest_neighbors(fit_embeddings_matrix, query_embeddings_matrix, n_neighbors):
-    """(distances [Q,k] f64, indices [Q,k] i64, sort_indices) like eval_retrieval.py:133-146."""
+    """(distances, indices [Q,k] i64, sort_indices) like eval_retrieval.py:133-146.  When fit == query (:139-140) the
+    reference's self-retrieval branch applies: k+1 neighbours are taken, `distances` keeps k+1 columns (:76-78) and
+    each row drops its own index (:84-98)."""
     fit = np.asarray(fit_embeddings_matrix)
     query = np.asarray(query_embeddings_matrix)
-    if fit.shape == query.shape and np.allclose(fit, query):
-        raise NotImplementedError("self-retrieval (fit == query, eval_retrieval.py:84-98) is outside the "
-                                  "text->shape path; no fallback")
+    fit_eq_query = fit.shape == query.shape and np.allclose(fit, query)
+    k_eff = n_neighbors + 1 if fit_eq_query else n_neighbors
     dev = _device()
     q16 = ops.cast_16bit(torch.from_numpy(np.ascontiguousarray(query)).to(dev), OPERAND_FORMAT)
     g16 = ops.cast_16bit(torch.from_numpy(np.ascontiguousarray(fit)).to(dev), OPERAND_FORMAT)
     sim, n_g = ops.sim_gemm(q16, g16)
     dummy = torch.zeros((sim.shape[0],), dtype=torch.int64, device=dev)
-    val, idx, _, _ = ops.topk_rank(sim, n_g, n_neighbors, dummy)
+    val, idx, _, _ = ops.topk_rank(sim, n_g, k_eff, dummy)
     n_q = query.shape[0]
-    distances = _flip_distances_like_reference(val.cpu().numpy().astype(np.float64), 3000 if n_q > 8000 else None)
-    return distances, idx.cpu().numpy().astype(np.int64), SimilarityOrder(sim, n_g)
+    block = 3000 if n_q > 8000 else None
+    distances = _flip_distances_like_reference(val.cpu().numpy().astype(np.float64), block)
+    indices = idx.cpu().numpy().astype(np.int64)
+    if fit_eq_query:
+        indices = _drop_self(indices, n_neighbors, block)
+    return distances, indices, SimilarityOrder(sim, n_g)
 
 
 def metrics_from_ranks(indices: np.ndarray, rank: np.ndarray, labels: np.ndarray, n_neighbors: int,

@@ -67,6 +67,30 @@ def cast_16bit(x: torch.Tensor, op_format: int = BF16) -> torch.Tensor:
     return y
 
 
+def gather_sum_cast16(srcs: Sequence[torch.Tensor], index: torch.Tensor, op_format: int = BF16) -> torch.Tensor:
+    """out16[g] = round16(srcs[0][index[g]] (+ srcs[1][index[g]])): gallery build of the device-resident evaluation
+    hand-off (tricolo_net.py:125-158 + eval_retrieval.py:49-56).  index: int64 device tensor."""
+    dev = L.require_cuda(*srcs, index)
+    srcs = [_rows_2d(x) for x in srcs]
+    if not 1 <= len(srcs) <= 2:
+        raise ValueError("gather_sum_cast16: one or two sources")
+    rows, dim = srcs[0].shape
+    for x in srcs:
+        if x.shape != srcs[0].shape or x.dtype != srcs[0].dtype:
+            raise ValueError("gather_sum_cast16: sources must share shape and dtype")
+    if any(x.stride(0) != srcs[0].stride(0) for x in srcs):
+        srcs = [x.contiguous() for x in srcs]
+    index = index.to(torch.int64).contiguous()
+    if index.numel() and (int(index.min()) < 0 or int(index.max()) >= rows):
+        raise IndexError("gather_sum_cast16: index out of range")
+    out = torch.empty((index.numel(), dim), dtype=L.op_torch_dtype(op_format), device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_gather_sum_cast16(len(srcs), L.ptr_array(srcs), L.dtype_code(srcs[0]), rows, dim,
+                                          srcs[0].stride(0), L.ptr(index), index.numel(), L.ptr(out), op_format,
+                                          L.stream_ptr(dev)))
+    return out
+
+
 def bwd_needs_transpose(dim: int) -> bool:
     """Whether tcl_ntxent_bwd wants the transposed operand copies for this dim (the default kernel for
     dim > 256 reads the row-major operands directly)."""
