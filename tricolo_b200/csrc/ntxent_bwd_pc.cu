@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
   const bool is_producer = crank == 0;
   PT_DECL
   const int n_chunk = (P.dim + 255) / 256;  // 256-column accumulator chunks of the consumer
+  const int x_slots = (num_kb + 1) / 2;     // producer ring slots per tile, and per staged self block
 
   if (warp == 0 && elect_one()) {
     for (int j = 0; j < TCL_MAX_TENSORS; ++j) {
@@ -207,6 +208,16 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
         uint32_t it = 0;
         while (walk.next(P, pc)) {
           const BwdJobDev& J = P.job[pc.job];
+          // the piece's self rows travel through the ring first (staging for the copy into TMEM): they are fetched
+          // while the previous piece is still being computed
+          for (int kb = 0; kb < num_kb; kb += 2, ++it) {
+            const int nk = kb + 1 < num_kb ? 2 : 1;
+            const int s = it % PC_PSTAGES;
+            mbar_wait(p_empty(s), ((it / PC_PSTAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(p_full(s), nk * BW_KB_BYTES);
+            for (int k2 = 0; k2 < nk; ++k2)
+              tma_load_2d(ring + s * PC_SLOT + k2 * BW_KB_BYTES, &J.tm_self, p_full(s), (kb + k2) * BW_BK, pc.ib * BW_BM);
+          }
           for (int t = pc.ta; t < pc.tb; ++t) {
             const BwdSegDev& sg = J.seg[t / P.n_jtiles];
             const int j0 = (t % P.n_jtiles) * BW_BN;
@@ -235,6 +246,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
           mbar_wait(x_full_bar, piece & 1);  // this piece's self rows are in TMEM
           PT_END(12);
           tc_fence_after();
+          it += static_cast<uint32_t>(x_slots);  // ring slots that staged the self rows (released by the epilogue warps)
           for (int t = pc.ta; t < pc.tb; ++t, ++tg) {
             const int b = tg % PC_SBUFS;
             PT_BEGIN();
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
       const uint32_t row_off = static_cast<uint32_t>(ch * BW_KB_BYTES + r * 128);
       uint8_t* stage_ptr = base_ptr + PcSmem::p_stage_off;
       const uint32_t s_addr = tmem_addr(tmem + gi * BW_BN, q * 32, ch * 64);
-      uint32_t tg0 = 0, s_par = 0, piece = 0;
+      uint32_t tg0 = 0, s_par = 0, piece = 0, it_ring = 0;
 #ifdef TCL_PAIR_TRACE
       const unsigned long long pt_e0 = clock64();
 #endif
@@ -296,29 +308,35 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
         // before the self block in TMEM is overwritten
         if (piece > 0) asm volatile("bar.sync 7, 512;" ::: "memory");
         {
-          // self block -> TMEM: row = lane, 16-bit element k -> column k/2; this thread: two K-blocks of its row
-          const uint16_t* zrow = J.z_self + static_cast<int64_t>(grow) * P.z_row_stride;
+          // self block ring slots -> registers -> TMEM: row = lane, 16-bit element k -> column k/2; this thread: the two
+          // K-blocks (= one ring slot) c0, c0+1 of its row.  16-byte chunk e of a row sits at chunk position e ^ (r & 7).
           const int c0 = (gi * 2 + ch) * 2;
+          if (c0 < num_kb) {
+            const uint32_t itx = it_ring + static_cast<uint32_t>(c0 >> 1);
+            const int sx = itx % PC_PSTAGES;
+            mbar_wait(p_full(sx), (itx / PC_PSTAGES) & 1);
+            const uint8_t* slot = base_ptr + PcSmem::p_ring_off + sx * PC_SLOT;
 #pragma unroll 1
-          for (int c32 = c0; c32 < c0 + 2; ++c32) {  // 32 columns = 64 elements = one K-block
-            if (c32 >= num_kb) break;
-            uint32_t xv[32];
-            if (grow < P.n_self) {
+            for (int c32 = c0; c32 < c0 + 2; ++c32) {  // 32 TMEM columns = 64 elements = one K-block
+              if (c32 >= num_kb) break;
+              const uint8_t* rowp = slot + (c32 - c0) * BW_KB_BYTES + r * 128;
+              uint32_t xv[32];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                const uint4 u = *reinterpret_cast<const uint4*>(zrow + c32 * 64 + e * 8);
+                const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((e ^ (r & 7)) << 4));
                 xv[4 * e] = u.x; xv[4 * e + 1] = u.y; xv[4 * e + 2] = u.z; xv[4 * e + 3] = u.w;
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) xv[e] = 0u;
+              tmem_st_32x32b_x32(tmem_addr(tmem_x, q * 32, c32 * 32), xv);
             }
-            tmem_st_32x32b_x32(tmem_addr(tmem_x, q * 32, c32 * 32), xv);
+            tc_wait_st();
           }
-          tc_wait_st();
           tc_fence_before();
-          __syncwarp();
+          // everyone has read its staging slot: hand the slots back to the TMA warp, then publish the TMEM block
+          asm volatile("bar.sync 8, 512;" ::: "memory");
+          if (ew == 0 && lane == 0)
+            for (int x = 0; x < x_slots; ++x) mbar_arrive(p_empty((it_ring + x) % PC_PSTAGES));
           if (lane == 0) mbar_arrive(x_full_bar);
+          it_ring += static_cast<uint32_t>(x_slots + (pc.tb - pc.ta) * x_slots);  // ring slots of this piece
         }
         PT_END(13);
         float gs[2] = {0.f, 0.f};
