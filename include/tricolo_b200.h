@@ -67,6 +67,22 @@ int tcl_l2norm_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, i
                    int64_t dim, int64_t x_row_stride, void* const* z_host_ptrs, int64_t z_row_stride,
                    int op_format, float* const* inv_norm_host_ptrs, float eps, void* stream);
 
+/* K1 fused with the all-gather of the sharded loss (tricolo_b200/distributed.py): the same computation as
+ * tcl_l2norm_fwd, but every normalised row is stored to n_dst destinations, dst r being rank r's copy of the gathered
+ * operand buffer (peer-mapped device memory, e.g. a torch symmetric-memory allocation: plain st.global over NVLink).
+ *   z_dst_host_ptrs[r * n_tensors + m] = address of THIS rank's first row of modality m inside rank r's buffer.
+ * No synchronisation: the caller brackets the call with cross-device barriers (nobody still reads the buffers before,
+ * every rank's rows have landed after).  n_dst <= TCL_MAX_PEERS. */
+#define TCL_MAX_PEERS 8
+int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t rows, int64_t dim,
+                         int64_t x_row_stride, int n_dst, void* const* z_dst_host_ptrs, int64_t z_row_stride,
+                         int op_format, float* const* inv_norm_host_ptrs, float eps, void* stream);
+
+/* out[i] = sum over r < n_src (in that order) of src[r][i], fp32: the one-shot all-reduce of the sum-exp statistics
+ * over peer-mapped buffers (every rank reads all ranks' partials and adds them in rank order, so all ranks get
+ * bit-identical sums).  n % 4 == 0, 16-byte aligned pointers. */
+int tcl_peer_sum_f32(int n_src, const float* const* src_host_ptrs, int64_t n, float* out, void* stream);
+
 /* 16-bit cast without normalisation (retrieval uses the raw dot product,
  * eval_retrieval.py:74).  Accepts f32/f64/f16/bf16 input. */
 int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t x_row_stride,
@@ -260,7 +276,8 @@ enum {
   TCL_K_TOPK_MERGE = 11,
   TCL_K_SIM_TOPK_FUSED = 12,
   TCL_K_GATHER_SUM = 13,
-  TCL_K_COUNT = 14
+  TCL_K_PEER_SUM = 14,
+  TCL_K_COUNT = 15
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);

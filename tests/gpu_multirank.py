@@ -29,21 +29,42 @@ def main():
     full = [(base + 0.5 * torch.randn(b, 512, generator=g)).bfloat16().float() for _ in range(3)]
     bl = b // world
     loc = [f[rank * bl:(rank + 1) * bl].cuda().requires_grad_(True) for f in full]
-    out = global_calculate_losses({"text_features": loc[0], "image_features": loc[1], "voxel_features": loc[2]},
-                                  "train_loss", TAU, ALPHA)
-    out["train_loss/total_loss"].backward()
     ref_l, ref_g = NO.trimodal_forward_backward(
         {"text_features": full[0].numpy(), "image_features": full[1].numpy(), "voxel_features": full[2].numpy()}, TAU, ALPHA)
-    for k, v in ref_l.items():
-        rel = abs(float(out[k].detach()) - v) / abs(v)
-        ok &= rel < 1e-3
-    errs = []
-    for m, key in enumerate(["text_features", "image_features", "voxel_features"]):
-        ref = ref_g[key][rank * bl:(rank + 1) * bl]
-        errs.append(np.linalg.norm(loc[m].grad.double().cpu().numpy() - ref) / np.linalg.norm(ref))
-    ok &= max(errs) < 1e-3
-    print(f"[rank {rank}] loss total {float(out['train_loss/total_loss'].detach()):.6f} ref {ref_l['train_loss/total_loss']:.6f} "
-          f"grad errs {['%.2e' % e for e in errs]}", flush=True)
+    results = {}
+    for transport in ("1", "0"):  # NVLink peer memory (symmetric memory) and NCCL collectives
+        os.environ["TRICOLO_B200_SYMM"] = transport
+        for x in loc:
+            x.grad = None
+        out = global_calculate_losses({"text_features": loc[0], "image_features": loc[1], "voxel_features": loc[2]},
+                                      "train_loss", TAU, ALPHA)
+        out["train_loss/total_loss"].backward()
+        for k, v in ref_l.items():
+            rel = abs(float(out[k].detach()) - v) / abs(v)
+            ok &= rel < 1e-3
+        errs = []
+        for m, key in enumerate(["text_features", "image_features", "voxel_features"]):
+            ref = ref_g[key][rank * bl:(rank + 1) * bl]
+            errs.append(np.linalg.norm(loc[m].grad.double().cpu().numpy() - ref) / np.linalg.norm(ref))
+        ok &= max(errs) < 1e-3
+        results[transport] = (float(out["train_loss/total_loss"].detach()), [x.grad.clone() for x in loc])
+        print(f"[rank {rank}] transport {'symm' if transport == '1' else 'nccl'}: loss total "
+              f"{results[transport][0]:.6f} ref {ref_l['train_loss/total_loss']:.6f} grad errs {['%.2e' % e for e in errs]}", flush=True)
+    same = abs(results["1"][0] - results["0"][0]) <= 1e-6 * abs(results["0"][0])
+    same &= all(torch.allclose(a, b, rtol=1e-5, atol=1e-9) for a, b in zip(results["1"][1], results["0"][1]))
+    ok &= same
+    # two forwards before the two backwards: the second forward must not overwrite the operands the first backward needs
+    os.environ["TRICOLO_B200_SYMM"] = "1"
+    loc2 = [(x.detach() * 0.5 + 0.1).requires_grad_(True) for x in loc]
+    for x in loc:
+        x.grad = None
+    o1 = global_calculate_losses({"text_features": loc[0], "image_features": loc[1], "voxel_features": loc[2]}, "a", TAU, ALPHA)
+    o2 = global_calculate_losses({"text_features": loc2[0], "image_features": loc2[1], "voxel_features": loc2[2]}, "a", TAU, ALPHA)
+    o2["a/total_loss"].backward()
+    o1["a/total_loss"].backward()
+    inter = all(torch.allclose(x.grad, g, rtol=1e-5, atol=1e-9) for x, g in zip(loc, results["1"][1]))
+    ok &= inter
+    print(f"[rank {rank}] symm == nccl: {same}; interleaved forwards keep their operands: {inter}", flush=True)
 
     # ---- gallery-sharded retrieval vs the unsharded single-GPU path and the oracle
     tuples = RO.make_val_shaped(seed=3, n_shapes=1486, n_queries=3000, dim=512, round_bf16=True)

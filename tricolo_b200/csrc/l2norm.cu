@@ -133,6 +133,64 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(PtrPack3 pk, int64_t ro
   }
 }
 
+// K1 + all-gather: the normalised row goes to n_dst peer-mapped buffers (st.global over NVLink for the remote ones)
+struct BcastPack {
+  const void* in[TCL_MAX_TENSORS];
+  void* out[TCL_MAX_PEERS][TCL_MAX_TENSORS];
+  float* aux[TCL_MAX_TENSORS];
+  int n_dst;
+};
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) l2norm_fwd_bcast_kernel(const __grid_constant__ BcastPack pk, int64_t rows, int dim,
+                                                               int64_t x_stride, int64_t z_stride, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const TIn* x = static_cast<const TIn*>(pk.in[blockIdx.y]) + row * x_stride;
+  constexpr int kMaxIter = 4;  // dim <= 512: the row stays in registers
+  float v[kMaxIter][4];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < dim) {
+      load4<TIn>(x + c, v[it]);
+      ss += v[it][0] * v[it][0] + v[it][1] * v[it][1] + v[it][2] * v[it][2] + v[it][3] * v[it][3];
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  if (lane == 0) pk.aux[blockIdx.y][row] = inv;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < dim) {
+      float o[4] = {v[it][0] * inv, v[it][1] * inv, v[it][2] * inv, v[it][3] * inv};
+      for (int d = 0; d < pk.n_dst; ++d)
+        store4<TOut>(static_cast<TOut*>(pk.out[d][blockIdx.y]) + row * z_stride + c, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_sum_kernel(const float* const* __restrict__ /*unused*/, int n_src,
+                                                       const float* s0, const float* s1, const float* s2, const float* s3,
+                                                       const float* s4, const float* s5, const float* s6, const float* s7,
+                                                       int64_t n4, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float* src[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+  float4 part[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    part[r] = r < n_src ? __ldcv(reinterpret_cast<const float4*>(src[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a = part[0];
+#pragma unroll
+  for (int r = 1; r < 8; ++r) {
+    if (r < n_src) { a.x += part[r].x; a.y += part[r].y; a.z += part[r].z; a.w += part[r].w; }
+  }
+  reinterpret_cast<float4*>(out)[i] = a;
+}
+
 template <typename TIn, bool kNormalise>
 static int launch_fwd_t(const PtrPack3& pk, int n_tensors, int64_t rows, int dim, int64_t stride,
                         int64_t z_stride, int op_format, float eps, cudaStream_t st) {
@@ -357,6 +415,73 @@ extern "C" int tcl_l2norm_fwd(int n_tensors, const void* const* x, int x_dtype, 
   }
   return launch_fwd<true>(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
                           static_cast<cudaStream_t>(stream));
+}
+
+template <typename TIn>
+static int launch_bcast_t(const BcastPack& pk, int n_tensors, int64_t rows, int dim, int64_t stride, int64_t z_stride,
+                          int op_format, float eps, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_tensors);
+  ProfScope prof(TCL_K_L2NORM_FWD, st);
+  if (op_format == TCL_OP_F16)
+    l2norm_fwd_bcast_kernel<TIn, __half><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
+  else
+    l2norm_fwd_bcast_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_dtype, int64_t rows, int64_t dim,
+                                    int64_t x_row_stride, int n_dst, void* const* z_dst, int64_t z_row_stride,
+                                    int op_format, float* const* inv_norm, float eps, void* stream) {
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 8 == 0, TCL_ERR_BAD_ALIGN, "l2norm_bcast: z_row_stride");
+  TCL_REQUIRE(n_tensors >= 1 && n_tensors <= TCL_MAX_TENSORS, TCL_ERR_BAD_ARG, "n_tensors %d", n_tensors);
+  TCL_REQUIRE(n_dst >= 1 && n_dst <= TCL_MAX_PEERS, TCL_ERR_BAD_ARG, "l2norm_bcast: n_dst %d", n_dst);
+  TCL_REQUIRE(rows >= 0 && dim >= 8 && dim % 8 == 0 && dim <= 512, TCL_ERR_BAD_SHAPE,
+              "l2norm_bcast: dim must be a multiple of 8 in [8, 512] (got %lld)", (long long)dim);
+  TCL_REQUIRE(x_row_stride >= dim && (x_row_stride * dtype_size(x_dtype)) % 16 == 0, TCL_ERR_BAD_ALIGN, "l2norm_bcast: row stride");
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  if (int e = require_sm100()) return e;
+  if (rows == 0) return TCL_OK;
+  BcastPack pk{};
+  pk.n_dst = n_dst;
+  for (int i = 0; i < n_tensors; ++i) {
+    TCL_REQUIRE(x[i] && inv_norm[i] && aligned_to(x[i], 16), TCL_ERR_BAD_ALIGN, "l2norm_bcast: input %d", i);
+    pk.in[i] = x[i];
+    pk.aux[i] = inv_norm[i];
+    for (int d = 0; d < n_dst; ++d) {
+      void* p = z_dst[d * n_tensors + i];
+      TCL_REQUIRE(p && aligned_to(p, 16), TCL_ERR_BAD_ALIGN, "l2norm_bcast: destination %d of tensor %d", d, i);
+      pk.out[d][i] = p;
+    }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (x_dtype) {
+    case TCL_DT_F32: return launch_bcast_t<float>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
+    case TCL_DT_F64: return launch_bcast_t<double>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
+    case TCL_DT_F16: return launch_bcast_t<__half>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
+    case TCL_DT_BF16: return launch_bcast_t<__nv_bfloat16>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
+  }
+  return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
+}
+
+extern "C" int tcl_peer_sum_f32(int n_src, const float* const* src, int64_t n, float* out, void* stream) {
+  TCL_REQUIRE(n_src >= 1 && n_src <= TCL_MAX_PEERS && src && out, TCL_ERR_BAD_ARG, "peer_sum: n_src %d", n_src);
+  TCL_REQUIRE(n >= 0 && n % 4 == 0 && aligned_to(out, 16), TCL_ERR_BAD_ALIGN, "peer_sum: n %% 4, alignment");
+  if (int e = require_sm100()) return e;
+  if (n == 0) return TCL_OK;
+  const float* s[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int r = 0; r < n_src; ++r) {
+    TCL_REQUIRE(src[r] && aligned_to(src[r], 16), TCL_ERR_BAD_ALIGN, "peer_sum: source %d", r);
+    s[r] = src[r];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n4 = n / 4;
+  ProfScope prof(TCL_K_PEER_SUM, st);
+  peer_sum_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(nullptr, n_src, s[0], s[1], s[2], s[3], s[4], s[5],
+                                                                           s[6], s[7], n4, out);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
 }
 
 extern "C" int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim,

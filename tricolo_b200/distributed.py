@@ -4,10 +4,11 @@ Training — global-negative trimodal InfoNCE (BASELINE.json configs[3]).  The r
 gathers negatives; the semantics here are "the reference loss evaluated on the
 concatenated global batch".  Each rank holds B/W rows of every modality and owns that row block
 of each logit matrix:
-    all-gather   16-bit normalised embeddings, all modalities in ONE call (interleaved rows,
-                 strided TMA operands)                          (W-1)/W * 3*B*D*2 bytes in
-    all-reduce   column sum-exp partials, 3 x [B] fp32         (fixed shift -> plain sums)
-    all-gather   row LSEs 3 x [B/W] fp32 + loss partials
+    gather       16-bit normalised embeddings, all modalities at once (interleaved rows, strided TMA operands):
+                 K1 stores its rows straight into every peer's buffer over NVLink (symmetric memory), or one
+                 NCCL all-gather                                 (W-1)/W * 3*B*D*2 bytes in
+    reduce       sum-exp statistics [3, P, B] fp32 (column partials + every rank's row sums and positives; fixed
+                 shift -> plain sums): one-shot peer read + add in rank order, or one NCCL all-reduce
 The backward is the same directional kernel as on one GPU, run for the local rows of each
 modality against ALL rows of the partner modality, so every local gradient is complete without a
 gradient reduce-scatter (the recompute the kernel does anyway replaces the exchange).
@@ -24,8 +25,64 @@ from typing import List, Sequence
 import torch
 import torch.distributed as dist
 
+import os
+import weakref
+
 from . import ops
 from .loss.nt_xent import DEFAULT_OP_FORMAT
+
+# ---------------------------------------------------------------------------------------------------------------
+# NVLink peer-memory transport of the sharded loss (default when torch symmetric memory is available;
+# TRICOLO_B200_SYMM=0 selects NCCL).  The gathered operand buffer and the statistics buffer of every rank are
+# symmetric-memory allocations mapped into every peer:
+#   * K1 writes each normalised row straight into all ranks' gathered buffers (tcl_l2norm_fwd_bcast: the all-gather
+#     is the kernel's own store traffic over NVLink), bracketed by two device-side barriers;
+#   * the sum-exp statistics are reduced one-shot: barrier, then every rank adds all ranks' partials in rank order
+#     (tcl_peer_sum_f32) - bit-identical sums everywhere, no NCCL launch.
+# Buffers are cached per (group, shapes); a forward that needs gradients holds its buffer until its backward ran.
+# ---------------------------------------------------------------------------------------------------------------
+_SYMM_CACHE = {}
+
+
+class _SymmWorkspace:
+    def __init__(self, group, world, rank, b_loc, n, dim, dt, p, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        b_glob = b_loc * world
+        self.z = symm_mem.empty((b_glob, n * dim), dtype=dt, device=dev)
+        self.hz = symm_mem.rendezvous(self.z, group if group is not None else dist.group.WORLD)
+        self.stats = symm_mem.empty((3, p, b_glob), dtype=torch.float32, device=dev)
+        self.hs = symm_mem.rendezvous(self.stats, group if group is not None else dist.group.WORLD)
+        self.z_peers = [self.hz.get_buffer(r, self.z.shape, dt) for r in range(world)]
+        self.stats_peers = [self.hs.get_buffer(r, self.stats.shape, torch.float32) for r in range(world)]
+        lo = rank * b_loc
+        # dsts[r][m]: this rank's rows of modality m inside rank r's gathered buffer
+        self.dsts = [[zp.view(b_glob, n, dim)[lo:lo + b_loc, m] for m in range(n)] for zp in self.z_peers]
+        self.busy = False  # a forward with autograd holds the gathered operands until its backward
+
+
+def _symm_enabled() -> bool:
+    return os.environ.get("TRICOLO_B200_SYMM", "1") != "0"
+
+
+def _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev):
+    """Cached symmetric workspace, or None (transport unavailable / all cached buffers still held by a pending
+    backward: the caller uses NCCL for this step).  Collective: every rank takes the same branch because the key and
+    the busy flags evolve identically on all ranks."""
+    if not _symm_enabled() or world > 8 or world < 2:
+        return None
+    key = (id(group) if group is not None else 0, world, b_loc, n, dim, dt, p, dev.index)
+    if key not in _SYMM_CACHE:
+        try:
+            _SYMM_CACHE[key] = _SymmWorkspace(group, world, rank, b_loc, n, dim, dt, p, dev)
+        except Exception as e:  # symmetric memory not supported on this system: say so once, use NCCL
+            _SYMM_CACHE[key] = None
+            if rank == 0:
+                print(f"tricolo_b200.distributed: symmetric memory unavailable ({e!r:.120}); using NCCL collectives")
+    ws = _SYMM_CACHE[key]
+    if ws is None or ws.busy:
+        return None
+    return ws
 
 
 def _world(group=None):
@@ -48,27 +105,45 @@ class _GlobalNTXent(torch.autograd.Function):
         dev = feats[0].device
         dt = ops.L.op_torch_dtype(op_format)
         # all modalities interleaved per row: [b_loc, n*dim]; modality m = columns [m*dim, (m+1)*dim) with row
-        # stride n*dim, so ONE all-gather yields every [B, dim] operand without a copy
-        z_loc = torch.empty((b_loc, n * dim), dtype=dt, device=dev)
-        z_loc3 = z_loc.view(b_loc, n, dim)
-        _, invs, xs = ops.l2norm_fwd(feats, op_format, out=[z_loc3[:, m] for m in range(n)])
-        z_glob = torch.empty((b_glob, n * dim), dtype=dt, device=dev)
-        dist.all_gather_into_tensor(z_glob, z_loc, group=group)
+        # stride n*dim, so ONE gathered buffer yields every [B, dim] operand without a copy
+        needs_grad = any(ctx.needs_input_grad[6:])
+        ws = _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev)
+        if ws is not None:
+            # peer-memory transport: K1 stores every row into all ranks' buffers; barriers before (nobody still reads
+            # the previous step's operands) and after (every rank's rows have landed everywhere)
+            ws.hz.barrier(channel=0)
+            invs, xs = ops.l2norm_fwd_bcast(feats, ws.dsts, op_format)
+            ws.hz.barrier(channel=0)
+            z_glob = ws.z
+        else:
+            z_loc = torch.empty((b_loc, n * dim), dtype=dt, device=dev)
+            z_loc3 = z_loc.view(b_loc, n, dim)
+            _, invs, xs = ops.l2norm_fwd(feats, op_format, out=[z_loc3[:, m] for m in range(n)])
+            z_glob = torch.empty((b_glob, n * dim), dtype=dt, device=dev)
+            dist.all_gather_into_tensor(z_glob, z_loc, group=group)
         z_glob3 = z_glob.view(b_glob, n, dim)
         z_all = [z_glob3[:, m] for m in range(n)]
         z_own = [z[row_offset:row_offset + b_loc] for z in z_all]  # local rows inside the gathered buffer
         row_sum, col_sum, diag2 = ops.ntxent_fwd([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs],
                                                  row_offset, inv_tau, op_format)
-        # ONE all-reduce carries the column sum-exp partials and, each rank writing only its own row range of a zeroed
+        # ONE reduction carries the column sum-exp partials and, each rank writing only its own row range of a zeroed
         # buffer, every rank's row sums and positives: afterwards every rank finalises ALL rows itself (row LSEs of
         # all ranks are needed by the backward when a local column block is "self"), no second exchange
-        stats = torch.zeros((3, p, b_glob), dtype=torch.float32, device=dev)
+        stats = ws.stats if ws is not None else torch.empty((3, p, b_glob), dtype=torch.float32, device=dev)
+        stats.zero_()
         stats[0].copy_(col_sum)
         stats[1, :, row_offset:row_offset + b_loc].copy_(row_sum)
         stats[2, :, row_offset:row_offset + b_loc].copy_(diag2)
-        dist.all_reduce(stats, group=group)
+        if ws is not None:
+            ws.hs.barrier(channel=0)
+            stats = ops.peer_sum(ws.stats_peers)  # fixed rank order: identical on every rank
+        else:
+            dist.all_reduce(stats, group=group)
         lse2_row_all, lse2_col, _, loss = ops.ntxent_finalize(stats[1], stats[0], stats[2], 0, inv_tau, alpha,
                                                               want_loss=True)
+        if ws is not None and needs_grad:
+            ws.busy = True
+            ctx.symm_ws = ws
         ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
         ctx.save_for_backward(lse2_row_all, lse2_col, z_glob, *xs, *invs)
         return loss
@@ -108,6 +183,9 @@ class _GlobalNTXent(torch.autograd.Function):
         if jobs:
             for m, dx in zip(owners, ops.ntxent_bwd(jobs, b_glob, row_offset, ld_t, inv_tau, op_format)):
                 grads[m] = dx
+        ws = getattr(ctx, "symm_ws", None)
+        if ws is not None:
+            ws.busy = False  # the gathered operands may be overwritten by the next forward (after its first barrier)
         return (None, None, None, None, None, None, *grads)
 
 

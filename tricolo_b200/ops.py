@@ -57,6 +57,43 @@ def l2norm_fwd(xs: Sequence[torch.Tensor], op_format: int = F16, eps: float = EP
     return zs, invs, xs
 
 
+def l2norm_fwd_bcast(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence[torch.Tensor]], op_format: int = F16,
+                     eps: float = EPS):
+    """K1 fused with the all-gather: dsts[r][m] = view of THIS rank's rows of modality m inside rank r's gathered
+    buffer (peer-mapped memory).  Returns ([inv_norm], xs).  The caller provides the cross-device barriers."""
+    dev = L.require_cuda(*xs)
+    xs = [_rows_2d(x) for x in xs]
+    rows, dim = xs[0].shape
+    for x in xs:
+        if x.shape != xs[0].shape or x.dtype != xs[0].dtype:
+            raise ValueError("l2norm_fwd_bcast: all tensors must share shape and dtype")
+    if not all(x.stride(0) == xs[0].stride(0) for x in xs):
+        xs = [x.contiguous() for x in xs]
+    flat = [d for per_rank in dsts for d in per_rank]
+    if any(d.shape != (rows, dim) or d.stride(1) != 1 for d in flat) or len(flat) != len(dsts) * len(xs):
+        raise ValueError("l2norm_fwd_bcast: every destination is a [rows, dim] view, one per (rank, modality)")
+    inv_all = torch.empty((len(xs), rows), dtype=torch.float32, device=dev)
+    invs = [inv_all[m] for m in range(len(xs))]
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_l2norm_fwd_bcast(len(xs), L.ptr_array(xs), L.dtype_code(xs[0]), rows, dim, xs[0].stride(0),
+                                         len(dsts), L.ptr_array(flat), _z_stride(flat), op_format, L.ptr_array(invs),
+                                         eps, L.stream_ptr(dev)))
+    return invs, xs
+
+
+def peer_sum(srcs: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = srcs[0] + srcs[1] + ... in that order (fp32, same shape): one-shot all-reduce over peer-mapped buffers."""
+    dev = L.require_cuda(srcs[0])
+    if out is None:
+        out = torch.empty(srcs[0].shape, dtype=torch.float32, device=dev)
+    n = out.numel()
+    if any(t.numel() != n or t.dtype != torch.float32 or not t.is_contiguous() for t in list(srcs) + [out]):
+        raise ValueError("peer_sum: contiguous fp32 tensors of one size")
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_peer_sum_f32(len(srcs), L.ptr_array(list(srcs)), n, L.ptr(out), L.stream_ptr(dev)))
+    return out
+
+
 def cast_16bit(x: torch.Tensor, op_format: int = BF16) -> torch.Tensor:
     dev = L.require_cuda(x)
     x = _rows_2d(x)
