@@ -56,8 +56,15 @@ class _SymmWorkspace:
         self.z_peers = [self.hz.get_buffer(r, self.z.shape, dt) for r in range(world)]
         self.stats_peers = [self.hs.get_buffer(r, self.stats.shape, torch.float32) for r in range(world)]
         lo = rank * b_loc
-        # dsts[r][m]: this rank's rows of modality m inside rank r's gathered buffer
-        self.dsts = [[zp.view(b_glob, n, dim)[lo:lo + b_loc, m] for m in range(n)] for zp in self.z_peers]
+        esz = self.z.element_size()
+        self.z_row_stride = n * dim
+        # destinations of K1's stores: address of this rank's first row of modality m inside each target: one store
+        # per peer-mapped buffer.  TRICOLO_B200_MULTICAST=1 stores ONCE to the NVLink multicast (NVLS) mapping instead
+        # and lets the switch replicate; correct, but measured slower at N=2 (47 vs 29 us for K1), so opt-in.
+        mc = int(self.hz.multicast_ptr) if os.environ.get("TRICOLO_B200_MULTICAST", "0") == "1" else 0
+        bases = [mc] if mc else [int(zp.data_ptr()) for zp in self.z_peers]
+        self.multicast = bool(mc)
+        self.dsts = [[base + (lo * n * dim + m * dim) * esz for m in range(n)] for base in bases]
         self.busy = False  # a forward with autograd holds the gathered operands until its backward
 
 
@@ -112,7 +119,7 @@ class _GlobalNTXent(torch.autograd.Function):
             # peer-memory transport: K1 stores every row into all ranks' buffers; barriers before (nobody still reads
             # the previous step's operands) and after (every rank's rows have landed everywhere)
             ws.hz.barrier(channel=0)
-            invs, xs = ops.l2norm_fwd_bcast(feats, ws.dsts, op_format)
+            invs, xs = ops.l2norm_fwd_bcast(feats, ws.dsts, ws.z_row_stride, op_format)
             ws.hz.barrier(channel=0)
             z_glob = ws.z
         else:

@@ -57,10 +57,11 @@ def l2norm_fwd(xs: Sequence[torch.Tensor], op_format: int = F16, eps: float = EP
     return zs, invs, xs
 
 
-def l2norm_fwd_bcast(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence[torch.Tensor]], op_format: int = F16,
+def l2norm_fwd_bcast(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence], z_row_stride: int, op_format: int = F16,
                      eps: float = EPS):
-    """K1 fused with the all-gather: dsts[r][m] = view of THIS rank's rows of modality m inside rank r's gathered
-    buffer (peer-mapped memory).  Returns ([inv_norm], xs).  The caller provides the cross-device barriers."""
+    """K1 fused with the all-gather: dsts[r][m] = device address (int) of THIS rank's first row of modality m inside
+    destination r - a peer-mapped buffer of rank r, or ONE NVLink-multicast mapping that the switch replicates to
+    every rank.  z_row_stride in elements.  Returns ([inv_norm], xs).  The caller provides the cross-device barriers."""
     dev = L.require_cuda(*xs)
     xs = [_rows_2d(x) for x in xs]
     rows, dim = xs[0].shape
@@ -69,14 +70,15 @@ def l2norm_fwd_bcast(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence[torch.T
             raise ValueError("l2norm_fwd_bcast: all tensors must share shape and dtype")
     if not all(x.stride(0) == xs[0].stride(0) for x in xs):
         xs = [x.contiguous() for x in xs]
-    flat = [d for per_rank in dsts for d in per_rank]
-    if any(d.shape != (rows, dim) or d.stride(1) != 1 for d in flat) or len(flat) != len(dsts) * len(xs):
-        raise ValueError("l2norm_fwd_bcast: every destination is a [rows, dim] view, one per (rank, modality)")
+    flat = [int(d) for per_dst in dsts for d in per_dst]
+    if len(flat) != len(dsts) * len(xs):
+        raise ValueError("l2norm_fwd_bcast: one destination address per (destination, modality)")
     inv_all = torch.empty((len(xs), rows), dtype=torch.float32, device=dev)
     invs = [inv_all[m] for m in range(len(xs))]
+    dst_arr = (C.c_void_p * len(flat))(*flat)
     with torch.cuda.device(dev):
         L.check(LIB.tcl_l2norm_fwd_bcast(len(xs), L.ptr_array(xs), L.dtype_code(xs[0]), rows, dim, xs[0].stride(0),
-                                         len(dsts), L.ptr_array(flat), _z_stride(flat), op_format, L.ptr_array(invs),
+                                         len(dsts), dst_arr, z_row_stride, op_format, L.ptr_array(invs),
                                          eps, L.stream_ptr(dev)))
     return invs, xs
 
