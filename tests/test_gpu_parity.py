@@ -461,3 +461,41 @@ def test_rank_emulation_offsets_match_unsharded(tb, b_glob, world, interleaved):
         for m in range(3):
             ref = dev[m].grad[sl]
             assert torch.allclose(dxs[m], ref, rtol=1e-4, atol=1e-5 * ref.abs().max().item()), (r, m)
+
+
+def test_bcast_normalise_and_peer_sum_single_gpu(tb):
+    """tcl_l2norm_fwd_bcast with several local destinations must equal tcl_l2norm_fwd bit for bit (on a multi-GPU
+    box the destinations are peer-mapped buffers: tests/gpu_multirank.py); tcl_peer_sum_f32 adds in the given order."""
+    ops = tb.ops
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(300, 512, generator=g).cuda() for _ in range(3)]
+    xs[1][7] = 0  # clamped row
+    zs, invs, _ = ops.l2norm_fwd(xs, 0)
+    bufs = [torch.zeros((700, 3 * 512), dtype=torch.float16, device="cuda") for _ in range(3)]
+    lo = 200
+    dsts = [[b.data_ptr() + (lo * 3 * 512 + m * 512) * 2 for m in range(3)] for b in bufs]
+    invs2, _ = ops.l2norm_fwd_bcast(xs, dsts, 3 * 512, 0)
+    for b in bufs:
+        v = b.view(700, 3, 512)
+        for m in range(3):
+            assert torch.equal(v[lo:lo + 300, m], zs[m])
+            assert torch.equal(invs2[m], invs[m])
+        assert float(v[:lo].abs().max()) == 0 and float(v[lo + 300:].abs().max()) == 0
+    parts = [torch.randn(3, 3, 1000, generator=g).cuda() for _ in range(5)]
+    want = parts[0].clone()
+    for p in parts[1:]:
+        want = want + p
+    assert torch.equal(ops.peer_sum(parts), want)
+
+
+def test_gather_sum_cast16(tb):
+    ops = tb.ops
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(500, 256, generator=g).cuda()
+    b = torch.randn(500, 256, generator=g).cuda()
+    idx = torch.randint(0, 500, (137,), generator=g).cuda()
+    got = ops.gather_sum_cast16([a, b], idx, 1)
+    assert torch.equal(got, (a[idx] + b[idx]).bfloat16())
+    assert torch.equal(ops.gather_sum_cast16([a], idx, 0), a[idx].half())
+    with pytest.raises(IndexError):
+        ops.gather_sum_cast16([a], torch.tensor([500], device="cuda"), 1)
