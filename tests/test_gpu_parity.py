@@ -499,3 +499,36 @@ def test_gather_sum_cast16(tb):
     assert torch.equal(ops.gather_sum_cast16([a], idx, 0), a[idx].half())
     with pytest.raises(IndexError):
         ops.gather_sum_cast16([a], torch.tensor([500], device="cuda"), 1)
+
+
+def test_host_pipelined_loss_matches_direct(tb):
+    """HostPipelinedLoss (H2D / graph replay / D2H of consecutive steps on three streams) returns, for every step,
+    exactly what the direct call returns for that step's inputs."""
+    from tricolo_b200.graphs import HostPipelinedLoss
+
+    g = torch.Generator().manual_seed(31)
+    steps = []
+    for _ in range(7):
+        base = torch.randn(384, 512, generator=g)
+        steps.append([(base + 0.5 * torch.randn(384, 512, generator=g)).pin_memory() for _ in range(3)])
+    want = []
+    for fs in steps:
+        dv = [f.cuda().requires_grad_(True) for f in fs]
+        ls = tb.loss.trimodal_ntxent(dv, TAU, ALPHA)
+        ls.sum().backward()
+        want.append((ls.detach().cpu(), [d.grad.cpu() for d in dv]))
+    pipe = HostPipelinedLoss(steps[0], TAU, ALPHA, depth=3)
+    tickets, got = [], []
+    for k, fs in enumerate(steps):
+        tickets.append(pipe.submit(fs))
+        if k >= 2:
+            ls, gr = pipe.result(tickets[k - 2])
+            got.append((ls.clone(), [x.clone() for x in gr]))
+    for t in tickets[-2:]:
+        ls, gr = pipe.result(t)
+        got.append((ls.clone(), [x.clone() for x in gr]))
+    assert len(got) == len(want)
+    for (l0, g0), (l1, g1) in zip(got, want):
+        assert torch.equal(l0, l1)
+        for a, b in zip(g0, g1):
+            assert torch.equal(a, b)
