@@ -296,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
     traffic = None
     try:  # DRAM bytes per launch of the same kernel at the same shapes, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1d_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
             traffic = json.load(f).get("ntxent_bwd_pc_kernel") if (world == 1 and batch == 8192) else None
     except Exception:
         traffic = None
