@@ -75,6 +75,28 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 // ntxent_bwd_pc.cu: persistent; *n_clusters_out = the number of tile ranges it used (<= pc_max_pieces() per unit)
 int launch_bwd_pc(const BwdParams& P, int n_jobs, int op_format, int* n_clusters_out, cudaStream_t st);
+// ntxent_bwd_g.cu: shared-G form of the single-GPU whole-loss backward (G of a pair formed once, two GEMM passes)
+struct BwdSharedGArgs {
+  int n_tensors, n_pairs;
+  const int32_t* pair_row;
+  const int32_t* pair_col;
+  const uint8_t* need_grad;
+  const void* const* z;      // [n_tensors] normalised 16-bit operands [batch, dim], contiguous
+  const void* const* x;      // [n_tensors] original inputs
+  void* const* dx;           // [n_tensors]
+  const float* inv_norm;     // [n_tensors][batch]
+  const float* lse_row;      // [n_pairs][batch]
+  const float* lse_col;
+  const float* grad_losses;  // [n_pairs] device
+  int64_t batch, dim, x_row_stride;
+  int x_dtype, op_format;
+  float inv_tau, alpha, eps;
+  void* workspace;           // [partials (tcl_ntxent_bwd_workspace_bytes)] [G matrices]
+  size_t partials_bytes;
+};
+size_t bwd_sharedg_workspace_bytes(int n_pairs, int64_t batch);
+bool bwd_sharedg_enabled(int n_pairs, int64_t batch, int64_t dim);
+int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st);
 // ntxent_bwd_cluster.cu
 int launch_bwd_cluster(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 

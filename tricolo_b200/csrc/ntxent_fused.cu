@@ -4,7 +4,7 @@
 // sequence the kernels of l2norm.cu / ntxent_fwd.cu / ntxent_bwd.cu over one caller-allocated
 // "state" buffer (kept between forward and backward) and one scratch workspace, so that a training
 // step costs two library calls instead of seven.
-#include "host_common.h"
+#include "ntxent_bwd.h"
 #include "../../include/tricolo_b200.h"
 
 namespace tcl {
@@ -43,8 +43,9 @@ extern "C" size_t tcl_ntxent_loss_workspace_bytes(int n_tensors, int n_pairs, in
   if (n_tensors < 2 || n_tensors > TCL_MAX_TENSORS || n_pairs < 1 || n_pairs > TCL_MAX_PAIRS || batch < 1 || dim < 1) return 0;
   const size_t fwd = tcl_ntxent_fwd_workspace_bytes(n_pairs, batch, batch);
   const int64_t ld_t = (batch + 7) / 8 * 8;
-  const size_t bwd = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256) +
-                     tcl_ntxent_bwd_workspace_bytes(n_tensors, batch, dim);
+  size_t bwd = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256) +
+               align_up(tcl_ntxent_bwd_workspace_bytes(n_tensors, batch, dim), 1024);
+  if (bwd_sharedg_enabled(n_pairs, batch, dim)) bwd += bwd_sharedg_workspace_bytes(n_pairs, batch);  // G per pair
   return (fwd > bwd ? fwd : bwd) + 256;
 }
 
@@ -107,13 +108,36 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
     z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
     zt[m] = ws8 + static_cast<size_t>(m) * dim * ld_t * 2;
   }
-  const bool need_t = tcl_ntxent_bwd_needs_transpose(dim) != 0;
+  const size_t zt_bytes = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256);
+  const bool need_t = tcl_ntxent_bwd_needs_transpose(dim) != 0 && !bwd_sharedg_enabled(n_pairs, batch, dim);
   if (need_t) {
     if (int e = tcl_transpose_16bit(n_tensors, z, batch, dim, 0, zt, ld_t, stream)) return e;
   }
-  const size_t zt_bytes = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256);
   const float* lse_row = reinterpret_cast<const float*>(st8 + L.lse_row);
   const float* lse_col = reinterpret_cast<const float*>(st8 + L.lse_col);
+  if (bwd_sharedg_enabled(n_pairs, batch, dim)) {
+    // one GPU, whole batch: the pair's gradient matrix G is formed once and shared by both of its tensors
+    for (int p = 0; p < n_pairs; ++p)
+      TCL_REQUIRE(pair_row[p] >= 0 && pair_row[p] < n_tensors && pair_col[p] >= 0 && pair_col[p] < n_tensors &&
+                      pair_row[p] != pair_col[p], TCL_ERR_BAD_ARG, "loss_bwd: pair %d out of range", p);
+    TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+    TCL_REQUIRE(dim % 64 == 0 && dim <= 512, TCL_ERR_BAD_SHAPE, "loss_bwd: dim %lld", (long long)dim);
+    if (int e = require_sm100()) return e;
+    BwdSharedGArgs a;
+    a.n_tensors = n_tensors; a.n_pairs = n_pairs;
+    a.pair_row = pair_row; a.pair_col = pair_col; a.need_grad = need_grad;
+    a.z = z; a.x = x; a.dx = dx;
+    a.inv_norm = reinterpret_cast<const float*>(st8 + L.inv);
+    a.lse_row = lse_row; a.lse_col = lse_col; a.grad_losses = grad_losses;
+    a.batch = batch; a.dim = dim; a.x_row_stride = x_row_stride;
+    a.x_dtype = x_dtype; a.op_format = op_format;
+    a.inv_tau = inv_tau; a.alpha = alpha; a.eps = eps;
+    a.workspace = ws8 + zt_bytes;
+    a.partials_bytes = align_up(tcl_ntxent_bwd_workspace_bytes(n_tensors, batch, dim), 1024);
+    for (int m = 0; m < n_tensors; ++m)
+      TCL_REQUIRE(!need_grad[m] || dx[m] != nullptr, TCL_ERR_BAD_ARG, "loss_bwd: dx[%d] is null", m);
+    return launch_bwd_sharedg(a, static_cast<cudaStream_t>(stream));
+  }
   tcl_bwd_job jobs[TCL_MAX_TENSORS];
   memset(jobs, 0, sizeof(jobs));
   int n_jobs = 0;
