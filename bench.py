@@ -286,21 +286,39 @@ def run_ours(args, rank, world, local_rank):
     if "ntxent_bwd" in kern:
         # executed flop of the gradient kernel per algorithmic flop: the producer/consumer and pair kernels recompute
         # the logits once per direction (2x), the independent-CTA kernel once per dim half (3x)
-        bwd_mode = os.environ.get("TRICOLO_B200_BWD", "pc")
-        exec_factor = 3.0 if bwd_mode == "indep" or os.environ.get("TRICOLO_B200_BWD_NOPAIR") else 2.0
-        kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
-                                   "executed_tflops": tf(flops_bwd * exec_factor, "ntxent_bwd"), "mode": bwd_mode})
+        # the shared-G form (one GPU, >= 2048 rows) forms the logits once per pair (1.5x), the producer/consumer
+        # kernel once per direction (2x), the independent-CTA kernel once per dim half (3x)
+        bwd_mode = os.environ.get("TRICOLO_B200_BWD") or ("sharedg" if (world == 1 and batch >= 2048) else "pc")
+        exec_factor = {"indep": 3.0, "sharedg": 1.5}.get(bwd_mode, 2.0)
+        if os.environ.get("TRICOLO_B200_BWD_NOPAIR"):
+            exec_factor = 3.0
+        if bwd_mode == "sharedg" and "ntxent_g" in kern:
+            # two kernels: ntxent_g (logit recompute -> 16-bit G, 2 B^2 D per pair, not algorithmic) and the gradient
+            # GEMMs ntxent_ggemm (event id ntxent_bwd: exactly the algorithmic 4 B^2 D per pair)
+            kern["ntxent_g"].update({"bound": "tensor", "executed_tflops": tf(flops_fwd, "ntxent_g"),
+                                     "note": "logit recompute for the backward: executed, not algorithmic"})
+            kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
+                                       "executed_tflops": tf(flops_bwd, "ntxent_bwd"), "mode": bwd_mode,
+                                       "kernel": "ntxent_ggemm_kernel"})
+        else:
+            kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
+                                       "executed_tflops": tf(flops_bwd * exec_factor, "ntxent_bwd"), "mode": bwd_mode})
     if "l2norm_fwd" in kern:
         kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9})
     peak_tf = peaks["tf_sustained"]
+    bwd_is_sharedg = kern.get("ntxent_bwd", {}).get("mode") == "sharedg"
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
     traffic = None
     try:  # DRAM bytes per launch of the same kernel at the same shapes, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
-            traffic = json.load(f).get("ntxent_bwd_pc_kernel") if (world == 1 and batch == 8192) else None
+        with open(os.path.join(ROOT, "profiles", "r1f_traffic.json")) as f:
+            tj = json.load(f)
+            traffic = tj.get("ntxent_ggemm_kernel") if bwd_is_sharedg else tj.get("ntxent_bwd_pc_kernel")
+            if not (world == 1 and batch == 8192):
+                traffic = None
     except Exception:
         traffic = None
-    roofline = {"kernel": "ntxent_bwd_pc_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+    bwd_kernel = "ntxent_ggemm_kernel" if bwd_is_sharedg else "ntxent_bwd_pc_kernel"
+    roofline = {"kernel": bwd_kernel, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (ach / peak_tf) if ach else None, "traffic": traffic,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops_bwd,

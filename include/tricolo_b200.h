@@ -277,7 +277,8 @@ enum {
   TCL_K_SIM_TOPK_FUSED = 12,
   TCL_K_GATHER_SUM = 13,
   TCL_K_PEER_SUM = 14,
-  TCL_K_COUNT = 15
+  TCL_K_NTXENT_G = 15, /* shared-G backward, kernel A (logit recompute -> G); its GEMM kernel is TCL_K_NTXENT_BWD */
+  TCL_K_COUNT = 16
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);

@@ -637,9 +637,10 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   A.idesc = umma_idesc_f16(BW_BM, BW_BN, a.op_format);
   const int64_t total_a = static_cast<int64_t>(A.n_pairs) * n_iblocks * n_jtiles;
   const int ctas_a = static_cast<int>(total_a < n_sm ? total_a : n_sm);
-  prof_begin(TCL_K_NTXENT_BWD, st);
+  prof_begin(TCL_K_NTXENT_G, st);
   if (int e = (a.op_format == TCL_OP_F16 ? launch_g_kernel<TCL_OP_F16>(A, ctas_a, st) : launch_g_kernel<TCL_OP_BF16>(A, ctas_a, st)))
     return e;
+  prof_end(TCL_K_NTXENT_G, st);
 
   // ---- kernel B: per tensor, acc += A * Zother over its pairs
   GBParams B;
@@ -693,10 +694,11 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
       TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_ggemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       set = true;
     }
+    prof_begin(TCL_K_NTXENT_BWD, st);
     ntxent_ggemm_kernel<<<static_cast<unsigned>(ctas_b), GB_THREADS, smem, st>>>(B);
+    prof_end(TCL_K_NTXENT_BWD, st);
     TCL_CHECK_CUDA(cudaGetLastError());
   }
-  prof_end(TCL_K_NTXENT_BWD, st);
   N.n_clusters = static_cast<int>(ctas_b);
   N.split_rows = n_self_pad;
   N.total_tiles = total_b;
