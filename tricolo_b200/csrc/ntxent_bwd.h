@@ -12,7 +12,12 @@ static constexpr int BW_EPI_WARPS = 8;  // two per TMEM lane quarter
 static constexpr int BW_EPI_THREADS = BW_EPI_WARPS * 32;
 static constexpr int BW_THREADS = 64 + BW_EPI_THREADS;
 static constexpr int BW_DH = 256;  // dim columns per CTA
-static constexpr int kBwdMaxSplit = 8;  // fp32 gradient partials per 128-row unit the workspace provides for
+static constexpr int kBwdMaxSplit = 8;
+// The 16-bit gradient weights are stored as G * kGScale / max|grad_scale| (a power of two: exact), and the factor is
+// taken out again in fp32 by the normalise backward.  Off-diagonal entries are ~ weight / B: at B = 8192 that is 3e-5,
+// below fp16's smallest normal number (6.1e-5), where only 9 instead of 11 significant bits survive; scaled by 4096
+// every entry of interest is a normal number and the largest (|G| <= 1 on the diagonal) is far from fp16's maximum.
+static constexpr float kGScale = 4096.f;  // fp32 gradient partials per 128-row unit the workspace provides for
 
 
 struct BwdSegDev {

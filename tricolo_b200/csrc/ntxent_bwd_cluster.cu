@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_cluster_kernel(const
       gs[s] = J.seg[s].grad_scale ? *J.seg[s].grad_scale : 1.f;
       gmax = fmaxf(gmax, fabsf(gs[s]));
     }
-    const float inv_gmax = gmax > 0.f ? 1.f / gmax : 0.f;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && et == 0) *J.scale_out = gmax * P.out_scale;
+    const float inv_gmax = gmax > 0.f ? kGScale / gmax : 0.f;  // G in [-kGScale, kGScale]: see ntxent_bwd.h
+    if (blockIdx.x == 0 && blockIdx.y == 0 && et == 0) *J.scale_out = gmax * P.out_scale * (1.f / kGScale);
 
     auto load_bj = [&](int t) -> float {
       if (et >= 64 || t >= n_tiles) return 0.f;

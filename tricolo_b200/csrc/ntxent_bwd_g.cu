@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
       gs[p] = P.pair[p].grad_scale ? *P.pair[p].grad_scale : 1.f;
       gmax = fmaxf(gmax, fabsf(gs[p]));
     }
-    const float inv_gmax = gmax > 0.f ? 1.f / gmax : 0.f;
-    if (blockIdx.x == 0 && ew == 0 && lane == 0) *P.scale_out = gmax * P.out_scale;
+    const float inv_gmax = gmax > 0.f ? kGScale / gmax : 0.f;  // G in [-kGScale, kGScale]: see ntxent_bwd.h
+    if (blockIdx.x == 0 && ew == 0 && lane == 0) *P.scale_out = gmax * P.out_scale * (1.f / kGScale);
 
     while (walk.next(unit, ta, tb)) {
       const int pi = unit / P.n_iblocks;

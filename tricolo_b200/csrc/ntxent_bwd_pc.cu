@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
           gs[s] = J.seg[s].grad_scale ? *J.seg[s].grad_scale : 1.f;
           gmax = fmaxf(gmax, fabsf(gs[s]));
         }
-        const float inv_gmax = gmax > 0.f ? 1.f / gmax : 0.f;
-        if (pc.ib == 0 && pc.ta == 0 && ew == 0 && lane == 0) *J.scale_out = gmax * P.out_scale;
+        const float inv_gmax = gmax > 0.f ? kGScale / gmax : 0.f;  // G in [-kGScale, kGScale]: see ntxent_bwd.h
+        if (pc.ib == 0 && pc.ta == 0 && ew == 0 && lane == 0) *J.scale_out = gmax * P.out_scale * (1.f / kGScale);
 
         // tiles of this group in the piece: running index tg0 + (t - ta) == gi (mod 2)
         int t = pc.ta + static_cast<int>((static_cast<uint32_t>(gi) - tg0) & 1u);
