@@ -414,6 +414,12 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(batch)
+        # the same PyTorch ops as the reference loss, eager, ON this GPU (fp32 inputs, torch defaults):
+        # "the kernel to beat on the same box".  Part of the baseline leg; never on the product path.
+        try:
+            cpu["torch_eager_on_gpu"] = torch_eager_gpu_baseline(batch, dev)
+        except Exception as ex:
+            cpu["torch_eager_on_gpu"] = {"error": repr(ex)[:200]}
 
     if rank == 0:
         line = {
@@ -495,6 +501,22 @@ def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrie
                                 "ms_per_launch": ms_g / n_g_l,
                                 "hbm_write_gbs": block * g_loc * 4 / (ms_g / n_g_l * 1e-3) / 1e9}
     out["two_kernel_form"] = two
+    if world > 1:
+        # SURVEY 8(e) comparison: QUERY sharding (gallery replicated, every rank scores Q/W queries, no merge, no
+        # collective) against the gallery sharding above
+        try:
+            gen_full = torch.Generator(device=dev).manual_seed(1234)
+            gal_full = torch.randn(n_g, DIM, generator=gen_full, device=dev).bfloat16()
+            q_loc = (n_q + world - 1) // world
+            lo, hi = rank * q_loc, min((rank + 1) * q_loc, n_q)
+            fq = lambda: retrieve(text[lo:hi], gal_full, labels[lo:hi], 5)
+            fq()
+            tq = timed(fq, steps, 0)
+            msq = max_over_ranks(sum(tq)) / steps
+            out["query_sharded_comparison"] = {"ms_per_step": msq, "queries_per_s": n_q / (msq * 1e-3),
+                                               "note": "gallery replicated on every rank, Q/W queries per rank, no merge"}
+        except Exception as ex:
+            out["query_sharded_comparison"] = {"error": repr(ex)[:200]}
     return out
 
 
@@ -526,6 +548,35 @@ def cpu_baseline(batch):
             "sample": f"{n} fwd+bwd steps of the trimodal loss at B={sample_batch} (fp32, torch CPU, {cores} threads), "
                       f"scaled x{(batch // sample_batch) ** 2} to B={batch} (cost is quadratic in B)",
             "ms_per_sample_step": dt * 1e3}
+
+
+def torch_eager_gpu_baseline(batch, dev):
+    """The oracle's PyTorch port of nt_xent.py:24-74 + tricolo_net.py:56-65 run eagerly on the GPU (autograd backward)."""
+    import torch
+
+    from oracle import ntxent_oracle as NO
+
+    feats = {k: v.to(dev) for k, v in make_features(batch, batch, 0).items()}
+
+    def step():
+        fd = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+        out = NO.torch_trimodal(fd, TAU, ALPHA)
+        out["train_loss/total_loss"].backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / n
+    return {"value": batch / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "kind": "port",
+            "sample": f"{n} eager fwd+bwd steps at B={batch} on the GPU, fp32 tensors, "
+                      f"allow_tf32={torch.backends.cuda.matmul.allow_tf32}"}
 
 
 def main():

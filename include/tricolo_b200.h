@@ -177,6 +177,25 @@ int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Triplet loss: TripletLoss.forward(zis, zls) of tricolo/loss/triplet.py:202-224 with
+ * _pairwise_distances (:11-45) and their autograd; selected by loss.name=TripletLoss (config/config.yaml:102-104).
+ * Plain fp32 on a materialised B x B distance matrix (training batch sizes; the margin is below 16-bit operand
+ * resolution).  Semantics, including the reference's pairing of the norms (:32):
+ *   d2[a][b] = |zls_b|^2 - 2 <zls_a, zis_b> + |zis_a|^2, D = sqrt(max(d2,0));
+ *   terms D[i][i] - D[i][j] + margin over j != i with D[i][i] < D[i][j] < D[i][i] + margin (semi-hard), or, when there
+ *   is none, over D[i][j] < D[i][i] (hard); loss = mean of the terms.
+ * info_out (device int32[4]) = {n_semi_hard, n_hard, mode (0 semi-hard, 1 hard, 2 no term: loss = NaN, the reference
+ * divides by zero), n_terms_used}.  The workspace carries D and info from the forward to the backward.
+ * d_zis / d_zls: [batch, dim] contiguous, input dtype; either may be NULL.
+ * ------------------------------------------------------------------------- */
+size_t tcl_triplet_workspace_bytes(int64_t batch);
+int tcl_triplet_fwd(const void* zis, const void* zls, int x_dtype, int64_t batch, int64_t dim, int64_t row_stride,
+                    float margin, float* loss, int32_t* info_out, void* workspace, size_t workspace_bytes, void* stream);
+int tcl_triplet_bwd(const void* zis, const void* zls, int x_dtype, int64_t batch, int64_t dim, int64_t row_stride,
+                    float margin, const float* grad_loss, void* workspace, size_t workspace_bytes, void* d_zis,
+                    void* d_zls, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Whole-loss entry points for one GPU: the kernels above sequenced by the library, so that a
  * training step is two calls.  Replaces TriCoLoNet._calculate_losses (tricolo_net.py:56-65) +
  * NTXentLoss.forward (nt_xent.py:24-74) and their autograd.

@@ -71,6 +71,26 @@ def main():
     npz["SELFBLK.indices"] = idx.astype(np.int32)
     npz["SELFBLK.distances_head"] = dist[:4]
     npz["SELFBLK.distances_tail"] = dist[-4:]
+    # ---- triplet loss: the reference module on seeded inputs, autograd gradients
+    import torch
+    from tricolo.loss.triplet import TripletLoss
+    from oracle import triplet_oracle as TO
+
+    trip = {}
+    for name, (margin, noise, norm) in {"T1_SEMI": (0.025, 3.0, True), "T2_HARD": (1e-7, 3.0, True),
+                                        "T3_NONE": (0.025, 0.35, True), "T4_RAW": (0.025, 3.0, False)}.items():
+        zis, zls = TO.make_triplet_case(noise=noise, normalise=norm)
+        a = torch.from_numpy(zis).requires_grad_(True)
+        b = torch.from_numpy(zls).requires_grad_(True)
+        try:
+            loss = TripletLoss(margin)(a, b)
+            loss.backward()
+            trip[name] = {"loss": float(loss), "margin": margin, "noise": noise, "normalise": norm}
+            npz[f"{name}.d_zis"] = a.grad.numpy()
+            npz[f"{name}.d_zls"] = b.grad.numpy()
+        except ZeroDivisionError:
+            trip[name] = {"loss": None, "error": "ZeroDivisionError", "margin": margin, "noise": noise, "normalise": norm}
+    out["TRIPLET"] = trip
     os.chdir(cwd)
     out["numpy"] = np.__version__
     with open(os.path.join(HERE, "next_rows.json"), "w") as f:

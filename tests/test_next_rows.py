@@ -166,3 +166,87 @@ def test_self_retrieval_matches_reference(golden, case):
     else:
         assert np.allclose(dist[:4], npz["SELFBLK.distances_head"], rtol=1e-5, atol=1e-6)
         assert np.allclose(dist[-4:], npz["SELFBLK.distances_tail"], rtol=1e-5, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------- triplet loss (8f row 4)
+TRIPLET_CASES = ["T1_SEMI", "T2_HARD", "T4_RAW"]
+
+
+def _triplet_inputs(js, name):
+    from oracle import triplet_oracle as TO
+
+    c = js["TRIPLET"][name]
+    zis, zls = TO.make_triplet_case(noise=c["noise"], normalise=c["normalise"])
+    return zis, zls, c
+
+
+@pytest.mark.parametrize("name", TRIPLET_CASES)
+def test_triplet_oracle_matches_reference(golden, name):
+    from oracle import triplet_oracle as TO
+
+    js, npz = golden
+    zis, zls, c = _triplet_inputs(js, name)
+    loss, d_zis, d_zls, info = TO.triplet_forward_backward(zis, zls, c["margin"])
+    # T4_RAW: unnormalised inputs, d2 ~ 1e4: the reference's fp32 cancellation noise moves a few boundary terms
+    tol = 1e-3 if name == "T4_RAW" else 1e-5
+    assert loss == pytest.approx(c["loss"], rel=tol)
+    for got, key in ((d_zis, "d_zis"), (d_zls, "d_zls")):
+        ref = npz[f"{name}.{key}"].astype(np.float64)
+        assert np.linalg.norm(got - ref) <= max(tol, 1e-4) * np.linalg.norm(ref) * (30 if name == "T4_RAW" else 1)
+    assert info[2] == (1 if name == "T2_HARD" else 0)
+
+
+def test_triplet_oracle_no_term_raises(golden):
+    from oracle import triplet_oracle as TO
+
+    js, _ = golden
+    c = js["TRIPLET"]["T3_NONE"]
+    assert c["error"] == "ZeroDivisionError"
+    zis, zls = TO.make_triplet_case(noise=c["noise"], normalise=c["normalise"])
+    with pytest.raises(ZeroDivisionError):
+        TO.triplet_forward_backward(zis, zls, c["margin"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TRIPLET_CASES)
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_triplet_loss_matches_reference(golden, name, dtype, capsys):
+    from oracle import triplet_oracle as TO
+    from tricolo_b200.loss.triplet import TripletLoss
+
+    js, npz = golden
+    zis, zls, c = _triplet_inputs(js, name)  # bf16-exact values: both dtypes see the same numbers
+    dt = getattr(torch, dtype)
+    a = torch.from_numpy(zis).cuda().to(dt).requires_grad_(True)
+    b = torch.from_numpy(zls).cuda().to(dt).requires_grad_(True)
+    mod = TripletLoss(c["margin"])
+    assert len(list(mod.parameters())) == 0 and len(mod.state_dict()) == 0
+    loss = mod(a, b)
+    assert loss.dim() == 0 and loss.dtype == dt
+    (2.0 * loss).backward()
+    assert ("loss_list is 0" in capsys.readouterr().out) == (name == "T2_HARD")
+    o_loss, o_dzis, o_dzls, _ = TO.triplet_forward_backward(zis, zls, c["margin"])
+    loose = name == "T4_RAW" or dtype == "bfloat16"
+    assert float(loss) == pytest.approx(c["loss"], rel=1e-2 if dtype == "bfloat16" else 1e-3)
+    assert float(loss) == pytest.approx(o_loss, rel=1e-2 if dtype == "bfloat16" else (1e-3 if loose else 1e-5))
+    for got, ref in ((a.grad, o_dzis), (b.grad, o_dzls)):
+        g = got.double().cpu().numpy() / 2.0
+        assert np.linalg.norm(g - ref) <= (3e-2 if loose else 1e-4) * np.linalg.norm(ref)
+    if dtype == "float32" and name != "T4_RAW":
+        for got, key in ((a.grad, "d_zis"), (b.grad, "d_zls")):
+            ref = npz[f"{name}.{key}"].astype(np.float64)
+            assert np.linalg.norm(got.double().cpu().numpy() / 2.0 - ref) <= 1e-3 * np.linalg.norm(ref)
+
+
+@pytest.mark.gpu
+def test_triplet_no_term_raises_like_reference(golden):
+    from oracle import triplet_oracle as TO
+    from tricolo_b200.loss.triplet import TripletLoss
+
+    js, _ = golden
+    c = js["TRIPLET"]["T3_NONE"]
+    zis, zls = TO.make_triplet_case(noise=c["noise"], normalise=c["normalise"])
+    with pytest.raises(ZeroDivisionError):
+        TripletLoss(c["margin"])(torch.from_numpy(zis).cuda().requires_grad_(True), torch.from_numpy(zls).cuda())
+    with pytest.raises(RuntimeError):
+        TripletLoss(0.025)(torch.from_numpy(zis), torch.from_numpy(zls))  # CPU tensors: no fallback

@@ -73,6 +73,9 @@ SIGNATURES = {
     "tcl_l2norm_fwd_bcast": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, _pp, _i64, _i, _pp, _f, _vp]),
     "tcl_peer_sum_f32": (_i, [_i, _pp, _i64, _vp, _vp]),
     "tcl_cast_16bit": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp]),
+    "tcl_triplet_workspace_bytes": (_sz, [_i64]),
+    "tcl_triplet_fwd": (_i, [_vp, _vp, _i, _i64, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
+    "tcl_triplet_bwd": (_i, [_vp, _vp, _i, _i64, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp, _vp]),
     "tcl_transpose_16bit": (_i, [_i, _pp, _i64, _i64, _i64, _pp, _i64, _vp]),
     "tcl_gather_sum_cast16": (_i, [_i, _pp, _i, _i64, _i64, _i64, _vp, _i64, _vp, _i, _vp]),
     "tcl_ntxent_fwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
