@@ -572,3 +572,26 @@ def test_backward_forms_agree(tb, b, n_mod, monkeypatch):
         # max|grad_scale|): they differ by independent rounding noise of the size of each one's own error
         rel = float((grads["sharedg"][m] - grads["pc"][m]).norm()) / float(grads["pc"][m].norm())
         assert rel <= RTOL, (m, rel)
+
+
+@pytest.mark.parametrize("dim", [64, 192, 320, 448])
+@pytest.mark.parametrize("b", [300, 2200])
+def test_other_dims_all_kernels(tb, dim, b, monkeypatch):
+    """dim != 512: odd numbers of 64-wide K-blocks (ring slots with one block, partly empty accumulator chunks), the
+    dim <= 256 kernels, both forward kernels (b >= 2048 -> CTA pair) and both backward forms, against the oracle."""
+    g = torch.Generator().manual_seed(1000 + dim + b)
+    base = torch.randn(b, dim, generator=g)
+    feats = [(base + 0.5 * torch.randn(b, dim, generator=g)).bfloat16().float() for _ in range(3)]
+    keys = ["text_features", "image_features", "voxel_features"]
+    ref_l, ref_g = NO.trimodal_forward_backward({k: f.numpy() for k, f in zip(keys, feats)}, TAU, ALPHA)
+    names = ["train_loss/text_image_loss", "train_loss/text_voxel_loss", "train_loss/image_voxel_loss"]
+    for mode in (("sharedg", "pc") if dim > 256 else ("pc",)):
+        monkeypatch.setenv("TRICOLO_B200_BWD", mode)
+        dev = [f.cuda().requires_grad_(True) for f in feats]
+        losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA)
+        losses.sum().backward()
+        for p, k in enumerate(names):
+            assert float(losses[p].detach()) == pytest.approx(ref_l[k], rel=RTOL), (mode, k)
+        for x, k in zip(dev, keys):
+            err = np.linalg.norm(x.grad.double().cpu().numpy() - ref_g[k]) / np.linalg.norm(ref_g[k])
+            assert err <= RTOL, (mode, k, err)
