@@ -80,12 +80,9 @@ extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dt
   float* row_sum = reinterpret_cast<float*>(st8 + L.row_sum);
   float* col_sum = reinterpret_cast<float*>(st8 + L.col_sum);
   float* diag2 = reinterpret_cast<float*>(st8 + L.diag2);
-  if (int e = tcl_ntxent_fwd(n_pairs, zrow, zcol, batch, batch, dim, 0, 0, op_format, inv_tau, row_sum, col_sum, diag2,
-                             workspace, workspace_bytes, stream))
-    return e;
-  return tcl_ntxent_finalize(n_pairs, batch, batch, 0, inv_tau, alpha, row_sum, col_sum, diag2,
-                             reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
-                             reinterpret_cast<float*>(st8 + L.parts), loss, stream);
+  return ntxent_fwd_finalize_fused(n_pairs, zrow, zcol, batch, dim, op_format, inv_tau, alpha, row_sum, col_sum, diag2,
+                                   reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
+                                   reinterpret_cast<float*>(st8 + L.parts), loss, workspace, workspace_bytes, stream);
 }
 
 extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,

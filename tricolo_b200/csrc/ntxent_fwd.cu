@@ -582,17 +582,34 @@ __global__ void fwd_reduce_kernel(const float* __restrict__ row_part, const floa
 // rank order through distributed shared memory) so the result is reproducible and needs no global scratch
 static constexpr int FIN_CTAS = 8;
 __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
-    int n_rows, int n_cols, int row_offset, float c1, float alpha, const float* __restrict__ row_sum,
-    const float* __restrict__ col_sum, const float* __restrict__ diag2, float* __restrict__ lse2_row,
-    float* __restrict__ lse2_col, float* __restrict__ loss_parts, float* __restrict__ loss) {
+    int n_rows, int n_cols, int row_offset, float c1, float alpha, float* __restrict__ row_sum,
+    float* __restrict__ col_sum, const float* __restrict__ diag2, float* __restrict__ lse2_row,
+    float* __restrict__ lse2_col, float* __restrict__ loss_parts, float* __restrict__ loss,
+    const float* __restrict__ row_part, const float* __restrict__ col_part, int n_row_slots, int n_iblocks) {
   const int pair = blockIdx.y;
   const int crank = static_cast<int>(cluster_ctarank());
-  const float* rs = row_sum + static_cast<int64_t>(pair) * n_rows;
-  const float* cs = col_sum + static_cast<int64_t>(pair) * n_cols;
+  float* rs = row_sum + static_cast<int64_t>(pair) * n_rows;
+  float* cs = col_sum + static_cast<int64_t>(pair) * n_cols;
   const float* dg = diag2 + static_cast<int64_t>(pair) * n_rows;
   float* lr = lse2_row + static_cast<int64_t>(pair) * n_rows;
   float* lc = lse2_col + static_cast<int64_t>(pair) * n_cols;
   const int tid = crank * blockDim.x + threadIdx.x, nth = FIN_CTAS * blockDim.x;
+  if (row_part != nullptr) {
+    // fused with the reduction of the tile kernel's partials (single-GPU whole-loss entry: n_rows == n_cols,
+    // row_offset == 0): the same fixed summation order as fwd_reduce_kernel
+    for (int i = tid; i < n_rows; i += nth) {
+      float a = 0.f;
+      for (int s = 0; s < n_row_slots; ++s) a += row_part[(static_cast<int64_t>(pair) * n_row_slots + s) * n_rows + i];
+      rs[i] = a;
+    }
+    for (int j = tid; j < n_cols; j += nth) {
+      float a = 0.f;
+      for (int b = 0; b < n_iblocks; ++b) a += col_part[(static_cast<int64_t>(pair) * n_iblocks + b) * n_cols + j];
+      cs[j] = a;
+    }
+    // a thread reads back only what it wrote itself (same index sets: tid + k nth), so no barrier is needed as long
+    // as n_rows == n_cols and row_offset == 0 (checked on the host)
+  }
   for (int j = tid; j < n_cols; j += nth) lc[j] = log2f(cs[j]) + c1;
   double a = 0.0, b = 0.0;
   for (int i = tid; i < n_rows; i += nth) {
@@ -669,10 +686,10 @@ extern "C" size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, in
          (static_cast<size_t>(2 * n_jsplit) * n_rows + static_cast<size_t>(n_iblocks) * n_cols);
 }
 
-extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* const* zcol,
-                              int64_t n_rows, int64_t n_cols, int64_t dim, int64_t z_row_stride, int64_t row_offset,
-                              int op_format, float inv_tau, float* row_sumexp, float* col_sumexp,
-                              float* diag2, void* workspace, size_t workspace_bytes, void* stream) {
+static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* const* zcol,
+                           int64_t n_rows, int64_t n_cols, int64_t dim, int64_t z_row_stride, int64_t row_offset,
+                           int op_format, float inv_tau, float* row_sumexp, float* col_sumexp,
+                           float* diag2, void* workspace, size_t workspace_bytes, void* stream, FwdPartials* parts) {
   TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "ntxent_fwd: n_pairs %d", n_pairs);
   TCL_REQUIRE(n_rows >= 1 && n_cols >= 1 && n_rows < (1 << 24) && n_cols < (1 << 24), TCL_ERR_BAD_SHAPE,
               "ntxent_fwd: batch sizes out of range (%lld x %lld)", (long long)n_rows, (long long)n_cols);
@@ -756,6 +773,13 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
     ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
+  if (parts != nullptr) {  // the caller reduces the partials itself (fused into the finalise kernel)
+    parts->row_part = P.row_part;
+    parts->col_part = P.col_part;
+    parts->n_row_slots = 2 * P.n_jsplit;
+    parts->n_iblocks = P.n_iblocks;
+    return TCL_OK;
+  }
   const int nmax = (int)(n_rows > n_cols ? n_rows : n_cols);
   {
     ProfScope prof(TCL_K_FWD_REDUCE, st);
@@ -766,10 +790,18 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
   return TCL_OK;
 }
 
-extern "C" int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row_offset,
-                                   float inv_tau, float alpha, const float* row_sumexp,
-                                   const float* col_sumexp, const float* diag2, float* lse2_row,
-                                   float* lse2_col, float* loss_parts, float* loss, void* stream) {
+extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* const* zcol,
+                              int64_t n_rows, int64_t n_cols, int64_t dim, int64_t z_row_stride, int64_t row_offset,
+                              int op_format, float inv_tau, float* row_sumexp, float* col_sumexp,
+                              float* diag2, void* workspace, size_t workspace_bytes, void* stream) {
+  return ntxent_fwd_impl(n_pairs, zrow, zcol, n_rows, n_cols, dim, z_row_stride, row_offset, op_format, inv_tau,
+                         row_sumexp, col_sumexp, diag2, workspace, workspace_bytes, stream, nullptr);
+}
+
+static int ntxent_finalize_impl(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row_offset,
+                                float inv_tau, float alpha, float* row_sumexp, float* col_sumexp,
+                                const float* diag2, float* lse2_row, float* lse2_col, float* loss_parts, float* loss,
+                                void* stream, const FwdPartials* parts) {
   TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "finalize: n_pairs %d", n_pairs);
   TCL_REQUIRE(n_rows >= 1 && n_cols >= 1, TCL_ERR_BAD_SHAPE, "finalize: sizes");
   TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && lse2_row && lse2_col && loss_parts, TCL_ERR_BAD_ARG, "finalize: null pointer");
@@ -791,9 +823,39 @@ extern "C" int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    const float* rp = parts ? parts->row_part : nullptr;
+    const float* cp = parts ? parts->col_part : nullptr;
     TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_finalize_kernel, (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha,
-                                      row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss));
+                                      row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss, rp, cp,
+                                      parts ? parts->n_row_slots : 0, parts ? parts->n_iblocks : 0));
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
+
+extern "C" int tcl_ntxent_finalize(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row_offset,
+                                   float inv_tau, float alpha, const float* row_sumexp,
+                                   const float* col_sumexp, const float* diag2, float* lse2_row,
+                                   float* lse2_col, float* loss_parts, float* loss, void* stream) {
+  return ntxent_finalize_impl(n_pairs, n_rows, n_cols, row_offset, inv_tau, alpha, const_cast<float*>(row_sumexp),
+                              const_cast<float*>(col_sumexp), diag2, lse2_row, lse2_col, loss_parts, loss, stream, nullptr);
+}
+
+namespace tcl {
+// Whole-loss forward on one GPU (ntxent_fused.cu): tile kernel, then ONE cluster kernel that reduces the tile
+// kernel's partials and finalises (two launches instead of three) - for small batches.
+int ntxent_fwd_finalize_fused(int n_pairs, const void* const* zrow, const void* const* zcol, int64_t batch, int64_t dim,
+                              int op_format, float inv_tau, float alpha, float* row_sumexp, float* col_sumexp,
+                              float* diag2, float* lse2_row, float* lse2_col, float* loss_parts, float* loss,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  // Small batches are launch-bound: the finalise cluster reduces the partials itself (B = 256: 15 -> 9 us).  At
+  // large batches the partials are megabytes and the wide reduce kernel in front of the finalise is faster.
+  const bool fuse = batch <= 2048;
+  FwdPartials parts;
+  if (int e = ntxent_fwd_impl(n_pairs, zrow, zcol, batch, batch, dim, 0, 0, op_format, inv_tau, row_sumexp, col_sumexp,
+                              diag2, workspace, workspace_bytes, stream, fuse ? &parts : nullptr))
+    return e;
+  return ntxent_finalize_impl(n_pairs, batch, batch, 0, inv_tau, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col,
+                              loss_parts, loss, stream, fuse ? &parts : nullptr);
+}
+}  // namespace tcl
