@@ -426,7 +426,8 @@ def run_ours(args, rank, world, local_rank):
             "metric": "infonce_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if op == ops.F16 else "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd (BASELINE configs[3])",
+            "config": {"workload": (f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd (BASELINE configs[3])" if args.workload == "c4"
+                                    else f"{args.workload}: Tri(I+V) trimodal loss fwd+bwd, batch 256 (BASELINE configs[1])"),
                        "global_batch": batch, "rows_per_rank": b_loc, "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA,
                        "pairs": 3, "accumulate": "f32", "l2": "flushed (256 MB write) before every timed step",
                        "launch": launch_mode, "eager_ms_per_step": eager_ms,
