@@ -333,6 +333,38 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(NormBwdParams pr, int64
     n_split = pc_range_of(pr.total_tiles, u0 + pr.unit_tiles[blockIdx.y] - 1, pr.n_clusters) -
               pc_range_of(pr.total_tiles, u0, pr.n_clusters) + 1;
   }
+  if (n_split <= 3) {
+    // common case (1-3 partials per row): EVERY load of the row - x and all partials, up to 16 x 16 bytes per lane - is
+    // issued before anything is consumed; with the loads inside the per-128-column loop the row cost four dependent
+    // round trips to memory
+    float4 part[3][kMaxIter];
+    float xv[kMaxIter][4];
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = it * 128 + lane * 4;
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        part[s][it] = (c < dim && s < n_split)
+                          ? __ldcs(reinterpret_cast<const float4*>(jb.gpart + s * split_stride + row * dim + c))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < dim) load4<T>(x + c, xv[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < dim) {
+        // same summation order as the general path: s = 0, 1, 2
+        const float acc[4] = {part[0][it].x + part[1][it].x + part[2][it].x, part[0][it].y + part[1][it].y + part[2][it].y,
+                              part[0][it].z + part[1][it].z + part[2][it].z, part[0][it].w + part[1][it].w + part[2][it].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          g[it][e] = acc[e] * scale;
+          z[it][e] = xv[it][e] * inv;
+          dot += g[it][e] * z[it][e];
+        }
+      }
+    }
+  } else {
 #pragma unroll
   for (int it = 0; it < kMaxIter; ++it) {
     const int c = it * 128 + lane * 4;
@@ -358,6 +390,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(NormBwdParams pr, int64
         dot += g[it][e] * z[it][e];
       }
     }
+  }
   }
   dot = warp_sum(dot);
   if (clamped) dot = 0.f;
