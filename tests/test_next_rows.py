@@ -250,3 +250,25 @@ def test_triplet_no_term_raises_like_reference(golden):
         TripletLoss(c["margin"])(torch.from_numpy(zis).cuda().requires_grad_(True), torch.from_numpy(zls).cuda())
     with pytest.raises(RuntimeError):
         TripletLoss(0.025)(torch.from_numpy(zis), torch.from_numpy(zls))  # CPU tensors: no fallback
+
+
+def test_accumulator_label_logic_cpu(golden):
+    """Host half of the device-resident hand-off (labels, first occurrences, Primitives swap) needs no GPU."""
+    from tricolo_b200.evaluation import RetrievalAccumulator
+
+    js, npz = golden
+    acc = RetrievalAccumulator()
+    for d, _ in RO.make_val_batches():
+        acc._model_ids.extend(d["model_id"])
+        acc._categories.extend(d["category"])
+    labels, first_rows, m2l = acc._labels_and_first("Text2Shape")
+    assert np.array_equal(labels, npz["VAL_TRI.labels"])
+    assert len(first_rows) == js["VAL_TRI"]["n_gallery"]
+    assert [k for k, v in sorted(m2l.items(), key=lambda kv: kv[1])][:8] == js["VAL_TRI"]["label_to_model_id_head"]
+    # first_rows really are first occurrences, in first-seen order
+    seen = {}
+    for q, mid in enumerate(acc._model_ids):
+        seen.setdefault(mid, q)
+    assert list(first_rows) == list(seen.values())
+    labels_p, first_p, m2l_p = acc._labels_and_first("Primitives")  # eval_retrieval.py:45-46: ids = categories
+    assert len(first_p) == 3 and set(m2l_p) == {"c0", "c1", "c2"}
