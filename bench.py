@@ -310,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
     traffic = None
     try:  # DRAM bytes per launch of the same kernel at the same shapes, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1f_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1h_traffic.json")) as f:
             tj = json.load(f)
             traffic = tj.get("ntxent_ggemm_kernel") if bwd_is_sharedg else tj.get("ntxent_bwd_pc_kernel")
             if not (world == 1 and batch == 8192):
