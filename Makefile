@@ -17,7 +17,7 @@ $(LIB): $(OBJS)
 	@mkdir -p tricolo_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart shared
 
-# wait-time accounting build of the CTA-pair backward (profiles/pair_trace.py)
+# wait-time accounting build (profiles/pc_trace.py, profiles/fwd_trace.py)
 TRACE_LEVEL ?= 2
 EXP ?= 0
 TRACE_LIB ?= tricolo_b200/lib/libtricolo_b200_trace.so

@@ -80,7 +80,7 @@ int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x_host_ptrs, int x_dt
 
 /* out[i] = sum over r < n_src (in that order) of src[r][i], fp32: the one-shot all-reduce of the sum-exp statistics
  * over peer-mapped buffers (every rank reads all ranks' partials and adds them in rank order, so all ranks get
- * bit-identical sums).  n % 4 == 0, 16-byte aligned pointers. */
+ * bit-identical sums).  16-byte aligned pointers; any n. */
 int tcl_peer_sum_f32(int n_src, const float* const* src_host_ptrs, int64_t n, float* out, void* stream);
 
 /* 16-bit cast without normalisation (retrieval uses the raw dot product,
@@ -309,10 +309,8 @@ int tcl_profile_read(int kernel_id, double* total_ms, int64_t* launches);
  * through the 16x256b load shape; out[(warp*2+half)*32*16 + thread*16 + reg].
  * ------------------------------------------------------------------------- */
 int tcl_debug_tmem_probe(uint32_t* out, void* stream);
-/* tcl_debug_pair_trace: cycles the roles of the first CTA pair of the pair backward kernel spent in each wait
- * (32 counters, see ntxent_bwd_pair.cu; all zero unless the library was built with `make trace`). */
-int tcl_debug_pair_trace(unsigned long long* out32, int reset);
-/* tcl_debug_pc_trace: the same for the first cluster of the producer/consumer backward kernel (ntxent_bwd_pc.cu). */
+/* tcl_debug_pc_trace: cycles the roles of the first cluster of the producer/consumer backward kernel (ntxent_bwd_pc.cu)
+ * spent in each wait (32 counters; all zero unless the library was built with `make trace`). */
 int tcl_debug_pc_trace(unsigned long long* out32, int reset);
 /* tcl_debug_fwd_trace: the same for the first cluster of the CTA-pair forward kernel (ntxent_fwd.cu). */
 int tcl_debug_fwd_trace(unsigned long long* out32, int reset);

@@ -490,6 +490,9 @@ def test_bcast_normalise_and_peer_sum_single_gpu(tb):
     for p in parts[1:]:
         want = want + p
     assert torch.equal(ops.peer_sum(parts), want)
+    # odd element counts (3 * P * b_glob with an odd local batch at world 2: 3 * 3 * 114 = 1026, not a multiple of 4)
+    parts = [torch.randn(3, 3, 114, generator=g).cuda() for _ in range(2)]
+    assert torch.equal(ops.peer_sum(parts), parts[0] + parts[1])
 
 
 def test_gather_sum_cast16(tb):

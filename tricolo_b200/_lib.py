@@ -101,7 +101,6 @@ SIGNATURES = {
     "tcl_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "tcl_debug_tmem_probe": (_i, [_vp, _vp]),
     "tcl_ntxent_bwd_needs_transpose": (_i, [_i64]),
-    "tcl_debug_pair_trace": (_i, [C.POINTER(C.c_uint64), _i]),
     "tcl_debug_pc_trace": (_i, [C.POINTER(C.c_uint64), _i]),
     "tcl_debug_fwd_trace": (_i, [C.POINTER(C.c_uint64), _i]),
     "tcl_debug_max_clusters": (_i, [_i, C.POINTER(C.c_int)]),

@@ -10,7 +10,7 @@ namespace tcl {
 static std::atomic<int64_t> g_launches{0};
 static std::atomic<bool> g_prof_on{false};
 static std::mutex g_prof_mu;
-struct EvPair { cudaEvent_t a, b; };
+struct EvPair { cudaEvent_t a, b; int dev; };  // events belong to the device they were created on
 static std::vector<EvPair> g_pool[TCL_K_COUNT];
 static size_t g_used[TCL_K_COUNT];
 static constexpr size_t kMaxPairs = 1 << 14;
@@ -20,8 +20,19 @@ void prof_begin(int id, cudaStream_t st) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_used[id] >= kMaxPairs) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (g_used[id] < g_pool[id].size() && g_pool[id][g_used[id]].dev != dev) {  // pooled pair of another device: replace it
+    cudaEventDestroy(g_pool[id][g_used[id]].a);
+    cudaEventDestroy(g_pool[id][g_used[id]].b);
+    EvPair e;
+    e.dev = dev;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) { g_pool[id].resize(g_used[id]); return; }
+    g_pool[id][g_used[id]] = e;
+  }
   if (g_used[id] == g_pool[id].size()) {
     EvPair e;
+    e.dev = dev;
     if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
     g_pool[id].push_back(e);
   }

@@ -40,6 +40,24 @@ int require_sm100() {
   return TCL_OK;
 }
 
+int ensure_dyn_smem_impl(const void* func, int bytes) {
+  struct Entry { const void* func; int dev; int bytes; };
+  static std::mutex mu;
+  static Entry table[256];
+  static int n_entries = 0;
+  int dev = 0;
+  TCL_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  Entry* hit = nullptr;
+  for (int i = 0; i < n_entries; ++i)
+    if (table[i].func == func && table[i].dev == dev) { hit = &table[i]; break; }
+  if (hit && hit->bytes >= bytes) return TCL_OK;
+  TCL_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (hit) hit->bytes = bytes;
+  else if (n_entries < 256) table[n_entries++] = Entry{func, dev, bytes};  // table full: set it every time (still correct)
+  return TCL_OK;
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                         const cuuint32_t*, CUtensorMapInterleave,

@@ -32,6 +32,14 @@ int set_error(int code, const char* fmt, ...);
 // 0 when the current device is sm_100 (B200); error otherwise.  Cached per device.
 int require_sm100();
 
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  The attribute is per device, so the
+// cache is keyed by (kernel, device ordinal) and guarded by a mutex (a process may drive several GPUs / host threads).
+int ensure_dyn_smem_impl(const void* func, int bytes);
+template <typename F>
+inline int ensure_dyn_smem(F* kernel, int bytes) {
+  return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // Encode a 2D row-major [rows, cols] 16-bit tensor for TMA tiled loads with a
 // {box_cols, box_rows} box and the 128-byte swizzle.  Out-of-bounds elements
 // are zero-filled (ragged edge tiles rely on this).

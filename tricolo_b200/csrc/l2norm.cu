@@ -175,10 +175,21 @@ __global__ void __launch_bounds__(256) l2norm_fwd_bcast_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) peer_sum_kernel(const float* const* __restrict__ /*unused*/, int n_src,
                                                        const float* s0, const float* s1, const float* s2, const float* s3,
                                                        const float* s4, const float* s5, const float* s6, const float* s7,
-                                                       int64_t n4, float* __restrict__ out) {
+                                                       int64_t n4, int n_tail, float* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
   const float* src[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+  if (i >= n4) {  // the n % 4 trailing elements (odd local batches at world 2): one thread each, same rank order
+    const int64_t t = i - n4;
+    if (t < n_tail) {
+      float a = 0.f;
+      for (int r = 0; r < n_src; ++r) {
+        const float v = __ldcv(src[r] + 4 * n4 + t);
+        a = r == 0 ? v : a + v;
+      }
+      out[4 * n4 + t] = a;
+    }
+    return;
+  }
   float4 part[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
@@ -500,7 +511,7 @@ extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_d
 
 extern "C" int tcl_peer_sum_f32(int n_src, const float* const* src, int64_t n, float* out, void* stream) {
   TCL_REQUIRE(n_src >= 1 && n_src <= TCL_MAX_PEERS && src && out, TCL_ERR_BAD_ARG, "peer_sum: n_src %d", n_src);
-  TCL_REQUIRE(n >= 0 && n % 4 == 0 && aligned_to(out, 16), TCL_ERR_BAD_ALIGN, "peer_sum: n %% 4, alignment");
+  TCL_REQUIRE(n >= 0 && aligned_to(out, 16), TCL_ERR_BAD_ALIGN, "peer_sum: output alignment");
   if (int e = require_sm100()) return e;
   if (n == 0) return TCL_OK;
   const float* s[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -510,9 +521,10 @@ extern "C" int tcl_peer_sum_f32(int n_src, const float* const* src, int64_t n, f
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n4 = n / 4;
+  const int n_tail = static_cast<int>(n - 4 * n4);
   ProfScope prof(TCL_K_PEER_SUM, st);
-  peer_sum_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(nullptr, n_src, s[0], s[1], s[2], s[3], s[4], s[5],
-                                                                           s[6], s[7], n4, out);
+  peer_sum_kernel<<<static_cast<unsigned>((n4 + n_tail + 255) / 256), 256, 0, st>>>(nullptr, n_src, s[0], s[1], s[2], s[3], s[4],
+                                                                                    s[5], s[6], s[7], n4, n_tail, out);
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }

@@ -297,14 +297,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) ntxent_bwd_kernel(const __grid_
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-enum class BwdMode { Pc, Pair, Cluster, Indep };
-static BwdMode bwd_mode() {  // read once: TRICOLO_B200_BWD=pc|pair|cluster|indep (legacy switches still honoured)
+enum class BwdMode { Pc, Indep };
+static BwdMode bwd_mode() {  // read once per process: TRICOLO_B200_BWD=indep selects the one-CTA-per-dim-half kernel for dim > 256
   static const BwdMode m = [] {
     const char* e = getenv("TRICOLO_B200_BWD");
-    if (getenv("TRICOLO_B200_BWD_CLUSTER") || (e && !strcmp(e, "cluster"))) return BwdMode::Cluster;
-    if (getenv("TRICOLO_B200_BWD_NOPAIR") || (e && !strcmp(e, "indep"))) return BwdMode::Indep;
-    if (e && !strcmp(e, "pair")) return BwdMode::Pair;
-    return BwdMode::Pc;
+    return (e && !strcmp(e, "indep")) ? BwdMode::Indep : BwdMode::Pc;
   }();
   return m;
 }
@@ -380,26 +377,14 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
   P.c1 = c1;
   P.out_scale = inv_tau / static_cast<float>(n_other);
   P.idesc = umma_idesc_f16(BW_BM, BW_BN, op_format);
-  P.idesc_n64 = umma_idesc_f16(BW_BM, 64, op_format);
-  // dim > 256 has four implementations, all behind the same ABI (TRICOLO_B200_BWD=pc|pair|cluster|indep):
+  // dim > 256 has two implementations behind this entry (TRICOLO_B200_BWD=pc|indep):
   //  pc      (default) producer/consumer 2-CTA cluster, ntxent_bwd_pc.cu: logit recompute on one SM, gradient GEMM
   //          with a full-dim accumulator on the other; 8 B^2 D executed per pair.
-  //  pair    ntxent_bwd_pair.cu: both GEMMs as 2-SM M=256 MMAs, G halves exchanged both ways through DSMEM.
-  //  cluster ntxent_bwd_cluster.cu: the two dim-half CTAs share the logit recompute through DSMEM (N=64 MMAs);
-  //          correct but slower than `indep` (1.22 ms vs 1.00 ms at B=8192x3).
-  //  indep   the kernel above: one CTA per dim half, logits recomputed per half (12 B^2 D executed).
-  const BwdMode mode = bwd_mode();
-  const bool want_cluster = mode == BwdMode::Cluster, want_indep = mode == BwdMode::Indep, want_pair = mode == BwdMode::Pair;
-  const bool wide = P.n_dhalf == 2;
-  const bool use_cluster = wide && want_cluster;
-  const bool use_pair = wide && !use_cluster && want_pair;
-  const bool use_pc = wide && !use_cluster && !use_pair && !want_indep;
-  P.idesc_m256 = umma_idesc_f16(256, BW_BN, op_format);
-  P.idesc_m256_bmn = P.idesc_m256 | (1u << 16);
+  //  indep   the kernel above (the only one for dim <= 256): one CTA per dim half, logits recomputed per half
+  //          (12 B^2 D executed).
+  const bool use_pc = P.n_dhalf == 2 && bwd_mode() != BwdMode::Indep;
   P.idesc_n256 = umma_idesc_f16(BW_BM, 256, op_format) | (1u << 16);  // B operand MN-major
-  // the pair kernel walks the column tiles two at a time
-  P.n_split = use_pair ? bwd_split(n_jobs, n_iblocks, 2, (min_seg * P.n_jtiles + 1) / 2)
-                       : bwd_split(n_jobs, n_iblocks, P.n_dhalf, min_seg * P.n_jtiles);
+  P.n_split = bwd_split(n_jobs, n_iblocks, P.n_dhalf, min_seg * P.n_jtiles);
   float* ws = static_cast<float*>(workspace);
   float* scales = ws;  // 64 floats reserved
   float* gbase = ws + 64;
@@ -408,13 +393,13 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
     BwdJobDev& J = P.job[j];
     TCL_REQUIRE(src.n_segments >= 1 && src.n_segments <= 2, TCL_ERR_BAD_ARG, "ntxent_bwd: job %d has %d segments", j, src.n_segments);
     TCL_REQUIRE(src.z_self && src.x_self && src.inv_norm && src.dx, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d", j);
-    if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, z_row_stride, use_pair ? 64 : BW_BM, BW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&J.tm_self, src.z_self, n_self, dim, z_row_stride, BW_BM, BW_BK)) return e;
     J.n_seg = src.n_segments;
     J.z_self = static_cast<const uint16_t*>(src.z_self);
     for (int s = 0; s < src.n_segments; ++s) {
       const tcl_bwd_segment& sg = src.seg[s];
       TCL_REQUIRE(sg.z_other && (sg.z_other_t || !need_t) && sg.lse2_self && sg.lse2_other, TCL_ERR_BAD_ARG, "ntxent_bwd: null pointer in job %d segment %d", j, s);
-      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, use_cluster ? 64 : BW_BN, BW_BK)) return e;
+      if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other, sg.z_other, n_other, dim, z_row_stride, BW_BN, BW_BK)) return e;
       if (use_pc) {  // the gradient GEMM reads the row-major operand itself (MN-major B): boxes {64 dim, 64 rows}
         if (int e = make_tmap_2d_16bit(&J.seg[s].tm_other_t, sg.z_other, n_other, dim, z_row_stride, 64, 64)) return e;
       } else {
@@ -455,17 +440,11 @@ extern "C" int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs, int64_t n_sel
       N.unit_tiles[j] = P.unit_tiles[j];
     }
     P.n_split = kBwdMaxSplit;
-  } else if (use_pair) {
-    if (int e = launch_bwd_pair(P, n_iblocks, n_jobs, op_format, st)) return e;
-  } else if (use_cluster) {
-    if (int e = launch_bwd_cluster(P, n_iblocks, n_jobs, op_format, st)) return e;
   } else if (op_format == TCL_OP_F16) {
-    static int set = 0;
-    if (set < smem) { TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_kernel<TCL_OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = smem; }
+    if (int e = ensure_dyn_smem(ntxent_bwd_kernel<TCL_OP_F16>, smem)) return e;
     ntxent_bwd_kernel<TCL_OP_F16><<<grid, BW_THREADS, smem, st>>>(P);
   } else {
-    static int set = 0;
-    if (set < smem) { TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_bwd_kernel<TCL_OP_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = smem; }
+    if (int e = ensure_dyn_smem(ntxent_bwd_kernel<TCL_OP_BF16>, smem)) return e;
     ntxent_bwd_kernel<TCL_OP_BF16><<<grid, BW_THREADS, smem, st>>>(P);
   }
   prof_end(TCL_K_NTXENT_BWD, st);

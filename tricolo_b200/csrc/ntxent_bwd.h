@@ -1,5 +1,5 @@
-// Shared declarations of the NT-Xent backward kernels (ntxent_bwd.cu: one CTA per dim half,
-// ntxent_bwd_cluster.cu: the two dim halves as a 2-CTA cluster exchanging G through DSMEM).
+// Shared declarations of the NT-Xent backward kernels (ntxent_bwd.cu: one CTA per dim half; ntxent_bwd_pc.cu:
+// producer/consumer SM pairs; ntxent_bwd_g.cu: shared-G form, one GPU or sharded over ranks).
 #pragma once
 #include "host_common.h"
 
@@ -21,7 +21,7 @@ static constexpr float kGScale = 4096.f;  // fp32 gradient partials per 128-row 
 
 
 struct BwdSegDev {
-  CUtensorMap tm_other;    // [n_other, dim]   box {64, 128} (cluster kernel: {64, 64})
+  CUtensorMap tm_other;    // [n_other, dim]   box {64, 128}
   CUtensorMap tm_other_t;  // [dim, n_other]   box {64, 128} (producer/consumer kernel: {64, 256})
   const float* lse2_self;
   const float* lse2_other;
@@ -44,9 +44,6 @@ struct BwdParams {
   float c1;         // log2(e)/tau
   float out_scale;  // 1/(tau*n_other)
   uint32_t idesc;   // M=128, N=128
-  uint32_t idesc_n64;  // M=128, N=64 (cluster kernel: half logit tile)
-  uint32_t idesc_m256;      // M=256 (CTA pair), N=128, both operands K-major (pair kernel: logit MMA)
-  uint32_t idesc_m256_bmn;  // same with an MN-major B operand (pair kernel: gradient MMA)
   uint32_t idesc_n256;      // M=128, N=256 (producer/consumer kernel: gradient MMA)
   // persistent producer/consumer kernel: the flat tile sequence (job-major, then 128-row unit, then tile) is cut
   // into n_clusters equal contiguous ranges; a unit cut by a range boundary leaves one partial per piece
@@ -76,8 +73,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-// ntxent_bwd_pair.cu
-int launch_bwd_pair(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 // ntxent_bwd_pc.cu: persistent; *n_clusters_out = the number of tile ranges it used (<= pc_max_pieces() per unit)
 int launch_bwd_pc(const BwdParams& P, int n_jobs, int op_format, int* n_clusters_out, cudaStream_t st);
 // ntxent_bwd_g.cu: shared-G form of the single-GPU whole-loss backward (G of a pair formed once, two GEMM passes)
@@ -102,7 +97,5 @@ struct BwdSharedGArgs {
 size_t bwd_sharedg_workspace_bytes(int n_pairs, int64_t batch);
 bool bwd_sharedg_enabled(int n_pairs, int64_t batch, int64_t dim);
 int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st);
-// ntxent_bwd_cluster.cu
-int launch_bwd_cluster(const BwdParams& P, int n_iblocks, int n_jobs, int op_format, cudaStream_t st);
 
 }  // namespace tcl

@@ -584,11 +584,7 @@ bool bwd_sharedg_enabled(int n_pairs, int64_t batch, int64_t dim) {
 template <int kOp>
 static int launch_g_kernel(const GAParams& A, int n_ctas, cudaStream_t st) {
   const int smem = static_cast<int>(GASmem::total);
-  static bool set = false;
-  if (!set) {
-    TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_g_kernel<kOp>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
-  }
+  if (int e = ensure_dyn_smem(ntxent_g_kernel<kOp>, smem)) return e;
   ntxent_g_kernel<kOp><<<n_ctas, GA_THREADS, smem, st>>>(A);
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
@@ -689,11 +685,7 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   if (ctas_b < 1) ctas_b = 1;
   {
     const int smem = static_cast<int>(GBSmem::total);
-    static bool set = false;
-    if (!set) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_ggemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = true;
-    }
+    if (int e = ensure_dyn_smem(ntxent_ggemm_kernel, smem)) return e;
     prof_begin(TCL_K_NTXENT_BWD, st);
     ntxent_ggemm_kernel<<<static_cast<unsigned>(ctas_b), GB_THREADS, smem, st>>>(B);
     prof_end(TCL_K_NTXENT_BWD, st);

@@ -742,11 +742,7 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_pair) {
     const int smem = (int)Fwd2Smem::total;
-    static bool smem_set = false;
-    if (!smem_set) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      smem_set = true;
-    }
+    if (int e = ensure_dyn_smem(ntxent_fwd_pair_kernel, smem)) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * ((P.n_iblocks + 1) / 2), P.n_jsplit, n_pairs);
     cfg.blockDim = dim3(F2_THREADS);
@@ -763,11 +759,7 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
     TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_fwd_pair_kernel, P));
   } else {
     const int smem = (int)FwdSmem::total(P.num_kb);
-    static int smem_set = 0;
-    if (smem_set < smem) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(ntxent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      smem_set = smem;
-    }
+    if (int e = ensure_dyn_smem(ntxent_fwd_kernel, smem)) return e;
     dim3 grid(P.n_iblocks, P.n_jsplit, n_pairs);
     ProfScope prof(TCL_K_NTXENT_FWD, st);
     ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);

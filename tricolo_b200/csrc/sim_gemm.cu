@@ -183,11 +183,7 @@ extern "C" int tcl_sim_gemm(const void* q, const void* g, int64_t n_q, int64_t n
   CUtensorMap tm_a, tm_b;
   if (int e = make_tmap_2d_16bit(&tm_a, q, n_q, dim, dim, SG_BM, SG_BK)) return e;
   if (int e = make_tmap_2d_16bit(&tm_b, g, n_g, dim, dim, SG_BN, SG_BK)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int e = ensure_dyn_smem(sim_gemm_kernel, SG_SMEM_BYTES)) return e;
   dim3 grid(static_cast<unsigned>((n_g + SG_BN - 1) / SG_BN), static_cast<unsigned>((n_q + SG_BM - 1) / SG_BM));
   TCL_REQUIRE(grid.y <= 65535, TCL_ERR_BAD_SHAPE, "sim_gemm: more than 65535*128 query rows per call; chunk the queries");
   {

@@ -267,11 +267,7 @@ int launch_sim_gemm_resident(const void* q, const void* g, int64_t n_q, int64_t 
   const int smem = static_cast<int>(SimResSmem::total(P.num_kb));
   ProfScope prof(TCL_K_SIM_GEMM, st);
   if (cluster) {
-    static int set = 0;
-    if (set < smem) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_gemm_resident_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = smem;
-    }
+    if (int e = ensure_dyn_smem(sim_gemm_resident_kernel<2>, smem)) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_mblocks, P.n_split);
     cfg.blockDim = dim3(SR_THREADS);
@@ -286,11 +282,7 @@ int launch_sim_gemm_resident(const void* q, const void* g, int64_t n_q, int64_t 
     cfg.numAttrs = 1;
     TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sim_gemm_resident_kernel<2>, P));
   } else {
-    static int set = 0;
-    if (set < smem) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_gemm_resident_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = smem;
-    }
+    if (int e = ensure_dyn_smem(sim_gemm_resident_kernel<1>, smem)) return e;
     sim_gemm_resident_kernel<1><<<dim3(n_mblocks, P.n_split), SR_THREADS, smem, st>>>(P);
     TCL_CHECK_CUDA(cudaGetLastError());
   }

@@ -341,18 +341,10 @@ static int launch_fused(const FusedParams& P, int n_qblocks, int n_split, cudaSt
   const int smem = static_cast<int>(FusedSmem::total(P.num_kb));
   dim3 grid(n_qblocks, n_split);
   if (P.k <= 5) {
-    static int set = 0;
-    if (set < smem) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_topk_fused_kernel<5, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = smem;
-    }
+    if (int e = ensure_dyn_smem(sim_topk_fused_kernel<5, kMode>, smem)) return e;
     sim_topk_fused_kernel<5, kMode><<<grid, FT_THREADS, smem, st>>>(P);
   } else {
-    static int set = 0;
-    if (set < smem) {
-      TCL_CHECK_CUDA(cudaFuncSetAttribute(sim_topk_fused_kernel<16, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = smem;
-    }
+    if (int e = ensure_dyn_smem(sim_topk_fused_kernel<16, kMode>, smem)) return e;
     sim_topk_fused_kernel<16, kMode><<<grid, FT_THREADS, smem, st>>>(P);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
