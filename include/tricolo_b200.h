@@ -177,6 +177,43 @@ int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * K3, sharded over ranks (north_star: "each rank owns a row block of the logits, and gradients
+ * are reduce-scattered").  Semantics: the backward of the reference loss on the CONCATENATED global batch
+ * (nt_xent.py:68-74 per pair, pairs as tricolo_net.py:56-65), rank r holding rows [r*b_loc, (r+1)*b_loc).
+ *   gemm    forms the rank's row block G[b_loc x b_glob] of every pair once (16-bit, in `workspace`), then
+ *           dRow = G * Zcol for the local rows (local partials) and dCol = G^T * Zrow_local for ALL b_glob rows of
+ *           the column tensor; every 128-row piece of dCol is TMA-stored from the kernel's accumulator drain into the
+ *           OWNER rank's receive buffer (recv_ptrs[owner], peer-mapped memory: the reduce-scatter is the kernel's own
+ *           store traffic over NVLink, one slot per source rank, no atomics).  6*b_loc*b_glob*dim flop per pair.
+ *   finish  (after a cross-rank barrier the caller provides: every rank's gemm has completed) sums the local and
+ *           the received partials in a fixed order and applies the normalise backward -> dx[m] [b_loc, dim].
+ *   z_all[m]      gathered 16-bit operands [b_glob, dim] (row stride z_row_stride elements), identical on all ranks
+ *   lse_row/col   [n_pairs][b_glob] log2-domain LSEs of all rows / columns (tcl_ntxent_finalize)
+ *   recv_ptrs[r]  rank r's receive buffer as mapped into this process (recv_ptrs[rank] = the own one), each
+ *                 tcl_ntxent_bwd_sharded_recv_bytes() large, 256-byte aligned
+ *   workspace     local scratch, tcl_ntxent_bwd_sharded_workspace_bytes(), 256-byte aligned, kept until finish
+ * Requires 256 < dim <= 512, b_loc % 128 == 0, world <= TCL_MAX_PEERS, the same sizes, pair list and need_grad flags on
+ * every rank (the slot a partial lands in is a pure function of them).
+ * ------------------------------------------------------------------------- */
+size_t tcl_ntxent_bwd_sharded_workspace_bytes(int n_tensors, int n_pairs, const int32_t* pair_row,
+                                              const int32_t* pair_col, const uint8_t* need_grad_host, int64_t b_loc,
+                                              int64_t b_glob, int64_t dim, int world);
+size_t tcl_ntxent_bwd_sharded_recv_bytes(int n_tensors, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                                         const uint8_t* need_grad_host, int64_t b_loc, int64_t b_glob, int64_t dim,
+                                         int world);
+int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_all_host_ptrs, int64_t b_loc, int64_t b_glob,
+                                int64_t dim, int64_t z_row_stride, int rank, int world, int n_pairs,
+                                const int32_t* pair_row, const int32_t* pair_col, int op_format, float inv_tau,
+                                float alpha, const float* lse_row, const float* lse_col, const float* grad_losses,
+                                const uint8_t* need_grad_host, void* workspace, size_t workspace_bytes,
+                                void* const* recv_host_ptrs, size_t recv_bytes, void* stream);
+int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t b_loc,
+                                  int64_t b_glob, int64_t dim, int64_t x_row_stride, int rank, int world, int n_pairs,
+                                  const int32_t* pair_row, const int32_t* pair_col, const float* inv_norm,
+                                  const uint8_t* need_grad_host, float eps, const void* workspace,
+                                  const void* recv_own, void* const* dx_host_ptrs, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Triplet loss: TripletLoss.forward(zis, zls) of tricolo/loss/triplet.py:202-224 with
  * _pairwise_distances (:11-45) and their autograd; selected by loss.name=TripletLoss (config/config.yaml:102-104).
  * Plain fp32 on a materialised B x B distance matrix (training batch sizes; the margin is below 16-bit operand
@@ -312,6 +349,10 @@ int tcl_debug_tmem_probe(uint32_t* out, void* stream);
 /* tcl_debug_pc_trace: cycles the roles of the first cluster of the producer/consumer backward kernel (ntxent_bwd_pc.cu)
  * spent in each wait (32 counters; all zero unless the library was built with `make trace`). */
 int tcl_debug_pc_trace(unsigned long long* out32, int reset);
+/* tcl_debug_gb_trace: the same for the first ([0..31]) and the last ([32..63]) CTA of the shared-G gradient GEMM kernel
+ * (ntxent_bwd_g.cu): 0/1 TMA warp waits (G slot, operand stage), 2 TMA warp total, 3/4/5 MMA warp waits (accumulator,
+ * G tile, operand stage), 6 MMA warp total, 7 read-out wait, 8 read-out work, 9 read-out total, 10 tiles, 11 pieces. */
+int tcl_debug_gb_trace(unsigned long long* out64, int reset);
 /* tcl_debug_fwd_trace: the same for the first cluster of the CTA-pair forward kernel (ntxent_fwd.cu). */
 int tcl_debug_fwd_trace(unsigned long long* out32, int reset);
 /* tcl_debug_max_clusters: cudaOccupancyMaxActiveClusters for the producer/consumer kernel's footprint. */

@@ -137,6 +137,20 @@ def make_val_shaped(seed=0, n_shapes=1486, n_queries=7424, dim=512, noise=10.5, 
     return tuples
 
 
+def make_large_retrieval(seed=0, n_shapes=200_000, n_queries=3000, dim=512, noise=10.5):
+    """C5-shaped block (the C3 recipe with owners drawn uniformly): unit-norm Gaussian gallery of
+    n_shapes, n_queries captions = normalise(shape[owner] + noise * N(0, I) / sqrt(dim)); everything bf16-exact.
+    Returns (text [Q,D] f32, gallery [G,D] f32, labels [Q] i64) — the tensor-in form (a 200k-entry tuple list would
+    itself be the bottleneck)."""
+    rng = np.random.default_rng(seed)
+    shape = rng.standard_normal((n_shapes, dim), dtype=np.float32)
+    shape /= np.linalg.norm(shape, axis=1, keepdims=True)
+    owner = rng.integers(0, n_shapes, n_queries)
+    text = shape[owner] + np.float32(noise) * rng.standard_normal((n_queries, dim), dtype=np.float32) / np.float32(np.sqrt(dim))
+    text /= np.linalg.norm(text, axis=1, keepdims=True)
+    return bf16_round(text), bf16_round(shape), owner.astype(np.int64)
+
+
 def make_integer_kat(seed=42, n_shapes=50, dim=16, captions=3):
     """KAT-E1: integer-valued vectors -> every dot product is exact in any precision."""
     rng = np.random.default_rng(seed)

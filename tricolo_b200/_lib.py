@@ -83,6 +83,15 @@ SIGNATURES = {
     "tcl_ntxent_finalize": (_i, [_i, _i64, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_ntxent_bwd_workspace_bytes": (_sz, [_i, _i64, _i64]),
     "tcl_ntxent_bwd": (_i, [_i, C.POINTER(BwdJob), _i64, _i64, _i64, _i64, _i64, _i64, _i, _i64, _i, _f, _f, _vp, _sz, _vp]),
+    "tcl_ntxent_bwd_sharded_workspace_bytes": (_sz, [_i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
+                                                     _i64, _i64, _i64, _i]),
+    "tcl_ntxent_bwd_sharded_recv_bytes": (_sz, [_i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
+                                                _i64, _i64, _i64, _i]),
+    "tcl_ntxent_bwd_sharded_gemm": (_i, [_i, _pp, _i64, _i64, _i64, _i64, _i, _i, _i, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), _i, _f, _f, _vp, _vp, _vp, C.POINTER(C.c_uint8), _vp, _sz,
+                                         _pp, _sz, _vp]),
+    "tcl_ntxent_bwd_sharded_finish": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), _vp, C.POINTER(C.c_uint8), _f, _vp, _vp, _pp, _vp]),
     "tcl_ntxent_loss_state_bytes": (_sz, [_i, _i, _i64, _i64]),
     "tcl_ntxent_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i64]),
     "tcl_ntxent_loss_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -103,6 +112,7 @@ SIGNATURES = {
     "tcl_ntxent_bwd_needs_transpose": (_i, [_i64]),
     "tcl_debug_pc_trace": (_i, [C.POINTER(C.c_uint64), _i]),
     "tcl_debug_fwd_trace": (_i, [C.POINTER(C.c_uint64), _i]),
+    "tcl_debug_gb_trace": (_i, [C.POINTER(C.c_uint64), _i]),
     "tcl_debug_max_clusters": (_i, [_i, C.POINTER(C.c_int)]),
 }
 

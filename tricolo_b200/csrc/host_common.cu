@@ -102,6 +102,24 @@ int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64
   return TCL_OK;
 }
 
+int make_tmap_3d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n_chunks, uint64_t row_stride_elems,
+                       uint32_t box_rows, uint32_t box_chunks) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  TCL_REQUIRE(fn != nullptr, TCL_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  TCL_REQUIRE(aligned_to(base, 16) && (row_stride_elems * 2) % 16 == 0, TCL_ERR_BAD_ALIGN, "TMA 3D: 16-byte alignment");
+  TCL_REQUIRE(box_rows >= 1 && box_rows <= 256 && box_chunks >= 1 && box_chunks <= 256 && n_chunks >= 1, TCL_ERR_BAD_ARG,
+              "TMA 3D: box out of range");
+  cuuint64_t gdim[3] = {64, rows, n_chunks};
+  cuuint64_t gstride[2] = {row_stride_elems * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_chunks};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TCL_REQUIRE(r == CUDA_SUCCESS, TCL_ERR_DRIVER, "cuTensorMapEncodeTiled (3D) failed with CUresult %d", (int)r);
+  return TCL_OK;
+}
+
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                      uint32_t box_cols) {
   PFN_tmapEncodeTiled fn = get_encode_fn();

@@ -45,6 +45,11 @@ inline int ensure_dyn_smem(F* kernel, int bytes) {
 // are zero-filled (ragged edge tiles rely on this).
 int make_tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                        uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+// A row-major [rows, n_chunks * 64] 16-bit matrix viewed as (64, rows, n_chunks): box {64, box_rows, box_chunks} lands
+// as box_chunks consecutive 128-byte-swizzled {64, box_rows} tiles (tma_load_3d).  Out-of-range rows / chunks are
+// zero-filled.
+int make_tmap_3d_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t n_chunks, uint64_t row_stride_elems,
+                       uint32_t box_rows, uint32_t box_chunks);
 // The same for a dense fp32 [rows, cols] tensor (TMA stores of accumulator tiles): 32-element inner box.
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                      uint32_t box_cols);
@@ -78,6 +83,30 @@ struct NormBwdParams {
   int unit_tiles[3];
   int n_clusters;
 };
+// normalise backward of the sharded shared-G form (ntxent_bwd_g.cu): a tensor's gradient is the sum of its row-side
+// partials (local slots, one per tile range that touched the row's unit) and its column-side partials (receive
+// buffer: [source rank][slot][b_loc][dim], written by every rank's GEMM kernel over NVLink), each source scaled by
+// that source's scale.  Piece counts follow from the shared tile table (pc_range_of), identical on every rank.
+struct NormShJob {
+  const void* x;
+  const float* inv_norm;
+  void* dx;
+  const float* row_part;  // [kBwdMaxSplit][b_loc][dim] or unused (row_job < 0)
+  const float* col_part;  // [world][n_slots_col][b_loc][dim] or unused (col_job < 0)
+  int row_job, col_job;   // indices into the tile table
+};
+struct NormShParams {
+  NormShJob job[3];
+  int64_t job_tile_base[6];
+  int unit_tiles[6];
+  int64_t total_tiles;
+  int64_t row_slot_stride;  // elements between row-side slots
+  const float* scales;      // [world] scale of every source rank (receive-buffer header)
+  int n_ranges, n_dsplit, world, rank, n_slots_col;
+};
+int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim, int64_t x_stride,
+                              float eps, cudaStream_t st);
+
 // ntxent_fwd.cu: partial buffers of the forward tile kernel, for the finalise kernel that reduces them itself
 struct FwdPartials {
   const float* row_part;  // [pairs][n_row_slots][n_rows]

@@ -433,6 +433,108 @@ int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t 
   return TCL_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Normalise backward of the sharded shared-G form: g = sum over sources of scale[src] * partial (host_common.h:
+// NormShParams), then the same projection as above.  Fixed summation order: row-side slots, then source ranks
+// 0..W-1 with their slots.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_constant__ NormShParams pr, int64_t rows,
+                                                                 int dim, int64_t x_stride, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (row >= rows) return;
+  const NormShJob& jb = pr.job[blockIdx.y];
+  const T* x = static_cast<const T*>(jb.x) + row * x_stride;
+  T* dx = static_cast<T*>(jb.dx) + row * dim;
+  const float inv = jb.inv_norm[row];
+  const bool clamped = inv >= 1.f / eps;
+  // pieces of this row's units (per 256-column half when the accumulators were split)
+  int np_row[2] = {0, 0}, np_col[2] = {0, 0};
+  for (int dh = 0; dh < pr.n_dsplit; ++dh) {
+    if (jb.row_job >= 0) {
+      const int T_ = pr.unit_tiles[jb.row_job];
+      const int64_t u0 = pr.job_tile_base[jb.row_job] + ((row >> 7) * pr.n_dsplit + dh) * T_;
+      np_row[dh] = pc_range_of(pr.total_tiles, u0 + T_ - 1, pr.n_ranges) - pc_range_of(pr.total_tiles, u0, pr.n_ranges) + 1;
+    }
+    if (jb.col_job >= 0) {
+      const int T_ = pr.unit_tiles[jb.col_job];
+      const int64_t grow = static_cast<int64_t>(pr.rank) * rows + row;
+      const int64_t u0 = pr.job_tile_base[jb.col_job] + ((grow >> 7) * pr.n_dsplit + dh) * T_;
+      np_col[dh] = pc_range_of(pr.total_tiles, u0 + T_ - 1, pr.n_ranges) - pc_range_of(pr.total_tiles, u0, pr.n_ranges) + 1;
+    }
+  }
+  float sc[TCL_MAX_PEERS];
+#pragma unroll
+  for (int r = 0; r < TCL_MAX_PEERS; ++r) sc[r] = r < pr.world ? pr.scales[r] : 0.f;
+  const float sc_own = pr.scales[pr.rank];
+  constexpr int kMaxIter = 4;
+  float g[kMaxIter][4], z[kMaxIter][4];
+  float dot = 0.f;
+  const int64_t col_slot_stride = rows * static_cast<int64_t>(dim);
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < dim) {
+      const int dh = (pr.n_dsplit == 2 && c >= 256) ? 1 : 0;
+      float xv[4];
+      load4<T>(x + c, xv);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int64_t off = row * dim + c;
+      for (int k = 0; k < np_row[dh]; ++k) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(jb.row_part + k * pr.row_slot_stride + off));
+        acc[0] += sc_own * v.x; acc[1] += sc_own * v.y; acc[2] += sc_own * v.z; acc[3] += sc_own * v.w;
+      }
+      for (int k = 0; k < np_col[dh]; ++k) {
+        float4 v[TCL_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < TCL_MAX_PEERS; ++r)
+          v[r] = r < pr.world
+                     ? __ldcs(reinterpret_cast<const float4*>(jb.col_part + (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < TCL_MAX_PEERS; ++r) {
+          if (r < pr.world) { acc[0] += sc[r] * v[r].x; acc[1] += sc[r] * v[r].y; acc[2] += sc[r] * v[r].z; acc[3] += sc[r] * v[r].w; }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[it][e] = acc[e];
+        z[it][e] = xv[e] * inv;
+        dot += g[it][e] * z[it][e];
+      }
+    }
+  }
+  dot = warp_sum(dot);
+  if (clamped) dot = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < dim) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (g[it][e] - dot * z[it][e]) * inv;
+      store4<T>(dx + c, o);
+    }
+  }
+}
+
+int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim, int64_t x_stride,
+                              float eps, cudaStream_t st) {
+  TCL_REQUIRE(dim <= 512 && dim % 4 == 0, TCL_ERR_BAD_SHAPE, "normalise backward: dim %d > 512", dim);
+  dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_jobs);
+  ProfScope prof(TCL_K_L2NORM_BWD, st);
+  switch (x_dtype) {
+    case TCL_DT_F32: l2norm_bwd_sharded_kernel<float><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
+    case TCL_DT_F64: l2norm_bwd_sharded_kernel<double><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
+    case TCL_DT_F16: l2norm_bwd_sharded_kernel<__half><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
+    case TCL_DT_BF16: l2norm_bwd_sharded_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
+    default: return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
+  }
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
 }  // namespace tcl
 
 using namespace tcl;

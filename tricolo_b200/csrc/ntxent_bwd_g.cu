@@ -14,7 +14,12 @@
 //                                 transposed read of the same row-major G) when it is the column side - B the other
 //                                 operand MN-major straight from the row-major tensor; persistent tile ranges and the
 //                                 TMA-store drain of the producer/consumer kernel.
-// A sharded run cannot use this form (a rank's two directions need different blocks of G): it keeps ntxent_bwd_pc.cu.
+// Sharded over ranks (tricolo_b200/distributed.py): a rank owns the row block G[b_loc x B] of every pair.
+// Its row-side gradients dRow = G Zcol are complete locally; the column-side products dCol = G^T Zrow_local are partial
+// sums for ALL B rows of the column tensor, and kernel B's drain TMA-stores each 128-row piece straight into the owner
+// rank's receive buffer over NVLink peer memory (slot = source rank): the gradient reduce-scatter is the GEMM kernel's
+// own store traffic, 6 b B D executed per pair instead of the 8 of ntxent_bwd_pc.cu.  The owner's normalise backward
+// adds the W x pieces partials in a fixed order (bit-reproducible, no atomics).
 #include <stdlib.h>
 
 #include "ntxent_bwd.h"
@@ -45,9 +50,12 @@ struct GPairDev {
   const float* grad_scale;
 };
 struct GAParams {
-  GPairDev pair[TCL_MAX_PAIRS];
-  float* scale_out;  // device scalar: max|grad_scale| / (tau B), consumed by the normalise backward
-  int n_pairs, batch, num_kb, n_jtiles, n_iblocks;
+  GPairDev pair[TCL_MAX_PAIRS];  // lse_row is indexed by the LOCAL row (the host passes the rank's slice)
+  // device scalars max|grad_scale| / (tau B), consumed by the normalise backward: one local copy, or (sharded) this
+  // rank's entry of every rank's receive-buffer header
+  float* scale_out[TCL_MAX_PEERS];
+  int n_scale_out;
+  int n_pairs, n_rows, n_cols, row_offset, num_kb, n_jtiles, n_iblocks;
   float c1, alpha, out_scale;
   uint32_t idesc;
 };
@@ -204,13 +212,15 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
       gmax = fmaxf(gmax, fabsf(gs[p]));
     }
     const float inv_gmax = gmax > 0.f ? kGScale / gmax : 0.f;  // G in [-kGScale, kGScale]: see ntxent_bwd.h
-    if (blockIdx.x == 0 && ew == 0 && lane == 0) *P.scale_out = gmax * P.out_scale * (1.f / kGScale);
+    if (blockIdx.x == 0 && ew == 0 && lane < P.n_scale_out) *P.scale_out[lane] = gmax * P.out_scale * (1.f / kGScale);
 
     while (walk.next(unit, ta, tb)) {
       const int pi = unit / P.n_iblocks;
       const GPairDev& G = P.pair[pi];
       const int i0 = (unit % P.n_iblocks) * BW_BM;
-      const int grow = i0 + r;
+      const int lrow = i0 + r;                  // local row (row of G)
+      const int grow = P.row_offset + lrow;     // its index in the global batch (column of the positive)
+      const int i0g = P.row_offset + i0;
       if (piece > 0) asm volatile("bar.sync 7, 512;" ::: "memory");  // the previous piece's logit MMAs are complete
       {
         const int c0 = (gi * 2 + ch) * 2;
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
         it_ring += static_cast<uint32_t>(x_slots + (tb - ta) * x_slots);
       }
       const float rr = gs[pi] * inv_gmax;
-      const float lse_i = grow < P.batch ? G.lse_row[grow] : 0.f;
+      const float lse_i = lrow < P.n_rows ? G.lse_row[lrow] : 0.f;
       const float ws = rr * P.alpha;
       const float wo_i = rr * (1.f - P.alpha) * ex2_approx(lse_i - P.c1);
 
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
       auto load_lse = [&](int jtile, bool valid) -> float {
         if (gt >= 128 || !valid) return 1e30f;
         const int j = jtile * BW_BN + gt;
-        return j < P.batch ? G.lse_col[j] : 1e30f;
+        return j < P.n_cols ? G.lse_col[j] : 1e30f;
       };
       float lse_col = load_lse(t, t < tb);
       for (; t < tb; t += 2) {
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
         lse_col = load_lse(t + 2, t + 2 < tb);
         asm volatile("bar.sync %0, 256;" ::"r"(bar_grp) : "memory");
         const int dcol = grow - j0 - ch * 64;
-        const bool has_diag = (i0 < j0 + BW_BN) && (i0 + BW_BM > j0);
+        const bool has_diag = (i0g < j0 + BW_BN) && (i0g + BW_BM > j0);
 
         mbar_wait(s_full(gi), s_par);
         s_par ^= 1;
@@ -337,12 +347,22 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
 // =================================================================================================================
 // kernel B: gradient GEMMs over the stored G
 // =================================================================================================================
+// A job = one output matrix: the gradient of one tensor from the pairs in which it is the row side (A = G tiles
+// K-major, K runs over the B columns of G, output rows = the rank's local rows, local partial slots) or from the pairs
+// in which it is the column side (A = the transposed read of G, K runs over the rank's G rows, output rows = all B
+// rows of the tensor; sharded: stored into the owner rank's receive buffer).  On one GPU both kinds of a tensor share
+// one accumulator (one job with a row-side and a column-side segment).
+// A unit = (job, 128-row block[, 256-column half of dim]) = `unit_tiles` consecutive tiles of one accumulator.  With
+// n_dsplit = 2 the accumulator is one half of TMEM and consecutive pieces alternate halves, so the read-out of a piece
+// overlaps the MMAs of the next (short units: sharded runs); with n_dsplit = 1 it is all of TMEM (dim columns).
 static constexpr int GB_GSLOTS = 2;
 static constexpr int GB_CSTAGES = 4;
 static constexpr int GB_SLOT = 32768;
 static constexpr int GB_DRAIN_WARPS = 8;
 static constexpr int GB_DRAIN_BYTES = 4096;
 static constexpr int GB_THREADS = 64 + GB_DRAIN_WARPS * 32;
+static constexpr int GB_MAX_JOBS = 2 * TCL_MAX_TENSORS;
+static constexpr int GB_MAX_DST = TCL_MAX_TENSORS + TCL_MAX_TENSORS * TCL_MAX_PEERS;
 struct GBSmem {
   static constexpr uint32_t g_off = 0;
   static constexpr uint32_t ring_off = GB_GSLOTS * GB_SLOT;
@@ -353,48 +373,71 @@ struct GBSmem {
 static_assert(GBSmem::total <= 232448, "shared-G backward, kernel B: shared memory budget");
 
 struct GBSegDev {
-  CUtensorMap tm_g;      // row side: G [B, ld_g] box {64 k, 128 m};  column side: box {64 m, 64 k} (transposed read)
-  CUtensorMap tm_other;  // other operand [B, dim], box {64 dims, 64 rows} (MN-major B)
+  // G [n_rows, ld_g] as (64, n_rows, ld_g / 64), box {64, 128, 2}.  Row side: two K-blocks {64 k, 128 m} (K-major A);
+  // column side (transposed read): two 64-wide m groups of 128 k rows each (MN-major A), one instruction either way
+  CUtensorMap tm_g;
+  CUtensorMap tm_other;  // other operand [k rows, dim] as (64, rows, dim / 64), box {64, 64, 4}: MN-major B, 256 columns
   int col_side;
 };
 struct GBJobDev {
   GBSegDev seg[2];
-  CUtensorMap tm_gpart;  // [kBwdMaxSplit * n_self_pad, dim] f32, box {32, 32}
   int n_seg;
+  int k_tiles;       // 128-wide K tiles per segment
+  int dst_first;     // first tensor map of this job in GBParams::tm_dst
+  int owner_rows;    // > 0: output rows are owned in blocks of owner_rows by successive ranks (tm_dst[dst_first + owner])
+  int slot_rows;     // rows of one partial slot in the destination
+  int src_row_base;  // first destination row of this rank's slots (remote: rank * n_slots * slot_rows)
 };
 struct GBParams {
-  GBJobDev job[TCL_MAX_TENSORS];
-  int64_t job_tile_base[TCL_MAX_TENSORS + 1];
-  int unit_tiles[TCL_MAX_TENSORS];
-  int n_jtiles, n_self_pad, dim;
+  GBJobDev job[GB_MAX_JOBS];
+  CUtensorMap tm_dst[GB_MAX_DST];  // f32 [slots * rows, dim], box {32, 32}
+  int64_t job_tile_base[GB_MAX_JOBS + 1];
+  int unit_tiles[GB_MAX_JOBS];  // n_seg * k_tiles
+  int dim, n_dsplit;
   uint32_t idesc_row, idesc_col;  // M=128, N=256, B MN-major; A K-major / MN-major
 };
 
 struct GBPiece {
-  int job, ib, ta, tb, slot;
+  int job, ib, dh, ta, tb, slot;
 };
+
+// wait-time accounting of the first and the last CTA (`make trace`): [0..31] CTA 0, [32..63] the last CTA
+__device__ unsigned long long g_gb_trace[64];
+#ifdef TCL_PAIR_TRACE
+#define GT_DECL unsigned long long gt_t0 = 0; const bool gt_on = (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (threadIdx.x & 31) == 0; const int gt_base = blockIdx.x == 0 ? 0 : 32; (void)gt_t0; (void)gt_base;
+#define GT_BEGIN() do { if (gt_on) gt_t0 = clock64(); } while (0)
+#define GT_END(slot) do { if (gt_on) { const unsigned long long gt_t1 = clock64(); atomicAdd(&g_gb_trace[gt_base + (slot)], gt_t1 - gt_t0); gt_t0 = gt_t1; } } while (0)
+#define GT_ADD(slot, v) do { if (gt_on) atomicAdd(&g_gb_trace[gt_base + (slot)], (unsigned long long)(v)); } while (0)
+#else
+#define GT_DECL
+#define GT_BEGIN() do {} while (0)
+#define GT_END(slot) do {} while (0)
+#define GT_ADD(slot, v) do {} while (0)
+#endif
 struct GBWalk {
   int64_t cursor, end;
   int c, n;
   __device__ explicit GBWalk(const GBParams& P) {
     n = static_cast<int>(gridDim.x);
     c = static_cast<int>(blockIdx.x);
-    const int64_t total = P.job_tile_base[TCL_MAX_TENSORS];
+    const int64_t total = P.job_tile_base[GB_MAX_JOBS];
     cursor = pc_range_lo(total, c, n);
     end = pc_range_lo(total, c + 1, n);
   }
   __device__ bool next(const GBParams& P, GBPiece& pc) {
     if (cursor >= end) return false;
     int j = 0;
-    while (j + 1 < TCL_MAX_TENSORS && cursor >= P.job_tile_base[j + 1]) ++j;
+    while (j + 1 < GB_MAX_JOBS && cursor >= P.job_tile_base[j + 1]) ++j;
     const int T = P.unit_tiles[j];
     const int64_t local = cursor - P.job_tile_base[j];
+    const int u = static_cast<int>(local / T);
     pc.job = j;
-    pc.ib = static_cast<int>(local / T);
+    pc.ib = P.n_dsplit == 2 ? u >> 1 : u;
+    pc.dh = P.n_dsplit == 2 ? u & 1 : 0;
     pc.ta = static_cast<int>(local % T);
     const int64_t left = end - cursor;
     pc.tb = left < T - pc.ta ? pc.ta + static_cast<int>(left) : T;
-    pc.slot = c - pc_range_of(P.job_tile_base[TCL_MAX_TENSORS], cursor - pc.ta, n);
+    pc.slot = c - pc_range_of(P.job_tile_base[GB_MAX_JOBS], cursor - pc.ta, n);
     cursor += pc.tb - pc.ta;
     return true;
   }
@@ -410,20 +453,21 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
   auto g_empty = [&](int s) { return bars + 8u * (GB_GSLOTS + s); };
   auto c_full = [&](int s) { return bars + 8u * (2 * GB_GSLOTS + s); };
   auto c_empty = [&](int s) { return bars + 8u * (2 * GB_GSLOTS + GB_CSTAGES + s); };
-  const uint32_t acc_full_bar = bars + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES);
-  const uint32_t acc_empty_bar = acc_full_bar + 8u;
-  const uint32_t tmem_slot = acc_full_bar + 16u;
+  auto acc_full = [&](int b) { return bars + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      base_ptr + GBSmem::bar_off + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES) + 16u);
+      base_ptr + GBSmem::bar_off + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES + 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunk = (P.dim + 255) / 256;
+  const bool split = P.n_dsplit == 2;
+  const int n_chunk = split ? 1 : (P.dim + 255) / 256;  // 256-column MMAs per K step of one unit
+  const int n_buf = split ? 2 : 1;
   const uint32_t g_smem = base + GBSmem::g_off;
   const uint32_t ring = base + GBSmem::ring_off;
 
   if (warp == 0 && elect_one()) {
-    for (int j = 0; j < TCL_MAX_TENSORS; ++j) {
+    for (int j = 0; j < GB_MAX_JOBS; ++j) {
       if (P.unit_tiles[j] == 0) continue;
-      tma_prefetch_desc(&P.job[j].tm_gpart);
       for (int s = 0; s < P.job[j].n_seg; ++s) {
         tma_prefetch_desc(&P.job[j].seg[s].tm_g);
         tma_prefetch_desc(&P.job[j].seg[s].tm_other);
@@ -437,8 +481,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
       mbar_init(c_full(s), 1);
       mbar_init(c_empty(s), 1);
     }
-    mbar_init(acc_full_bar, 1);
-    mbar_init(acc_empty_bar, GB_DRAIN_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), GB_DRAIN_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -456,68 +502,91 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
     // ---------------------------------------------------------------- TMA warp: G tiles and operand tiles
     if (elect_one()) {
       uint32_t it = 0, tg = 0;
+      GT_DECL
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long gt_w0 = clock64();
+#endif
       while (walk.next(P, pc)) {
         const GBJobDev& J = P.job[pc.job];
         const int i0 = pc.ib * BW_BM;
         for (int t = pc.ta; t < pc.tb; ++t, ++tg) {
-          const GBSegDev& sg = J.seg[t / P.n_jtiles];
-          const int k0 = (t % P.n_jtiles) * BW_BN;  // first row of the other operand = first K index
+          const GBSegDev& sg = J.seg[t / J.k_tiles];
+          const int k0 = (t % J.k_tiles) * BW_BN;  // first row of the other operand = first K index
           const int gsl = tg % GB_GSLOTS;
+          GT_BEGIN();
           mbar_wait(g_empty(gsl), ((tg / GB_GSLOTS) & 1) ^ 1);
+          GT_END(0);
           mbar_arrive_expect_tx(g_full(gsl), GB_SLOT);
-          if (!sg.col_side) {  // A[m = self row, k = other row] = G[self row][other row]: K-major, two K-blocks
-            for (int h = 0; h < 2; ++h)
-              tma_load_2d(g_smem + gsl * GB_SLOT + h * BW_KB_BYTES, &sg.tm_g, g_full(gsl), k0 + h * BW_BK, i0);
-          } else {  // A[m, k] = G[other row k][self row m]: MN-major, per K half two groups of 64 self rows
-            for (int kh = 0; kh < 2; ++kh)
-              for (int mg = 0; mg < 2; ++mg)
-                tma_load_2d(g_smem + gsl * GB_SLOT + kh * BW_KB_BYTES + mg * 8192, &sg.tm_g, g_full(gsl), i0 + mg * 64,
-                            k0 + kh * BW_BK);
-          }
+          // row side: A[m = self row, k = other row] = G[self row][other row], K-major: [k block][128 m][64 k];
+          // column side: A[m, k] = G[other row k][self row m], MN-major: [m group][128 k][64 m]
+          if (!sg.col_side) tma_load_3d(g_smem + gsl * GB_SLOT, &sg.tm_g, g_full(gsl), 0, i0, k0 >> 6);
+          else tma_load_3d(g_smem + gsl * GB_SLOT, &sg.tm_g, g_full(gsl), 0, k0, i0 >> 6);
           for (int kb2 = 0; kb2 < 2; ++kb2)
             for (int c = 0; c < n_chunk; ++c, ++it) {
               const int s = it % GB_CSTAGES;
+              const int col0 = (split ? pc.dh : c) * 256;
+              GT_BEGIN();
               mbar_wait(c_empty(s), ((it / GB_CSTAGES) & 1) ^ 1);
+              GT_END(1);
               mbar_arrive_expect_tx(c_full(s), GB_SLOT);
-              for (int a = 0; a < 4; ++a)
-                tma_load_2d(ring + s * GB_SLOT + a * 8192, &sg.tm_other, c_full(s), c * 256 + a * 64, k0 + kb2 * BW_BK);
+              tma_load_3d(ring + s * GB_SLOT, &sg.tm_other, c_full(s), 0, k0 + kb2 * BW_BK, col0 >> 6);
             }
         }
       }
+#ifdef TCL_PAIR_TRACE
+      GT_ADD(2, clock64() - gt_w0);
+#endif
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- gradient MMAs
     if (elect_one()) {
       uint32_t it = 0, tg = 0, piece = 0;
+      GT_DECL
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long gt_w0 = clock64();
+#endif
       while (walk.next(P, pc)) {
         const GBJobDev& J = P.job[pc.job];
-        mbar_wait(acc_empty_bar, (piece & 1) ^ 1);
+        const int buf = static_cast<int>(piece % n_buf);
+        GT_BEGIN();
+        mbar_wait(acc_empty(buf), ((piece / n_buf) & 1) ^ 1);
+        GT_END(3);
         tc_fence_after();
         for (int t = pc.ta; t < pc.tb; ++t, ++tg) {
-          const bool col_side = J.seg[t / P.n_jtiles].col_side != 0;
+          const bool col_side = J.seg[t / J.k_tiles].col_side != 0;
           const uint32_t idesc = col_side ? P.idesc_col : P.idesc_row;
           const int gsl = tg % GB_GSLOTS;
+          GT_BEGIN();
           mbar_wait(g_full(gsl), (tg / GB_GSLOTS) & 1);
+          GT_END(4);
           tc_fence_after();
           for (int kb2 = 0; kb2 < 2; ++kb2)
             for (int c = 0; c < n_chunk; ++c, ++it) {
               const int s = it % GB_CSTAGES;
+              GT_BEGIN();
               mbar_wait(c_full(s), (it / GB_CSTAGES) & 1);
+              GT_END(5);
               tc_fence_after();
-              const uint32_t a_addr = g_smem + gsl * GB_SLOT + kb2 * BW_KB_BYTES;
-              const uint64_t ad = col_side ? umma_desc_mn_sw128(a_addr, 8192) : umma_desc_k_sw128(a_addr);
+              // K half kb2: the second K-block (row side) / the second 64 k rows of both m groups (column side)
+              const uint32_t a_addr = g_smem + gsl * GB_SLOT + kb2 * (col_side ? 8192 : BW_KB_BYTES);
+              const uint64_t ad = col_side ? umma_desc_mn_sw128(a_addr, BW_KB_BYTES) : umma_desc_k_sw128(a_addr);
               const uint32_t a_step = col_side ? 128u : 2u;  // one UMMA_K: 16 K rows of 128 bytes / 32 bytes along K
               const uint64_t bd = umma_desc_mn_sw128(ring + s * GB_SLOT, 8192);
 #pragma unroll
               for (int kk = 0; kk < BW_BK / 16; ++kk)
-                tc_mma_f16(tmem + c * 256, ad + a_step * kk, bd + 128 * kk, idesc, ((t - pc.ta) | kb2 | kk) != 0);
+                tc_mma_f16(tmem + (buf + c) * 256, ad + a_step * kk, bd + 128 * kk, idesc, ((t - pc.ta) | kb2 | kk) != 0);
               tc_commit(c_empty(s));
             }
           tc_commit(g_empty(gsl));
         }
-        tc_commit(acc_full_bar);
+        tc_commit(acc_full(buf));
         ++piece;
       }
+#ifdef TCL_PAIR_TRACE
+      GT_ADD(6, clock64() - gt_w0);
+      GT_ADD(10, tg);
+      GT_ADD(11, piece);
+#endif
     }
   } else {
     // ---------------------------------------------------------------- accumulator read-out (8 warps), as ntxent_bwd_pc.cu
@@ -525,17 +594,35 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
     const int half = (warp - 2) >> 2;
     const uint32_t stg = base + GBSmem::drain_off + static_cast<uint32_t>(warp - 2) * GB_DRAIN_BYTES;
     uint8_t* stg_ptr = base_ptr + GBSmem::drain_off + (warp - 2) * GB_DRAIN_BYTES;
+    const int ucols = split ? 256 : P.dim;  // columns of one unit
+    const int hw = split ? 128 : 256;       // columns read out by one group of four warps
     uint32_t piece = 0;
+#ifdef TCL_PAIR_TRACE
+    unsigned long long gt_t0 = 0;
+    const bool gt_on = (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && threadIdx.x == 64;
+    const int gt_base = blockIdx.x == 0 ? 0 : 32;
+    const unsigned long long gt_w0 = clock64();
+#endif
     while (walk.next(P, pc)) {
-      mbar_wait(acc_full_bar, piece & 1);
+      const GBJobDev& J = P.job[pc.job];
+      const int buf = static_cast<int>(piece % n_buf);
+      GT_BEGIN();
+      mbar_wait(acc_full(buf), (piece / n_buf) & 1);
+      GT_END(7);
       tc_fence_after();
-      const int row0 = pc.slot * P.n_self_pad + pc.ib * BW_BM + q * 32;
+      int owner = 0, rin = pc.ib * BW_BM;
+      if (J.owner_rows > 0) {
+        owner = rin / J.owner_rows;
+        rin -= owner * J.owner_rows;
+      }
+      const CUtensorMap* tm = &P.tm_dst[J.dst_first + owner];
+      const int row0 = J.src_row_base + pc.slot * J.slot_rows + rin + q * 32;
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col = half * 256 + cc * 32;
-        if (col >= P.dim) break;
+      for (int cc = 0; cc < hw / 32; ++cc) {
+        const int ucol = half * hw + cc * 32;
+        if (ucol >= ucols) break;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, col), v);
+        tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, buf * 256 + ucol), v);
         tc_wait_ld();
         if (lane == 0) bulk_wait_read_all();
         __syncwarp();
@@ -547,16 +634,20 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&P.job[pc.job].tm_gpart, stg, col, row0);
+          tma_store_2d(tm, stg, pc.dh * 256 + ucol, row0);
           bulk_commit_group();
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty_bar);
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      GT_END(8);
       ++piece;
     }
     if (lane == 0) bulk_wait_all();
+#ifdef TCL_PAIR_TRACE
+    GT_ADD(9, clock64() - gt_w0);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -566,6 +657,19 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
 // -----------------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------------
+}  // namespace tcl
+extern "C" int tcl_debug_gb_trace(unsigned long long* out64, int reset) {
+  using namespace tcl;
+  TCL_CHECK_CUDA(cudaDeviceSynchronize());
+  if (out64) TCL_CHECK_CUDA(cudaMemcpyFromSymbol(out64, g_gb_trace, sizeof(unsigned long long) * 64));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    TCL_CHECK_CUDA(cudaMemcpyToSymbol(g_gb_trace, z, sizeof(z)));
+  }
+  return TCL_OK;
+}
+namespace tcl {
+
 size_t bwd_sharedg_workspace_bytes(int n_pairs, int64_t batch) {
   const int64_t ld_g = (batch + 63) / 64 * 64;
   return static_cast<size_t>(n_pairs) * batch * ld_g * 2 + 1024;
@@ -590,15 +694,31 @@ static int launch_g_kernel(const GAParams& A, int n_ctas, cudaStream_t st) {
   return TCL_OK;
 }
 
+static int launch_ggemm(const GBParams& B, int n_ctas, cudaStream_t st) {
+  const int smem = static_cast<int>(GBSmem::total);
+  if (int e = ensure_dyn_smem(ntxent_ggemm_kernel, smem)) return e;
+  prof_begin(TCL_K_NTXENT_BWD, st);
+  ntxent_ggemm_kernel<<<static_cast<unsigned>(n_ctas), GB_THREADS, smem, st>>>(B);
+  prof_end(TCL_K_NTXENT_BWD, st);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+static int device_sm_count(int* n_sm) {
+  int dev = 0;
+  TCL_CHECK_CUDA(cudaGetDevice(&dev));
+  TCL_CHECK_CUDA(cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, dev));
+  return TCL_OK;
+}
+
 int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   const int64_t batch = a.batch, dim = a.dim;
   const int64_t ld_g = (batch + 63) / 64 * 64;
   const int n_iblocks = static_cast<int>((batch + BW_BM - 1) / BW_BM);
   const int n_jtiles = static_cast<int>((batch + BW_BN - 1) / BW_BN);
   const int n_self_pad = n_iblocks * BW_BM;
-  int n_sm = 0, dev = 0;
-  TCL_CHECK_CUDA(cudaGetDevice(&dev));
-  TCL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  int n_sm = 0;
+  if (int e = device_sm_count(&n_sm)) return e;
   char* ws = static_cast<char*>(a.workspace);
   float* scale = reinterpret_cast<float*>(ws);          // 64 floats reserved
   float* gbase = reinterpret_cast<float*>(ws) + 64;     // gradient partial slots, as tcl_ntxent_bwd
@@ -616,14 +736,17 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
     GPairDev& G = A.pair[k];
     if (int e = make_tmap_2d_16bit(&G.tm_row, a.z[a.pair_row[p]], batch, dim, dim, BW_BM, BW_BK)) return e;
     if (int e = make_tmap_2d_16bit(&G.tm_col, a.z[a.pair_col[p]], batch, dim, dim, BW_BN, BW_BK)) return e;
-    if (int e = make_tmap_2d_16bit(&G.tm_g, g_mat + static_cast<size_t>(k) * batch * ld_g, batch, batch, ld_g, BW_BM, 64)) return e;
+    // all ld_g columns are stored (finite values in the padding), so that kernel B may read whole 64-column chunks
+    if (int e = make_tmap_2d_16bit(&G.tm_g, g_mat + static_cast<size_t>(k) * batch * ld_g, batch, ld_g, ld_g, BW_BM, 64)) return e;
     G.lse_row = a.lse_row + static_cast<size_t>(p) * batch;
     G.lse_col = a.lse_col + static_cast<size_t>(p) * batch;
     G.grad_scale = a.grad_losses + p;
   }
   if (A.n_pairs == 0) return TCL_OK;
-  A.scale_out = scale;
-  A.batch = static_cast<int>(batch);
+  A.scale_out[0] = scale;
+  A.n_scale_out = 1;
+  A.n_rows = A.n_cols = static_cast<int>(batch);
+  A.row_offset = 0;
   A.num_kb = static_cast<int>(dim / 64);
   A.n_jtiles = n_jtiles;
   A.n_iblocks = n_iblocks;
@@ -654,12 +777,17 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
       S.col_side = a.pair_col[p] == m;
       const int o = S.col_side ? a.pair_row[p] : a.pair_col[p];
       uint16_t* gp = g_mat + static_cast<size_t>(pair_slot[p]) * batch * ld_g;
-      if (int e = make_tmap_2d_16bit(&S.tm_g, gp, batch, batch, ld_g, S.col_side ? 64 : BW_BM, 64)) return e;
-      if (int e = make_tmap_2d_16bit(&S.tm_other, a.z[o], batch, dim, dim, 64, 64)) return e;
+      if (int e = make_tmap_3d_16bit(&S.tm_g, gp, batch, ld_g / 64, ld_g, BW_BM, 2)) return e;
+      if (int e = make_tmap_3d_16bit(&S.tm_other, a.z[o], batch, dim / 64, dim, 64, 4)) return e;
     }
     if (J.n_seg == 0) continue;
     float* gpart = gbase + static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self_pad * dim;
-    if (int e = make_tmap_2d_f32(&J.tm_gpart, gpart, static_cast<uint64_t>(kBwdMaxSplit) * n_self_pad, dim, 32, 32)) return e;
+    if (int e = make_tmap_2d_f32(&B.tm_dst[n_jobs], gpart, static_cast<uint64_t>(kBwdMaxSplit) * n_self_pad, dim, 32, 32)) return e;
+    J.k_tiles = n_jtiles;
+    J.dst_first = n_jobs;
+    J.owner_rows = 0;
+    J.slot_rows = n_self_pad;
+    J.src_row_base = 0;
     B.unit_tiles[n_jobs] = J.n_seg * n_jtiles;
     B.job_tile_base[n_jobs + 1] = B.job_tile_base[n_jobs] + static_cast<int64_t>(n_iblocks) * B.unit_tiles[n_jobs];
     N.job[n_jobs].x = a.x[m];
@@ -669,13 +797,12 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
     N.job[n_jobs].dx = a.dx[m];
     ++n_jobs;
   }
-  for (int j = n_jobs; j < TCL_MAX_TENSORS; ++j) B.job_tile_base[j + 1] = B.job_tile_base[n_jobs];
-  B.n_jtiles = n_jtiles;
-  B.n_self_pad = n_self_pad;
+  for (int j = n_jobs; j < GB_MAX_JOBS; ++j) B.job_tile_base[j + 1] = B.job_tile_base[n_jobs];
   B.dim = static_cast<int>(dim);
+  B.n_dsplit = 1;  // one GPU: long units, G streams from HBM - reading it once per 256-column half would double that
   B.idesc_row = umma_idesc_f16(BW_BM, 256, a.op_format) | (1u << 16);
   B.idesc_col = B.idesc_row | (1u << 15);
-  const int64_t total_b = B.job_tile_base[TCL_MAX_TENSORS];
+  const int64_t total_b = B.job_tile_base[GB_MAX_JOBS];
   int t_max = 1;
   for (int j = 0; j < n_jobs; ++j) t_max = B.unit_tiles[j] > t_max ? B.unit_tiles[j] : t_max;
   int64_t ctas_b = n_sm;
@@ -683,14 +810,7 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   const int64_t cap = (kBwdMaxSplit - 1) * total_b / t_max;
   if (ctas_b > cap) ctas_b = cap;
   if (ctas_b < 1) ctas_b = 1;
-  {
-    const int smem = static_cast<int>(GBSmem::total);
-    if (int e = ensure_dyn_smem(ntxent_ggemm_kernel, smem)) return e;
-    prof_begin(TCL_K_NTXENT_BWD, st);
-    ntxent_ggemm_kernel<<<static_cast<unsigned>(ctas_b), GB_THREADS, smem, st>>>(B);
-    prof_end(TCL_K_NTXENT_BWD, st);
-    TCL_CHECK_CUDA(cudaGetLastError());
-  }
+  if (int e = launch_ggemm(B, static_cast<int>(ctas_b), st)) return e;
   N.n_clusters = static_cast<int>(ctas_b);
   N.split_rows = n_self_pad;
   N.total_tiles = total_b;
@@ -701,4 +821,301 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   return launch_l2norm_bwd(N, n_jobs, a.x_dtype, batch, static_cast<int>(dim), a.x_row_stride, kBwdMaxSplit, a.eps, st);
 }
 
+// =================================================================================================================
+// sharded form: rank r owns rows [r b_loc, (r+1) b_loc) of every tensor
+// =================================================================================================================
+// The plan (jobs, tile table, slot counts, buffer layout) is a pure function of the sizes, so every rank - and the
+// size queries, the GEMM launch and the finishing launch of one rank - derive the same one.
+struct ShardPlan {
+  int n_row_jobs, n_col_jobs;
+  int row_tensor[TCL_MAX_TENSORS], col_tensor[TCL_MAX_TENSORS];  // tensor index of each job
+  int n_dsplit, n_ctas, n_slots_col;
+  int n_iblocks, n_jtiles, n_self_pad;
+  int64_t ld_g;
+  int64_t job_tile_base[GB_MAX_JOBS + 1];
+  int unit_tiles[GB_MAX_JOBS];  // row jobs first, then column jobs: the short column-side units (whose stores cross
+                                // NVLink) are NOT first, so that... see make_shard_plan
+  int job_is_col[GB_MAX_JOBS], job_tensor[GB_MAX_JOBS];
+  int n_jobs;
+  size_t ws_scale, ws_part, ws_g, ws_total;  // local workspace offsets / size
+  size_t recv_hdr, recv_job_bytes, recv_total;
+  int pair_slot[TCL_MAX_PAIRS], n_gpairs;
+};
+
+static int max_pieces(int64_t total, int64_t first, int T, int n_units, int n) {
+  int worst = 1;
+  for (int u = 0; u < n_units; ++u) {
+    const int64_t u0 = first + static_cast<int64_t>(u) * T;
+    const int k = pc_range_of(total, u0 + T - 1, n) - pc_range_of(total, u0, n) + 1;
+    worst = k > worst ? k : worst;
+  }
+  return worst;
+}
+
+static int make_shard_plan(ShardPlan* out, int n_tensors, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                           const uint8_t* need_grad, int64_t b_loc, int64_t b_glob, int64_t dim, int world) {
+  ShardPlan& S = *out;
+  memset(&S, 0, sizeof(S));
+  TCL_REQUIRE(n_tensors >= 2 && n_tensors <= TCL_MAX_TENSORS && n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG,
+              "bwd_sharded: %d tensors / %d pairs", n_tensors, n_pairs);
+  TCL_REQUIRE(world >= 1 && world <= TCL_MAX_PEERS, TCL_ERR_BAD_ARG, "bwd_sharded: world %d", world);
+  TCL_REQUIRE(dim > BW_DH && dim % 64 == 0 && dim <= 512, TCL_ERR_BAD_SHAPE, "bwd_sharded: dim %lld (needs 256 < dim <= 512)", (long long)dim);
+  TCL_REQUIRE(b_loc >= BW_BM && b_loc % BW_BM == 0 && b_glob == b_loc * world && b_glob < (1 << 24), TCL_ERR_BAD_SHAPE,
+              "bwd_sharded: rows per rank (%lld) must be a multiple of 128 and b_glob = world * b_loc", (long long)b_loc);
+  S.n_iblocks = static_cast<int>(b_loc / BW_BM);
+  S.n_jtiles = static_cast<int>(b_glob / BW_BN);
+  S.n_self_pad = static_cast<int>(b_loc);
+  S.ld_g = b_glob;
+  for (int p = 0; p < n_pairs; ++p) {
+    TCL_REQUIRE(pair_row[p] >= 0 && pair_row[p] < n_tensors && pair_col[p] >= 0 && pair_col[p] < n_tensors &&
+                    pair_row[p] != pair_col[p], TCL_ERR_BAD_ARG, "bwd_sharded: pair %d out of range", p);
+    S.pair_slot[p] = (need_grad[pair_row[p]] || need_grad[pair_col[p]]) ? S.n_gpairs++ : -1;
+  }
+  // G of all pairs in L2 (126 MB): halve the accumulator so that read-outs overlap MMAs; otherwise G would stream from
+  // HBM once per half
+  const size_t g_bytes = static_cast<size_t>(S.n_gpairs) * b_loc * S.ld_g * 2;
+  S.n_dsplit = g_bytes <= (64ull << 20) ? 2 : 1;
+  if (const char* e = getenv("TRICOLO_B200_GSPLIT")) S.n_dsplit = atoi(e) == 2 ? 2 : 1;
+  // jobs: column-side first - their drains cross NVLink and should be in flight while the row-side tiles still compute
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int m = 0; m < n_tensors; ++m) {
+      if (!need_grad[m]) continue;
+      int n_seg = 0;
+      for (int p = 0; p < n_pairs; ++p) n_seg += (pass == 0 ? pair_col[p] : pair_row[p]) == m;
+      if (n_seg == 0) continue;
+      TCL_REQUIRE(n_seg <= 2, TCL_ERR_BAD_ARG, "bwd_sharded: tensor %d is on one side of more than two pairs", m);
+      const int j = S.n_jobs++;
+      S.job_is_col[j] = pass == 0;
+      S.job_tensor[j] = m;
+      const int k_tiles = pass == 0 ? S.n_iblocks : S.n_jtiles;
+      const int n_units = (pass == 0 ? S.n_jtiles : S.n_iblocks) * S.n_dsplit;
+      S.unit_tiles[j] = n_seg * k_tiles;
+      S.job_tile_base[j + 1] = S.job_tile_base[j] + static_cast<int64_t>(n_units) * S.unit_tiles[j];
+      if (pass == 0) S.col_tensor[S.n_col_jobs++] = m; else S.row_tensor[S.n_row_jobs++] = m;
+    }
+  }
+  for (int j = S.n_jobs; j < GB_MAX_JOBS; ++j) S.job_tile_base[j + 1] = S.job_tile_base[S.n_jobs];
+  const int64_t total = S.job_tile_base[GB_MAX_JOBS];
+  // tile ranges: one per SM of a B200 (every rank must derive the same number: it fixes the partial slots a unit uses)
+  int64_t n = kNumSMsB200;
+  if (const char* e = getenv("TRICOLO_B200_GCTAS")) { const int v = atoi(e); if (v >= 1 && v < n) n = v; }
+  if (n > total) n = total;
+  int t_max = 1;
+  for (int j = 0; j < S.n_jobs; ++j) t_max = S.unit_tiles[j] > t_max ? S.unit_tiles[j] : t_max;
+  const int64_t cap = (kBwdMaxSplit - 1) * total / t_max;
+  if (n > cap) n = cap;
+  if (n < 1) n = 1;
+  S.n_ctas = static_cast<int>(n);
+  S.n_slots_col = 1;
+  for (int j = 0; j < S.n_jobs; ++j) {
+    if (!S.job_is_col[j]) continue;
+    const int k = max_pieces(total, S.job_tile_base[j], S.unit_tiles[j], S.n_jtiles * S.n_dsplit, S.n_ctas);
+    S.n_slots_col = k > S.n_slots_col ? k : S.n_slots_col;
+  }
+  TCL_REQUIRE(S.n_slots_col <= kBwdMaxSplit, TCL_ERR_BAD_SHAPE, "bwd_sharded: %d pieces per column unit", S.n_slots_col);
+  auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+  S.ws_scale = 0;
+  S.ws_part = 1024;
+  S.ws_g = S.ws_part + up(static_cast<size_t>(S.n_row_jobs) * kBwdMaxSplit * S.n_self_pad * dim * 4);
+  S.ws_total = S.ws_g + up(g_bytes) + 1024;
+  S.recv_hdr = 1024;  // [world] floats: every source rank's scale
+  S.recv_job_bytes = static_cast<size_t>(world) * S.n_slots_col * b_loc * dim * 4;
+  S.recv_total = S.recv_hdr + static_cast<size_t>(S.n_col_jobs) * S.recv_job_bytes;
+  return TCL_OK;
+}
+
 }  // namespace tcl
+
+using namespace tcl;
+
+extern "C" size_t tcl_ntxent_bwd_sharded_workspace_bytes(int n_tensors, int n_pairs, const int32_t* pair_row,
+                                                         const int32_t* pair_col, const uint8_t* need_grad,
+                                                         int64_t b_loc, int64_t b_glob, int64_t dim, int world) {
+  ShardPlan S;
+  if (!pair_row || !pair_col || !need_grad) return 0;
+  if (make_shard_plan(&S, n_tensors, n_pairs, pair_row, pair_col, need_grad, b_loc, b_glob, dim, world)) return 0;
+  return S.ws_total;
+}
+
+extern "C" size_t tcl_ntxent_bwd_sharded_recv_bytes(int n_tensors, int n_pairs, const int32_t* pair_row,
+                                                    const int32_t* pair_col, const uint8_t* need_grad, int64_t b_loc,
+                                                    int64_t b_glob, int64_t dim, int world) {
+  ShardPlan S;
+  if (!pair_row || !pair_col || !need_grad) return 0;
+  if (make_shard_plan(&S, n_tensors, n_pairs, pair_row, pair_col, need_grad, b_loc, b_glob, dim, world)) return 0;
+  return S.recv_total;
+}
+
+extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_all, int64_t b_loc, int64_t b_glob,
+                                           int64_t dim, int64_t z_row_stride, int rank, int world, int n_pairs,
+                                           const int32_t* pair_row, const int32_t* pair_col, int op_format,
+                                           float inv_tau, float alpha, const float* lse_row, const float* lse_col,
+                                           const float* grad_losses, const uint8_t* need_grad, void* workspace,
+                                           size_t workspace_bytes, void* const* recv_ptrs, size_t recv_bytes,
+                                           void* stream) {
+  TCL_REQUIRE(z_all && pair_row && pair_col && lse_row && lse_col && grad_losses && need_grad && workspace && recv_ptrs,
+              TCL_ERR_BAD_ARG, "bwd_sharded_gemm: null pointer");
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  ShardPlan S;
+  if (int e = make_shard_plan(&S, n_tensors, n_pairs, pair_row, pair_col, need_grad, b_loc, b_glob, dim, world)) return e;
+  TCL_REQUIRE(rank >= 0 && rank < world, TCL_ERR_BAD_ARG, "bwd_sharded_gemm: rank %d of %d", rank, world);
+  TCL_REQUIRE(workspace_bytes >= S.ws_total && aligned_to(workspace, 256), TCL_ERR_WORKSPACE, "bwd_sharded_gemm: workspace");
+  TCL_REQUIRE(recv_bytes >= S.recv_total, TCL_ERR_WORKSPACE, "bwd_sharded_gemm: receive buffers too small");
+  const float c1 = inv_tau * 1.4426950408889634f;
+  TCL_REQUIRE(inv_tau > 0.f && 2.f * c1 < 120.f, TCL_ERR_BAD_ARG, "bwd_sharded_gemm: temperature too small (need tau >= 0.025)");
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 8 == 0, TCL_ERR_BAD_ALIGN, "bwd_sharded_gemm: z_row_stride");
+  for (int r = 0; r < world; ++r)
+    TCL_REQUIRE(recv_ptrs[r] && aligned_to(recv_ptrs[r], 256), TCL_ERR_BAD_ALIGN, "bwd_sharded_gemm: receive buffer %d", r);
+  if (int e = require_sm100()) return e;
+  if (S.n_jobs == 0) return TCL_OK;
+  int n_sm = 0;
+  if (int e = device_sm_count(&n_sm)) return e;
+  TCL_REQUIRE(n_sm >= S.n_ctas, TCL_ERR_BAD_ARCH, "bwd_sharded_gemm: %d SMs, the plan assumes %d", n_sm, S.n_ctas);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  uint16_t* g_mat = reinterpret_cast<uint16_t*>(ws + S.ws_g);
+  const size_t g_pair = static_cast<size_t>(b_loc) * S.ld_g;
+  const int64_t row_offset = static_cast<int64_t>(rank) * b_loc;
+  auto z_loc = [&](int m) { return static_cast<const char*>(z_all[m]) + static_cast<size_t>(row_offset) * z_row_stride * 2; };
+
+  // ---- kernel A: the rank's row block of every pair's G
+  GAParams A;
+  memset(&A, 0, sizeof(A));
+  for (int p = 0; p < n_pairs; ++p) {
+    if (S.pair_slot[p] < 0) continue;
+    GPairDev& G = A.pair[A.n_pairs++];
+    if (int e = make_tmap_2d_16bit(&G.tm_row, z_loc(pair_row[p]), b_loc, dim, z_row_stride, BW_BM, BW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&G.tm_col, z_all[pair_col[p]], b_glob, dim, z_row_stride, BW_BN, BW_BK)) return e;
+    if (int e = make_tmap_2d_16bit(&G.tm_g, g_mat + S.pair_slot[p] * g_pair, b_loc, b_glob, S.ld_g, BW_BM, 64)) return e;
+    G.lse_row = lse_row + static_cast<size_t>(p) * b_glob + row_offset;
+    G.lse_col = lse_col + static_cast<size_t>(p) * b_glob;
+    G.grad_scale = grad_losses + p;
+  }
+  A.n_scale_out = 0;
+  // this rank's scale goes to entry `rank` of every rank's receive-buffer header (the owner multiplies each source's
+  // partials by that source's scale); the own buffer is one of them
+  for (int r = 0; r < world; ++r) A.scale_out[A.n_scale_out++] = reinterpret_cast<float*>(recv_ptrs[r]) + rank;
+  A.n_rows = static_cast<int>(b_loc);
+  A.n_cols = static_cast<int>(b_glob);
+  A.row_offset = static_cast<int>(row_offset);
+  A.num_kb = static_cast<int>(dim / 64);
+  A.n_jtiles = S.n_jtiles;
+  A.n_iblocks = S.n_iblocks;
+  A.c1 = c1;
+  A.alpha = alpha;
+  A.out_scale = inv_tau / static_cast<float>(b_glob);
+  A.idesc = umma_idesc_f16(BW_BM, BW_BN, op_format);
+  const int64_t total_a = static_cast<int64_t>(A.n_pairs) * S.n_iblocks * S.n_jtiles;
+  const int ctas_a = static_cast<int>(total_a < n_sm ? total_a : n_sm);
+  prof_begin(TCL_K_NTXENT_G, st);
+  if (int e = (op_format == TCL_OP_F16 ? launch_g_kernel<TCL_OP_F16>(A, ctas_a, st) : launch_g_kernel<TCL_OP_BF16>(A, ctas_a, st)))
+    return e;
+  prof_end(TCL_K_NTXENT_G, st);
+
+  // ---- kernel B
+  GBParams B;
+  memset(&B, 0, sizeof(B));
+  int n_dst = 0, i_row = 0, i_col = 0;
+  for (int j = 0; j < S.n_jobs; ++j) {
+    GBJobDev& J = B.job[j];
+    const int m = S.job_tensor[j];
+    const bool col = S.job_is_col[j] != 0;
+    for (int p = 0; p < n_pairs; ++p) {
+      if ((col ? pair_col[p] : pair_row[p]) != m) continue;
+      GBSegDev& sg = J.seg[J.n_seg++];
+      sg.col_side = col;
+      uint16_t* gp = g_mat + S.pair_slot[p] * g_pair;
+      if (int e = make_tmap_3d_16bit(&sg.tm_g, gp, b_loc, S.ld_g / 64, S.ld_g, BW_BM, 2)) return e;
+      if (col) {  // B operand: the pair's row tensor, this rank's rows (K = local rows)
+        if (int e = make_tmap_3d_16bit(&sg.tm_other, z_loc(pair_row[p]), b_loc, dim / 64, z_row_stride, 64, 4)) return e;
+      } else {    // B operand: the pair's column tensor, all rows (K = global columns of G)
+        if (int e = make_tmap_3d_16bit(&sg.tm_other, z_all[pair_col[p]], b_glob, dim / 64, z_row_stride, 64, 4)) return e;
+      }
+    }
+    J.k_tiles = col ? S.n_iblocks : S.n_jtiles;
+    J.dst_first = n_dst;
+    if (col) {
+      for (int r = 0; r < world; ++r) {
+        char* dst = static_cast<char*>(recv_ptrs[r]) + S.recv_hdr + static_cast<size_t>(i_col) * S.recv_job_bytes;
+        if (int e = make_tmap_2d_f32(&B.tm_dst[n_dst++], dst, static_cast<uint64_t>(world) * S.n_slots_col * b_loc, dim, 32, 32)) return e;
+      }
+      J.owner_rows = static_cast<int>(b_loc);
+      J.slot_rows = static_cast<int>(b_loc);
+      J.src_row_base = rank * S.n_slots_col * static_cast<int>(b_loc);
+      ++i_col;
+    } else {
+      float* gpart = reinterpret_cast<float*>(ws + S.ws_part) + static_cast<size_t>(i_row) * kBwdMaxSplit * S.n_self_pad * dim;
+      if (int e = make_tmap_2d_f32(&B.tm_dst[n_dst++], gpart, static_cast<uint64_t>(kBwdMaxSplit) * S.n_self_pad, dim, 32, 32)) return e;
+      J.owner_rows = 0;
+      J.slot_rows = S.n_self_pad;
+      J.src_row_base = 0;
+      ++i_row;
+    }
+    B.unit_tiles[j] = S.unit_tiles[j];
+  }
+  for (int j = 0; j <= GB_MAX_JOBS; ++j) B.job_tile_base[j] = S.job_tile_base[j];
+  B.dim = static_cast<int>(dim);
+  B.n_dsplit = S.n_dsplit;
+  B.idesc_row = umma_idesc_f16(BW_BM, 256, op_format) | (1u << 16);
+  B.idesc_col = B.idesc_row | (1u << 15);
+  return launch_ggemm(B, S.n_ctas, st);
+}
+
+extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x, int x_dtype, int64_t b_loc,
+                                             int64_t b_glob, int64_t dim, int64_t x_row_stride, int rank, int world,
+                                             int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                                             const float* inv_norm, const uint8_t* need_grad, float eps,
+                                             const void* workspace, const void* recv_own, void* const* dx,
+                                             void* stream) {
+  TCL_REQUIRE(x && pair_row && pair_col && inv_norm && need_grad && workspace && recv_own && dx, TCL_ERR_BAD_ARG,
+              "bwd_sharded_finish: null pointer");
+  ShardPlan S;
+  if (int e = make_shard_plan(&S, n_tensors, n_pairs, pair_row, pair_col, need_grad, b_loc, b_glob, dim, world)) return e;
+  TCL_REQUIRE(rank >= 0 && rank < world, TCL_ERR_BAD_ARG, "bwd_sharded_finish: rank %d of %d", rank, world);
+  if (int e = require_sm100()) return e;
+  NormShParams N;
+  memset(&N, 0, sizeof(N));
+  const char* ws = static_cast<const char*>(workspace);
+  const char* rv = static_cast<const char*>(recv_own);
+  int n_out = 0;
+  for (int m = 0; m < n_tensors; ++m) {
+    if (!need_grad[m]) continue;
+    NormShJob& J = N.job[n_out];
+    J.x = x[m];
+    J.inv_norm = inv_norm + static_cast<size_t>(m) * b_loc;
+    J.dx = dx[m];
+    TCL_REQUIRE(J.dx != nullptr, TCL_ERR_BAD_ARG, "bwd_sharded_finish: dx[%d] is null", m);
+    J.row_job = J.col_job = -1;
+    int i_row = 0, i_col = 0;
+    for (int j = 0; j < S.n_jobs; ++j) {
+      if (S.job_tensor[j] == m && !S.job_is_col[j]) {
+        J.row_job = j;
+        J.row_part = reinterpret_cast<const float*>(ws + S.ws_part) + static_cast<size_t>(i_row) * kBwdMaxSplit * S.n_self_pad * dim;
+      }
+      if (S.job_tensor[j] == m && S.job_is_col[j]) {
+        J.col_job = j;
+        J.col_part = reinterpret_cast<const float*>(rv + S.recv_hdr + static_cast<size_t>(i_col) * S.recv_job_bytes);
+      }
+      i_row += !S.job_is_col[j];
+      i_col += S.job_is_col[j] != 0;
+    }
+    if (J.row_job < 0 && J.col_job < 0) continue;
+    ++n_out;
+  }
+  if (n_out == 0) return TCL_OK;
+  for (int j = 0; j < GB_MAX_JOBS; ++j) {
+    N.job_tile_base[j] = S.job_tile_base[j];
+    N.unit_tiles[j] = S.unit_tiles[j];
+  }
+  N.total_tiles = S.job_tile_base[GB_MAX_JOBS];
+  N.n_ranges = S.n_ctas;
+  N.n_dsplit = S.n_dsplit;
+  N.world = world;
+  N.rank = rank;
+  N.n_slots_col = S.n_slots_col;
+  N.row_slot_stride = static_cast<int64_t>(S.n_self_pad) * dim;
+  N.scales = reinterpret_cast<const float*>(rv);
+  return launch_l2norm_bwd_sharded(N, n_out, x_dtype, b_loc, static_cast<int>(dim), x_row_stride, eps,
+                                   static_cast<cudaStream_t>(stream));
+}

@@ -9,9 +9,14 @@ of each logit matrix:
                  NCCL all-gather                                 (W-1)/W * 3*B*D*2 bytes in
     reduce       sum-exp statistics [3, P, B] fp32 (column partials + every rank's row sums and positives; fixed
                  shift -> plain sums): one-shot peer read + add in rank order, or one NCCL all-reduce
-The backward is the same directional kernel as on one GPU, run for the local rows of each
-modality against ALL rows of the partner modality, so every local gradient is complete without a
-gradient reduce-scatter (the recompute the kernel does anyway replaces the exchange).
+Backward (peer-memory transport, 256 < dim <= 512, rows per rank a multiple of 128): the shared-G form sharded as
+north_star describes it - the rank forms its row block of every pair's softmax-gradient matrix G once, the row-side
+gradients G Zcol are complete locally, and the column-side products G^T Zrow_local are reduce-scattered by the GEMM
+kernel itself: its accumulator drain TMA-stores each piece into the owner rank's receive buffer over NVLink
+(tcl_ntxent_bwd_sharded_gemm); one barrier, then the owner adds the W partials in a fixed order inside the normalise
+backward (tcl_ntxent_bwd_sharded_finish).  6 b B D executed per pair.  Otherwise (NCCL transport, other shapes,
+TRICOLO_B200_SHARDED_BWD=pc): the directional kernel of one GPU run for the local rows of each modality against ALL
+rows of the partner - complete local gradients without any exchange, at 8 b B D.
 
 Retrieval — gallery sharded over ranks (configs[4]): every rank scores all queries against its
 shard; ground-truth similarities are all-reduced (owner contributes, others add 0), local top-k
@@ -66,6 +71,25 @@ class _SymmWorkspace:
         self.multicast = bool(mc)
         self.dsts = [[base + (lo * n * dim + m * dim) * esz for m in range(n)] for base in bases]
         self.busy = False  # a forward with autograd holds the gathered operands until its backward
+        self.group, self.world, self.rank, self.b_loc, self.n, self.dim = group, world, rank, b_loc, n, dim
+        self._bwd = {}
+
+    def sharded_bwd(self, pairs, need_grad):
+        """(plan, local workspace, receive-buffer addresses per rank, symmetric handle) of the sharded shared-G backward.
+        First use for a (pairs, need_grad) combination allocates and rendezvouses the receive buffer: collective -
+        every rank reaches it in the same backward because the flags must agree across ranks."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        key = (tuple(pairs), tuple(bool(g) for g in need_grad))
+        if key not in self._bwd:
+            plan = ops.ShardedBwdPlan(self.n, pairs, need_grad, self.b_loc, self.world, self.dim)
+            dev = self.z.device
+            recv = symm_mem.empty((plan.recv_bytes,), dtype=torch.uint8, device=dev)
+            hr = symm_mem.rendezvous(recv, self.group if self.group is not None else dist.group.WORLD)
+            addrs = [int(hr.get_buffer(r, (plan.recv_bytes,), torch.uint8).data_ptr()) for r in range(self.world)]
+            work = torch.empty((plan.workspace_bytes,), dtype=torch.uint8, device=dev)
+            self._bwd[key] = (plan, work, addrs, hr, recv)
+        return self._bwd[key][:4]
 
 
 def _symm_enabled() -> bool:
@@ -90,6 +114,10 @@ def _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev):
     if ws is None or ws.busy:
         return None
     return ws
+
+
+def _sharded_g_enabled() -> bool:
+    return os.environ.get("TRICOLO_B200_SHARDED_BWD", "sharedg") != "pc"
 
 
 def _world(group=None):
@@ -169,6 +197,19 @@ class _GlobalNTXent(torch.autograd.Function):
         if gscale != 1.0:
             grad_losses = grad_losses * gscale
         grad_losses = grad_losses.contiguous()
+        ws = getattr(ctx, "symm_ws", None)
+        need = [bool(ctx.needs_input_grad[6 + m]) for m in range(n)]
+        if ws is not None and any(need) and _sharded_g_enabled() and ops.ShardedBwdPlan.supported(b_loc, dim, ws.world):
+            # row block of G once per pair; column-side partials land in their owners' receive buffers over NVLink
+            plan, work, addrs, hr = ws.sharded_bwd(pairs, need)
+            rank = row_offset // b_loc
+            ops.ntxent_bwd_sharded_gemm(plan, z_all, rank, inv_tau, alpha, lse2_row_all, lse2_col, grad_losses, work,
+                                        addrs, op_format)
+            hr.barrier(channel=0)  # every rank's partials have landed
+            inv_all = invs[0]._base if invs[0]._base is not None and invs[0]._base.shape == (n, b_loc) else torch.stack(list(invs))
+            grads = ops.ntxent_bwd_sharded_finish(plan, list(xs), inv_all, rank, work, addrs[rank])
+            ws.busy = False
+            return (None, None, None, None, None, None, *grads)
         zts, ld_t = ops.transpose_for_bwd(z_all)  # none for the default dim-512 kernel
         jobs, owners = [], []
         sl = slice(row_offset, row_offset + b_loc)
@@ -190,7 +231,6 @@ class _GlobalNTXent(torch.autograd.Function):
         if jobs:
             for m, dx in zip(owners, ops.ntxent_bwd(jobs, b_glob, row_offset, ld_t, inv_tau, op_format)):
                 grads[m] = dx
-        ws = getattr(ctx, "symm_ws", None)
         if ws is not None:
             ws.busy = False  # the gathered operands may be overwritten by the next forward (after its first barrier)
         return (None, None, None, None, None, None, *grads)

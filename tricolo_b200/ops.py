@@ -242,6 +242,67 @@ def ntxent_bwd(jobs: Sequence[BwdJobSpec], n_other: int, self_offset: int, ld_t:
     return dxs
 
 
+class ShardedBwdPlan:
+    """Sizes and host-side argument arrays of the sharded shared-G backward (tcl_ntxent_bwd_sharded_*): a pure function
+    of (pairs, need_grad, b_loc, world, dim), identical on every rank."""
+
+    def __init__(self, n_tensors: int, pairs, need_grad, b_loc: int, world: int, dim: int):
+        self.n_tensors, self.pairs, self.b_loc, self.world, self.dim = n_tensors, list(pairs), b_loc, world, dim
+        self.b_glob = b_loc * world
+        self.pair_row = (C.c_int32 * len(self.pairs))(*[a for a, _ in self.pairs])
+        self.pair_col = (C.c_int32 * len(self.pairs))(*[b for _, b in self.pairs])
+        self.need = (C.c_uint8 * n_tensors)(*[1 if g else 0 for g in need_grad])
+        self.need_grad = [bool(g) for g in need_grad]
+        args = (n_tensors, len(self.pairs), self.pair_row, self.pair_col, self.need, b_loc, self.b_glob, dim, world)
+        self.workspace_bytes = int(LIB.tcl_ntxent_bwd_sharded_workspace_bytes(*args))
+        self.recv_bytes = int(LIB.tcl_ntxent_bwd_sharded_recv_bytes(*args))
+        if self.workspace_bytes == 0 or self.recv_bytes == 0:
+            raise ValueError("sharded backward: unsupported configuration: " + LIB.tcl_last_error_string().decode())
+
+    @staticmethod
+    def supported(b_loc: int, dim: int, world: int) -> bool:
+        return 256 < dim <= 512 and dim % 64 == 0 and b_loc >= 128 and b_loc % 128 == 0 and 1 <= world <= 8
+
+
+def ntxent_bwd_sharded_gemm(plan: ShardedBwdPlan, z_all: Sequence[torch.Tensor], rank: int, inv_tau: float, alpha: float,
+                            lse2_row: torch.Tensor, lse2_col: torch.Tensor, grad_losses: torch.Tensor,
+                            workspace: torch.Tensor, recv_addrs: Sequence[int], op_format: int = F16) -> None:
+    """Kernel A (row block of G per pair) + kernel B (row-side gradients into local partials, column-side partials
+    stored into every owner's receive buffer, recv_addrs[r] = device address of rank r's buffer as mapped here)."""
+    dev = L.require_cuda(*z_all, lse2_row, lse2_col, grad_losses, workspace)
+    if lse2_row.shape != (len(plan.pairs), plan.b_glob) or lse2_col.shape != lse2_row.shape:
+        raise ValueError("sharded backward: LSEs must be [n_pairs, b_glob]")
+    if not (lse2_row.is_contiguous() and lse2_col.is_contiguous() and grad_losses.is_contiguous()):
+        raise ValueError("sharded backward: contiguous statistics expected")
+    recv = (C.c_void_p * plan.world)(*[int(a) for a in recv_addrs])
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_ntxent_bwd_sharded_gemm(plan.n_tensors, L.ptr_array(list(z_all)), plan.b_loc, plan.b_glob, plan.dim,
+                                                _z_stride(list(z_all)), rank, plan.world, len(plan.pairs), plan.pair_row,
+                                                plan.pair_col, op_format, inv_tau, alpha, L.ptr(lse2_row), L.ptr(lse2_col),
+                                                L.ptr(grad_losses), plan.need, L.ptr(workspace), workspace.numel(), recv,
+                                                plan.recv_bytes, L.stream_ptr(dev)))
+
+
+def ntxent_bwd_sharded_finish(plan: ShardedBwdPlan, xs: Sequence[torch.Tensor], invs: torch.Tensor, rank: int,
+                              workspace: torch.Tensor, recv_own_addr: int, eps: float = EPS) -> List[Optional[torch.Tensor]]:
+    """Sum of the local and received gradient partials + normalise backward.  Returns dx per tensor (None where no
+    gradient was requested).  The caller has made sure every rank's gemm call completed (cross-rank barrier)."""
+    dev = L.require_cuda(*xs, invs, workspace)
+    x0 = xs[0]
+    if any(x.shape != x0.shape or x.dtype != x0.dtype or x.stride(0) != x0.stride(0) or x.stride(1) != 1 for x in xs):
+        raise ValueError("sharded backward: inputs must share shape, dtype and row stride")
+    if invs.shape != (plan.n_tensors, plan.b_loc) or not invs.is_contiguous():
+        raise ValueError("sharded backward: inv_norm must be a contiguous [n_tensors, b_loc] tensor")
+    dxs = [torch.empty((plan.b_loc, plan.dim), dtype=x0.dtype, device=dev) if g else None for g in plan.need_grad]
+    dx_arr = (C.c_void_p * plan.n_tensors)(*[0 if d is None else d.data_ptr() for d in dxs])
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_ntxent_bwd_sharded_finish(plan.n_tensors, L.ptr_array(list(xs)), L.dtype_code(x0), plan.b_loc,
+                                                  plan.b_glob, plan.dim, x0.stride(0), rank, plan.world, len(plan.pairs),
+                                                  plan.pair_row, plan.pair_col, L.ptr(invs), plan.need, eps, L.ptr(workspace),
+                                                  C.c_void_p(int(recv_own_addr)), dx_arr, L.stream_ptr(dev)))
+    return dxs
+
+
 def sim_gemm(q16: torch.Tensor, g16: torch.Tensor, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
     """K2'. S = Q G^T in fp32 with leading dimension ld (multiple of 32 floats = one 128-byte line).
     Returns (S [n_q, ld], n_g)."""
