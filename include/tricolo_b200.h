@@ -78,6 +78,48 @@ int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x_host_ptrs, int x_dt
                          int64_t x_row_stride, int n_dst, void* const* z_dst_host_ptrs, int64_t z_row_stride,
                          int op_format, float* const* inv_norm_host_ptrs, float eps, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Sharded forward without barriers (tricolo_b200/distributed.py; semantics: nt_xent.py:55-74 on the concatenated
+ * global batch).  Every rank owns a zero-initialised, peer-mapped "sync pad" of
+ * tcl_shard_sync_bytes() (flags + step counters, tricolo_b200/csrc/host_common.h: ShardSync) and a peer-mapped
+ * statistics buffer of tcl_shard_stats_bytes(); sync_host_ptrs[r] / stats_host_ptrs[r] are rank r's buffers as
+ * mapped into this process.  Per step, in stream order on every rank:
+ *   tcl_l2norm_fwd_push      K1: normalised rows into the own gathered buffer + the flag "my operand buffer may be
+ *                            overwritten" to every peer at kernel start.  remote = 1: also the all-gather (as
+ *                            tcl_l2norm_fwd_bcast) with the flag "chunk c of my rows has landed" per 128 rows;
+ *                            remote = 0: the tile kernel's push warps do that while its MMAs run (n_push > 0 below)
+ *   tcl_ntxent_fwd_sharded   K2 on the local row block against all b_glob columns; column tiles are consumed in
+ *                            arrival order, each gated on its chunk's flag, so the NVLink gather overlaps the sweep.
+ *                            n_push > 0: the all-gather is FUSED into this kernel - two extra warps per CTA copy the
+ *                            rank's rows of the modalities at element offsets push_offsets[] of a gathered row into
+ *                            every rank's gathered buffer (z_base_host_ptrs[r]) while the MMAs run, and flag each
+ *                            128-row chunk.  Then the sum-exp statistics of this rank are stored into every rank's
+ *                            statistics buffer + flag
+ *   tcl_ntxent_finalize_sharded  waits for the W statistics flags, adds the column partials in rank order and
+ *                            finalises all rows: lse2_row [P][b_glob], lse2_col [P][b_glob], loss [P] (identical
+ *                            on every rank)
+ * No host synchronisation, no barrier kernel, capturable in a CUDA graph.  rows per rank % 128 == 0, <= 8192.
+ * Barrier form of the same two calls (sync pointers NULL; measured faster on 8 B200: system-scope fences are dear):
+ * tcl_ntxent_fwd_sharded sweeps contiguous tile ranges without gating (the caller ran a barrier after the gather) and
+ * writes this rank's statistics into slot `rank` of its OWN buffer; after a barrier, tcl_ntxent_finalize_sharded
+ * PULLS slot s from rank s's buffer over NVLink (W x ~100 KB) - one barrier and two kernels for the statistics
+ * exchange instead of zero/copy kernels + barrier + tcl_peer_sum_f32 + tcl_ntxent_finalize.
+ * ------------------------------------------------------------------------- */
+size_t tcl_shard_sync_bytes(void);
+size_t tcl_shard_stats_bytes(int n_pairs, int64_t b_loc, int world);
+int tcl_l2norm_fwd_push(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t rows, int64_t dim,
+                        int64_t x_row_stride, int rank, int world, void* const* z_dst_host_ptrs, int64_t z_row_stride,
+                        int op_format, float* const* inv_norm_host_ptrs, float eps, void* const* sync_host_ptrs,
+                        int remote, void* stream);
+int tcl_ntxent_fwd_sharded(int n_pairs, const void* const* zrow_host_ptrs, const void* const* zcol_host_ptrs,
+                           int64_t b_loc, int64_t b_glob, int64_t dim, int64_t z_row_stride, int rank, int world,
+                           int op_format, float inv_tau, float* diag2, void* workspace, size_t workspace_bytes,
+                           void* const* stats_host_ptrs, void* const* sync_host_ptrs, void* const* z_base_host_ptrs,
+                           int n_push, const int64_t* push_offsets_host, void* stream);
+int tcl_ntxent_finalize_sharded(int n_pairs, int64_t b_loc, int64_t b_glob, int rank, int world, float inv_tau,
+                                float alpha, void* const* stats_host_ptrs, const void* sync_own, float* lse2_row,
+                                float* lse2_col, float* loss, void* stream);
+
 /* out[i] = sum over r < n_src (in that order) of src[r][i], fp32: the one-shot all-reduce of the sum-exp statistics
  * over peer-mapped buffers (every rank reads all ranks' partials and adds them in rank order, so all ranks get
  * bit-identical sums).  16-byte aligned pointers; any n. */
@@ -185,8 +227,11 @@ int tcl_ntxent_bwd(int n_jobs, const tcl_bwd_job* jobs_host, int64_t n_self, int
  *           the column tensor; every 128-row piece of dCol is TMA-stored from the kernel's accumulator drain into the
  *           OWNER rank's receive buffer (recv_ptrs[owner], peer-mapped memory: the reduce-scatter is the kernel's own
  *           store traffic over NVLink, one slot per source rank, no atomics).  6*b_loc*b_glob*dim flop per pair.
- *   finish  (after a cross-rank barrier the caller provides: every rank's gemm has completed) sums the local and
- *           the received partials in a fixed order and applies the normalise backward -> dx[m] [b_loc, dim].
+ *   finish  sums the local and the received partials in a fixed order and applies the normalise backward ->
+ *           dx[m] [b_loc, dim].  It must not read before every rank's gemm has completed: either the caller runs a
+ *           cross-rank barrier between the two calls (sync pointers NULL), or both calls get the ranks' sync pads
+ *           (tcl_shard_sync_bytes): the last CTA of each gemm kernel then signals every rank and finish waits on
+ *           the device for the W flags - no barrier kernel, capturable in a CUDA graph.
  *   z_all[m]      gathered 16-bit operands [b_glob, dim] (row stride z_row_stride elements), identical on all ranks
  *   lse_row/col   [n_pairs][b_glob] log2-domain LSEs of all rows / columns (tcl_ntxent_finalize)
  *   recv_ptrs[r]  rank r's receive buffer as mapped into this process (recv_ptrs[rank] = the own one), each
@@ -206,12 +251,13 @@ int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_all_host_ptr
                                 const int32_t* pair_row, const int32_t* pair_col, int op_format, float inv_tau,
                                 float alpha, const float* lse_row, const float* lse_col, const float* grad_losses,
                                 const uint8_t* need_grad_host, void* workspace, size_t workspace_bytes,
-                                void* const* recv_host_ptrs, size_t recv_bytes, void* stream);
+                                void* const* recv_host_ptrs, size_t recv_bytes, void* const* sync_host_ptrs,
+                                void* stream);
 int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t b_loc,
                                   int64_t b_glob, int64_t dim, int64_t x_row_stride, int rank, int world, int n_pairs,
                                   const int32_t* pair_row, const int32_t* pair_col, const float* inv_norm,
                                   const uint8_t* need_grad_host, float eps, const void* workspace,
-                                  const void* recv_own, void* const* dx_host_ptrs, void* stream);
+                                  const void* recv_own, const void* sync_own, void* const* dx_host_ptrs, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Triplet loss: TripletLoss.forward(zis, zls) of tricolo/loss/triplet.py:202-224 with

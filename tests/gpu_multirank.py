@@ -24,9 +24,10 @@ def main():
     ok = True
     keys = ["text_features", "image_features", "voxel_features"]
 
-    def run_loss(loc, transport, bwd):
+    def run_loss(loc, transport, bwd, sync="flags"):
         os.environ["TRICOLO_B200_SYMM"] = transport
         os.environ["TRICOLO_B200_SHARDED_BWD"] = bwd
+        os.environ["TRICOLO_B200_SHARD_SYNC"] = sync
         for x in loc:
             x.grad = None
         out = global_calculate_losses(dict(zip(keys, loc)), "train_loss", TAU, ALPHA)
@@ -47,10 +48,12 @@ def main():
         loc = [f[rank * bl:(rank + 1) * bl].cuda().requires_grad_(True) for f in full]
         ref_l, ref_g = NO.trimodal_forward_backward(dict(zip(keys, [f.numpy() for f in full])), TAU, ALPHA)
         results = {}
-        # symm/sharedg: NVLink peer memory + sharded shared-G backward with the in-kernel reduce-scatter (the default
-        # for 128-row-aligned shards); symm/pc: same transport, directional backward; nccl: NCCL collectives
-        for name, transport, bwd in (("symm/sharedg", "1", "sharedg"), ("symm/pc", "1", "pc"), ("nccl/pc", "0", "pc")):
-            losses, grads = run_loss(loc, transport, bwd)
+        # symm/sharedg: NVLink peer memory, flag protocol (no barrier kernels), sharded shared-G backward with the
+        # in-kernel reduce-scatter - the default for 128-row-aligned shards; .../barrier: the same with cross-device
+        # barrier kernels instead of flags; symm/pc: directional backward; nccl: NCCL collectives
+        for name, transport, bwd, sync in (("symm/sharedg", "1", "sharedg", "flags"), ("symm/sharedg/barrier", "1", "sharedg", "barrier"),
+                                           ("symm/pc", "1", "pc", "flags"), ("nccl/pc", "0", "pc", "flags")):
+            losses, grads = run_loss(loc, transport, bwd, sync)
             lerr = max(abs(losses[k] - v) / abs(v) for k, v in ref_l.items())
             errs = [np.linalg.norm(grads[m].double().cpu().numpy() - ref_g[k][rank * bl:(rank + 1) * bl]) /
                     np.linalg.norm(ref_g[k][rank * bl:(rank + 1) * bl]) for m, k in enumerate(keys)]
@@ -58,13 +61,15 @@ def main():
             results[name] = (losses["train_loss/total_loss"], grads)
             print(f"[rank {rank}] rows/rank {bl} {name}: loss rel err {lerr:.2e} grad errs {['%.2e' % e for e in errs]}", flush=True)
         same = all(abs(results[n][0] - results["nccl/pc"][0]) <= 1e-6 * abs(results["nccl/pc"][0]) for n in results)
-        same &= all(torch.allclose(a, b, rtol=1e-5, atol=1e-9) for a, b in zip(results["symm/pc"][1], results["nccl/pc"][1]))
-        same &= all(close(a, b) for a, b in zip(results["symm/sharedg"][1], results["nccl/pc"][1]))
+        # (the flag protocol sweeps the column tiles in arrival order: the sum-exp statistics differ in the last fp32
+        # bit from the barrier / NCCL forms, which flips the 16-bit rounding of single entries of G)
+        same &= all(close(a, b) for n in results for a, b in zip(results[n][1], results["nccl/pc"][1]))
         ok &= same
         print(f"[rank {rank}] rows/rank {bl}: transports and backward forms agree: {same}", flush=True)
     # two forwards before the two backwards: the second forward must not overwrite the operands the first backward needs
     os.environ["TRICOLO_B200_SYMM"] = "1"
     os.environ["TRICOLO_B200_SHARDED_BWD"] = "sharedg"
+    os.environ["TRICOLO_B200_SHARD_SYNC"] = "flags"
     first = results["symm/sharedg"][1]
     loc2 = [(x.detach() * 0.5 + 0.1).requires_grad_(True) for x in loc]
     for x in loc:
@@ -73,7 +78,7 @@ def main():
     o2 = global_calculate_losses(dict(zip(keys, loc2)), "a", TAU, ALPHA)
     o2["a/total_loss"].backward()
     o1["a/total_loss"].backward()
-    inter = all(torch.allclose(x.grad, g, rtol=1e-5, atol=1e-9) for x, g in zip(loc, first))
+    inter = all(close(x.grad, g) for x, g in zip(loc, first))
     ok &= inter
     print(f"[rank {rank}] interleaved forwards keep their operands: {inter}", flush=True)
 

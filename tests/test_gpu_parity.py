@@ -534,6 +534,117 @@ def test_sharded_sharedg_backward_rank_emulation(tb, monkeypatch, b_glob, world,
             assert torch.allclose(dxs[m], ref, rtol=1e-3, atol=1e-3 * ref.abs().max().item()), (r, m)
 
 
+@pytest.mark.parametrize("b_glob,world,fused", [(1024, 8, True), (4096, 2, True), (1024, 8, False), (2048, 4, False),
+                                                (2048, 4, None), (1400, 2, None)])
+def test_flag_protocol_rank_emulation(tb, b_glob, world, fused):
+    """The barrier-free sharded step (tcl_l2norm_fwd_push -> tcl_ntxent_fwd_sharded -> tcl_ntxent_finalize_sharded ->
+    tcl_ntxent_bwd_sharded_gemm/_finish with sync pads) replayed rank by rank on ONE GPU, two steps in a row (the flags
+    carry the step number and are never reset).  fused: the all-gather of the column modalities (image, voxel) is done
+    by the tile kernel's push warps, text rows stay local; otherwise by K1.  Every wait finds its flag already set by
+    an earlier kernel of the replay, except the "ready" flags (a rank signals them at the start of ITS K1), which the
+    test sets by hand (and see the two-pass replay of the fused form below)."""
+    ops = tb.ops
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    b_loc = b_glob // world
+    n, dim = 3, 512
+    if fused is None:
+        return _barrier_form_rank_emulation(tb, b_glob, world)
+    zbufs = [torch.zeros((b_glob, n * dim), dtype=torch.float16, device="cuda") for _ in range(world)]
+    syncs = [torch.zeros((ops.shard_sync_bytes() // 4,), dtype=torch.int32, device="cuda") for _ in range(world)]
+    stats = [torch.full((ops.shard_stats_bytes(3, b_loc, world) // 4,), float("nan"), device="cuda") for _ in range(world)]
+    plan = ops.ShardedBwdPlan(3, pairs, (1, 1, 1), b_loc, world, dim)
+    recv = [torch.full((plan.recv_bytes,), 0xFF, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    wss = [torch.empty((plan.workspace_bytes,), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    sync_addrs, stats_addrs, recv_addrs = [x.data_ptr() for x in syncs], [x.data_ptr() for x in stats], [x.data_ptr() for x in recv]
+    for step in (1, 2):
+        g = torch.Generator().manual_seed(40 + step)
+        base = torch.randn(b_glob, dim, generator=g)
+        f = [(base + 0.5 * torch.randn(b_glob, dim, generator=g)).bfloat16().float().cuda() for _ in range(n)]
+        dev = [x.clone().requires_grad_(True) for x in f]
+        losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA)
+        losses.sum().backward()
+        for sy in syncs:
+            sy[16:16 + world] = step  # ShardSync::kReady: every peer is ready for this step
+        fwd = []
+        for r in range(world):
+            sl = slice(r * b_loc, (r + 1) * b_loc)
+            dsts = [[zb.data_ptr() + (r * b_loc * n * dim + m * dim) * 2 for m in range(n)] for zb in zbufs]
+            fwd.append(ops.l2norm_fwd_push([x[sl] for x in f], dsts, n * dim, r, world, sync_addrs, remote=not fused))
+        if not fused:
+            for zb in zbufs[1:]:
+                assert torch.equal(zb, zbufs[0])
+        z_addrs = [zb.data_ptr() for zb in zbufs]
+        # fused: rank r's tile kernel needs the rows that the LATER ranks' tile kernels push.  Replay in two passes: in
+        # the first every arrival flag is pre-set, so no kernel waits (its remote tiles read rows that may not have
+        # landed yet: results discarded) but every rank's push warps deliver and flag their rows; the second pass then
+        # finds all rows in place.  (The waiting itself is exercised across real GPUs by tests/gpu_multirank.py.)
+        for replay in ((0, 1) if fused else (1,)):
+            if fused and replay == 0:
+                for sy in syncs:
+                    sy[64:64 + 8 * 64] = step  # ShardSync::kArrived
+            for r in range(world):
+                z3 = zbufs[r].view(b_glob, n, dim)
+                z_all = [z3[:, m] for m in range(n)]
+                sl = slice(r * b_loc, (r + 1) * b_loc)
+                ops.ntxent_fwd_sharded([z_all[a][sl] for a, _ in pairs], [z_all[b] for _, b in pairs], r, world, 1.0 / TAU,
+                                       stats_addrs, sync_addrs, z_base_addrs=z_addrs,
+                                       push_offsets=[dim, 2 * dim] if fused else ())
+        if fused:  # image and voxel rows are everywhere, text rows only at home
+            for zb in zbufs[1:]:
+                assert torch.equal(zb.view(b_glob, n, dim)[:, 1:], zbufs[0].view(b_glob, n, dim)[:, 1:])
+        fin = [ops.ntxent_finalize_sharded(3, b_loc, r, world, 1.0 / TAU, ALPHA, stats_addrs, sync_addrs[r], f[0].device)
+               for r in range(world)]
+        for r in range(world):
+            assert torch.equal(fin[r][0], fin[0][0]) and torch.equal(fin[r][1], fin[0][1]) and torch.equal(fin[r][2], fin[0][2])
+        assert torch.allclose(fin[0][2], losses.detach(), rtol=1e-5)
+        ones = torch.ones((3,), device="cuda")
+        for r in range(world):
+            z3 = zbufs[r].view(b_glob, n, dim)
+            ops.ntxent_bwd_sharded_gemm(plan, [z3[:, m] for m in range(n)], r, 1.0 / TAU, ALPHA, fin[r][0], fin[r][1], ones,
+                                        wss[r], recv_addrs, sync_addrs=sync_addrs)
+        for r in range(world):
+            sl = slice(r * b_loc, (r + 1) * b_loc)
+            inv_all, xs = fwd[r]
+            dxs = ops.ntxent_bwd_sharded_finish(plan, xs, inv_all, r, wss[r], recv_addrs[r], sync_own_addr=sync_addrs[r])
+            for m in range(n):
+                ref = dev[m].grad[sl]
+                assert float((dxs[m] - ref).norm()) <= 1e-4 * float(ref.norm()), (step, r, m)
+        for sy in syncs:  # step counters: forward epoch, backward epoch, and every flag at this step's value
+            assert int(sy[0]) == step and int(sy[1]) == step
+            assert all(int(v) == step for v in sy[32:32 + world]) and all(int(v) == step for v in sy[48:48 + world])
+
+
+def _barrier_form_rank_emulation(tb, b_glob, world):
+    """fused=None: the barrier form of the same entry points (sync pointers NULL): contiguous tile ranges, statistics
+    written into the own slot and PULLED by the finalise kernel from every rank's buffer; any rows per rank."""
+    ops = tb.ops
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    b_loc, n, dim = b_glob // world, 3, 512
+    g = torch.Generator().manual_seed(50)
+    base = torch.randn(b_glob, dim, generator=g)
+    f = [(base + 0.5 * torch.randn(b_glob, dim, generator=g)).bfloat16().float().cuda() for _ in range(n)]
+    losses = tb.loss.trimodal_ntxent(f, TAU, ALPHA)
+    zbuf = torch.zeros((b_glob, n * dim), dtype=torch.float16, device="cuda")
+    stats = [torch.full((ops.shard_stats_bytes(3, b_loc, world) // 4,), float("nan"), device="cuda") for _ in range(world)]
+    stats_addrs = [x.data_ptr() for x in stats]
+    for r in range(world):  # tcl_l2norm_fwd_bcast (16-byte stores): here all destinations are one buffer
+        sl = slice(r * b_loc, (r + 1) * b_loc)
+        ops.l2norm_fwd_bcast([x[sl] for x in f], [[zbuf.data_ptr() + (r * b_loc * n * dim + m * dim) * 2 for m in range(n)]], n * dim)
+    z_ref, _, _ = ops.l2norm_fwd(f, 0)
+    for m in range(n):
+        assert torch.equal(zbuf.view(b_glob, n, dim)[:, m], z_ref[m])
+    z_all = [zbuf.view(b_glob, n, dim)[:, m] for m in range(n)]
+    for r in range(world):
+        sl = slice(r * b_loc, (r + 1) * b_loc)
+        ops.ntxent_fwd_sharded([z_all[a][sl] for a, _ in pairs], [z_all[b] for _, b in pairs], r, world, 1.0 / TAU, stats_addrs, None)
+    fin = [ops.ntxent_finalize_sharded(3, b_loc, r, world, 1.0 / TAU, ALPHA, stats_addrs, 0, f[0].device) for r in range(world)]
+    for r in range(world):
+        assert all(torch.equal(fin[r][k], fin[0][k]) for k in range(3))
+    assert torch.allclose(fin[0][2], losses, rtol=1e-5)
+    z_all2, invs, xs, lse2_row_all, lse2_col, loss = _emulated_forward(tb, f, pairs, world)
+    assert torch.allclose(fin[0][0], lse2_row_all, rtol=1e-6, atol=1e-6) and torch.allclose(fin[0][1], lse2_col, rtol=1e-6, atol=1e-6)
+
+
 def test_bcast_normalise_and_peer_sum_single_gpu(tb):
     """tcl_l2norm_fwd_bcast with several local destinations must equal tcl_l2norm_fwd bit for bit (on a multi-GPU
     box the destinations are peer-mapped buffers: tests/gpu_multirank.py); tcl_peer_sum_f32 adds in the given order."""

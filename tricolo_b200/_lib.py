@@ -72,6 +72,12 @@ SIGNATURES = {
     "tcl_l2norm_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _pp, _i64, _i, _pp, _f, _vp]),
     "tcl_l2norm_fwd_bcast": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, _pp, _i64, _i, _pp, _f, _vp]),
     "tcl_peer_sum_f32": (_i, [_i, _pp, _i64, _vp, _vp]),
+    "tcl_shard_sync_bytes": (_sz, []),
+    "tcl_shard_stats_bytes": (_sz, [_i, _i64, _i]),
+    "tcl_l2norm_fwd_push": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, _i, _pp, _i64, _i, _pp, _f, _pp, _i, _vp]),
+    "tcl_ntxent_fwd_sharded": (_i, [_i, _pp, _pp, _i64, _i64, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _sz, _pp, _pp, _pp, _i,
+                                    C.POINTER(C.c_int64), _vp]),
+    "tcl_ntxent_finalize_sharded": (_i, [_i, _i64, _i64, _i, _i, _f, _f, _pp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_cast_16bit": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp]),
     "tcl_triplet_workspace_bytes": (_sz, [_i64]),
     "tcl_triplet_fwd": (_i, [_vp, _vp, _i, _i64, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),
@@ -89,9 +95,9 @@ SIGNATURES = {
                                                 _i64, _i64, _i64, _i]),
     "tcl_ntxent_bwd_sharded_gemm": (_i, [_i, _pp, _i64, _i64, _i64, _i64, _i, _i, _i, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), _i, _f, _f, _vp, _vp, _vp, C.POINTER(C.c_uint8), _vp, _sz,
-                                         _pp, _sz, _vp]),
+                                         _pp, _sz, _pp, _vp]),
     "tcl_ntxent_bwd_sharded_finish": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, C.POINTER(C.c_int32),
-                                           C.POINTER(C.c_int32), _vp, C.POINTER(C.c_uint8), _f, _vp, _vp, _pp, _vp]),
+                                           C.POINTER(C.c_int32), _vp, C.POINTER(C.c_uint8), _f, _vp, _vp, _vp, _pp, _vp]),
     "tcl_ntxent_loss_state_bytes": (_sz, [_i, _i, _i64, _i64]),
     "tcl_ntxent_loss_workspace_bytes": (_sz, [_i, _i, _i64, _i64]),
     "tcl_ntxent_loss_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

@@ -48,6 +48,41 @@ __device__ __forceinline__ float lg2_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------
+// system-scope flags in (peer-mapped) global memory: the sharded loss signals "rows landed", "statistics landed",
+// "gradient partials landed" to the other ranks with a release store into THEIR flag word over NVLink and waits on
+// its own words with acquire loads.  Flags carry a step counter (epoch), compared with wrap-safe arithmetic, so they
+// are never reset.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic-proxy view of global memory (after an acquire) -> async proxy (TMA loads issued afterwards)
+__device__ __forceinline__ void fence_proxy_async_generic() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// spin until *p has reached epoch e; a dead peer turns into a trap after ~10 s instead of a hung GPU
+__device__ __forceinline__ void flag_wait_ge(const uint32_t* p, uint32_t e) {
+  if (static_cast<int32_t>(ld_acquire_sys_u32(p) - e) >= 0) return;
+  const long long t0 = clock64();
+  while (static_cast<int32_t>(ld_acquire_sys_u32(p) - e) < 0) {
+    __nanosleep(64);
+    if (clock64() - t0 > 20000000000LL) {
+      printf("tricolo_b200: cross-rank flag watchdog (block %d,%d thread %d, epoch %u, flag %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, e, ld_acquire_sys_u32(p));
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

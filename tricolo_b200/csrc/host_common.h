@@ -65,6 +65,25 @@ __host__ __device__ inline int pc_range_of(int64_t total, int64_t t, int n) {
   return static_cast<int>(((t + 1) * n - 1) / total);
 }
 
+// Word layout (uint32) of the "sync pad" of the sharded loss: one zero-initialised, peer-mapped 4 KB buffer per rank.
+// Epoch counters are written by the rank itself; flags are written by the peers (release stores over NVLink) and
+// polled locally.  include/tricolo_b200.h: tcl_shard_sync_bytes.
+struct ShardSync {
+  static constexpr int kFwdEpoch = 0;    // forward steps completed by this rank's K1
+  static constexpr int kBwdEpoch = 1;    // backward steps completed by this rank's gradient GEMM
+  static constexpr int kK1Done = 2;      // block counters (reset to 0 by the block that completes them)
+  static constexpr int kStatsDone = 3;
+  static constexpr int kGemmDone = 4;
+  static constexpr int kReady = 16;      // [src]: rank src no longer reads its operand buffer of the previous step
+  static constexpr int kStats = 32;      // [src]: rank src's sum-exp statistics have landed here
+  static constexpr int kGrads = 48;      // [src]: rank src's gradient partials have landed here
+  static constexpr int kArrived = 64;    // [src][chunk]: 128-row chunk of rank src's normalised rows has landed here
+  static constexpr int kMaxChunks = 64;  // rows per rank <= 8192
+  static constexpr int kChunkCnt = kArrived + TCL_MAX_PEERS * kMaxChunks;  // [chunk]: local block counters of K1
+  static constexpr int kWords = 1024;
+};
+static_assert(ShardSync::kChunkCnt + ShardSync::kMaxChunks <= ShardSync::kWords, "sync pad layout");
+
 // normalise backward (l2norm.cu), launched by tcl_ntxent_bwd after the gradient GEMM
 struct NormBwdJob {
   const void* x;
@@ -102,6 +121,7 @@ struct NormShParams {
   int64_t total_tiles;
   int64_t row_slot_stride;  // elements between row-side slots
   const float* scales;      // [world] scale of every source rank (receive-buffer header)
+  const uint32_t* sync;     // own sync pad: wait for every source's kGrads flag (NULL: the caller ran a barrier)
   int n_ranges, n_dsplit, world, rank, n_slots_col;
 };
 int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim, int64_t x_stride,

@@ -133,41 +133,123 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(PtrPack3 pk, int64_t ro
   }
 }
 
-// K1 + all-gather: the normalised row goes to n_dst peer-mapped buffers (st.global over NVLink for the remote ones)
-struct BcastPack {
+// K1 + all-gather + flags (the sharded loss's first kernel; tricolo_b200/distributed.py, host_common.h: ShardSync).
+//   * block (0,0) tells every peer "my operand buffer may be overwritten" (kReady, epoch e) - stream order guarantees
+//     that this rank's readers of the previous step have finished;
+//   * every warp normalises one row, stores it locally at once and to peer p as soon as p's kReady flag shows e;
+//   * the last block of a 128-row chunk (all modalities) signals kArrived[rank][chunk] = e to every peer: the forward
+//     tile kernel of the peer loads a column tile as soon as its chunk has landed (no barrier);
+//   * the last block of the grid publishes the new epoch locally.
+// Each lane handles 8 consecutive elements: 16-byte stores over NVLink.
+struct PushPack {
   const void* in[TCL_MAX_TENSORS];
   void* out[TCL_MAX_PEERS][TCL_MAX_TENSORS];
   float* aux[TCL_MAX_TENSORS];
-  int n_dst;
+  uint32_t* sync[TCL_MAX_PEERS];  // sync pad of every rank as mapped here; sync[rank] is the own one
+  int rank, world, n_tensors;
+  int remote;  // 1: this kernel also stores the rows to the peers and flags the chunks; 0: the forward tile kernel's
+               // push warps do that while its MMAs run (tcl_ntxent_fwd_sharded); 2: plain stores to `world` destinations,
+               // no flags at all (tcl_l2norm_fwd_bcast: the caller brackets the launch with barriers)
 };
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]);
+template <>
+__device__ __forceinline__ uint4 pack8<__half>(const float (&o)[8]) {
+  uint4 u;
+  *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(o[0], o[1]);
+  *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(o[2], o[3]);
+  *reinterpret_cast<__half2*>(&u.z) = __floats2half2_rn(o[4], o[5]);
+  *reinterpret_cast<__half2*>(&u.w) = __floats2half2_rn(o[6], o[7]);
+  return u;
+}
+template <>
+__device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&o)[8]) {
+  uint4 u;
+  *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(o[0], o[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(o[2], o[3]);
+  *reinterpret_cast<__nv_bfloat162*>(&u.z) = __floats2bfloat162_rn(o[4], o[5]);
+  *reinterpret_cast<__nv_bfloat162*>(&u.w) = __floats2bfloat162_rn(o[6], o[7]);
+  return u;
+}
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) l2norm_fwd_bcast_kernel(const __grid_constant__ BcastPack pk, int64_t rows, int dim,
-                                                               int64_t x_stride, int64_t z_stride, float eps) {
+__global__ void __launch_bounds__(256) l2norm_fwd_push_kernel(const __grid_constant__ PushPack pk, int64_t rows, int dim,
+                                                              int64_t x_stride, int64_t z_stride, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
-  if (row >= rows) return;
-  const TIn* x = static_cast<const TIn*>(pk.in[blockIdx.y]) + row * x_stride;
-  constexpr int kMaxIter = 4;  // dim <= 512: the row stays in registers
-  float v[kMaxIter][4];
-  float ss = 0.f;
+  // blocks in (row block, tensor) order, tensor fastest: the blocks of one 128-row chunk are scheduled together
+  const int tensor = static_cast<int>(blockIdx.x % pk.n_tensors);
+  const uint32_t rowblock = blockIdx.x / pk.n_tensors;
+  const int64_t row = static_cast<int64_t>(rowblock) * 8 + warp;
+  const bool flags = pk.remote != 2;
+  uint32_t* sy = pk.sync[pk.rank];
+  const uint32_t e = flags ? ld_relaxed_u32(sy + ShardSync::kFwdEpoch) + 1u : 0u;  // written only by the grid's LAST block
+  if (flags && blockIdx.x == 0 && threadIdx.x < pk.world && static_cast<int>(threadIdx.x) != pk.rank)
+    st_release_sys_u32(pk.sync[threadIdx.x] + ShardSync::kReady + pk.rank, e);
+  if (row < rows) {
+    const TIn* x = static_cast<const TIn*>(pk.in[tensor]) + row * x_stride;
+    float v[2][8];
+    float ss = 0.f;
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int c = it * 128 + lane * 4;
-    if (c < dim) {
-      load4<TIn>(x + c, v[it]);
-      ss += v[it][0] * v[it][0] + v[it][1] * v[it][1] + v[it][2] * v[it][2] + v[it][3] * v[it][3];
+    for (int it = 0; it < 2; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < dim) {
+        float a[4], b[4];
+        load4<TIn>(x + c, a);
+        load4<TIn>(x + c + 4, b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[it][k] = a[k];
+          v[it][4 + k] = b[k];
+          ss += a[k] * a[k] + b[k] * b[k];
+        }
+      }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0) pk.aux[tensor][row] = inv;
+    uint4 o[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = v[it][k] * inv;
+      o[it] = pack8<TOut>(t);
+    }
+    const int n_dst = pk.remote ? pk.world : 1;
+    for (int d = 0; d < n_dst; ++d) {
+      const int p = (pk.rank + d) % pk.world;  // own buffer first, then the peers in a rank-staggered order
+      if (d > 0 && flags) {
+        if (lane == 0) flag_wait_ge(sy + ShardSync::kReady + p, e);
+        __syncwarp();
+      }
+      TOut* z = static_cast<TOut*>(pk.out[p][tensor]) + row * z_stride;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int c = it * 256 + lane * 8;
+        if (c < dim) *reinterpret_cast<uint4*>(z + c) = o[it];
+      }
     }
   }
-  ss = warp_sum(ss);
-  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
-  if (lane == 0) pk.aux[blockIdx.y][row] = inv;
-#pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int c = it * 128 + lane * 4;
-    if (c < dim) {
-      float o[4] = {v[it][0] * inv, v[it][1] * inv, v[it][2] * inv, v[it][3] * inv};
-      for (int d = 0; d < pk.n_dst; ++d)
-        store4<TOut>(static_cast<TOut*>(pk.out[d][blockIdx.y]) + row * z_stride + c, o);
+  if (!flags) return;
+  if (pk.remote) __threadfence_system();
+  else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (pk.remote) {
+      const uint32_t chunk = rowblock >> 4;  // 16 row blocks of 8 rows, all tensors
+      const int64_t rows_left = rows - static_cast<int64_t>(chunk) * 128;
+      const uint32_t rows_in_chunk = static_cast<uint32_t>(rows_left < 128 ? rows_left : 128);
+      const uint32_t per_chunk = ((rows_in_chunk + 7) / 8) * pk.n_tensors;
+      if (atomicAdd(sy + ShardSync::kChunkCnt + chunk, 1u) + 1u == per_chunk) {  // last block of the chunk
+        sy[ShardSync::kChunkCnt + chunk] = 0u;  // nobody touches the counter again before the next step
+        __threadfence_system();
+        for (int p = 0; p < pk.world; ++p)
+          if (p != pk.rank) st_release_sys_u32(pk.sync[p] + ShardSync::kArrived + pk.rank * ShardSync::kMaxChunks + chunk, e);
+      }
+    }
+    if (atomicAdd(sy + ShardSync::kK1Done, 1u) + 1u == gridDim.x) {
+      sy[ShardSync::kK1Done] = 0u;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(sy + ShardSync::kFwdEpoch) = e;
     }
   }
 }
@@ -443,6 +525,11 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
                                                                  int dim, int64_t x_stride, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (pr.sync != nullptr) {  // every source rank's gradient GEMM has completed and its partials have landed here
+    if (static_cast<int>(threadIdx.x) < pr.world)
+      flag_wait_ge(pr.sync + ShardSync::kGrads + threadIdx.x, ld_relaxed_u32(pr.sync + ShardSync::kBwdEpoch));
+    __syncthreads();
+  }
   if (row >= rows) return;
   const NormShJob& jb = pr.job[blockIdx.y];
   const T* x = static_cast<const T*>(jb.x) + row * x_stride;
@@ -466,8 +553,8 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
   }
   float sc[TCL_MAX_PEERS];
 #pragma unroll
-  for (int r = 0; r < TCL_MAX_PEERS; ++r) sc[r] = r < pr.world ? pr.scales[r] : 0.f;
-  const float sc_own = pr.scales[pr.rank];
+  for (int r = 0; r < TCL_MAX_PEERS; ++r) sc[r] = r < pr.world ? __ldcv(pr.scales + r) : 0.f;
+  const float sc_own = __ldcv(pr.scales + pr.rank);
   constexpr int kMaxIter = 4;
   float g[kMaxIter][4], z[kMaxIter][4];
   float dot = 0.f;
@@ -490,7 +577,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
 #pragma unroll
         for (int r = 0; r < TCL_MAX_PEERS; ++r)
           v[r] = r < pr.world
-                     ? __ldcs(reinterpret_cast<const float4*>(jb.col_part + (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
+                     ? __ldcv(reinterpret_cast<const float4*>(jb.col_part + (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
                      : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < TCL_MAX_PEERS; ++r) {
@@ -539,6 +626,9 @@ int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, i
 
 using namespace tcl;
 
+static int launch_push(const struct tcl::PushPack& pk, int n_tensors, int x_dtype, int64_t rows, int dim, int64_t stride,
+                       int64_t z_stride, int op_format, float eps, cudaStream_t st);
+
 extern "C" int tcl_l2norm_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t rows,
                               int64_t dim, int64_t x_row_stride, void* const* z, int64_t z_row_stride,
                               int op_format, float* const* inv_norm, float eps, void* stream) {
@@ -559,21 +649,24 @@ extern "C" int tcl_l2norm_fwd(int n_tensors, const void* const* x, int x_dtype, 
     TCL_REQUIRE(aligned_to(x[i], 16) && aligned_to(z[i], 16), TCL_ERR_BAD_ALIGN, "l2norm: pointers must be 16-byte aligned");
     pk.in[i] = x[i]; pk.out[i] = z[i]; pk.aux[i] = inv_norm[i];
   }
+  if (dim <= 512) {
+    // the same kernel as the sharded forms (8 elements per lane, 16-byte stores, one destination): identical bits
+    // whether a row is normalised here, by tcl_l2norm_fwd_bcast or by tcl_l2norm_fwd_push
+    PushPack pp{};
+    pp.rank = 0;
+    pp.world = 1;
+    pp.n_tensors = n_tensors;
+    pp.remote = 2;
+    for (int i = 0; i < n_tensors; ++i) {
+      pp.in[i] = x[i];
+      pp.aux[i] = inv_norm[i];
+      pp.out[0][i] = z[i];
+    }
+    return launch_push(pp, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
+                       static_cast<cudaStream_t>(stream));
+  }
   return launch_fwd<true>(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
                           static_cast<cudaStream_t>(stream));
-}
-
-template <typename TIn>
-static int launch_bcast_t(const BcastPack& pk, int n_tensors, int64_t rows, int dim, int64_t stride, int64_t z_stride,
-                          int op_format, float eps, cudaStream_t st) {
-  dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_tensors);
-  ProfScope prof(TCL_K_L2NORM_FWD, st);
-  if (op_format == TCL_OP_F16)
-    l2norm_fwd_bcast_kernel<TIn, __half><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
-  else
-    l2norm_fwd_bcast_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
-  TCL_CHECK_CUDA(cudaGetLastError());
-  return TCL_OK;
 }
 
 extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_dtype, int64_t rows, int64_t dim,
@@ -589,8 +682,11 @@ extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_d
   TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
   if (int e = require_sm100()) return e;
   if (rows == 0) return TCL_OK;
-  BcastPack pk{};
-  pk.n_dst = n_dst;
+  PushPack pk{};
+  pk.rank = 0;
+  pk.world = n_dst;
+  pk.n_tensors = n_tensors;
+  pk.remote = 2;
   for (int i = 0; i < n_tensors; ++i) {
     TCL_REQUIRE(x[i] && inv_norm[i] && aligned_to(x[i], 16), TCL_ERR_BAD_ALIGN, "l2norm_bcast: input %d", i);
     pk.in[i] = x[i];
@@ -601,14 +697,72 @@ extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_d
       pk.out[d][i] = p;
     }
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return launch_push(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
+                     static_cast<cudaStream_t>(stream));
+}
+
+template <typename TIn>
+static int launch_push_t(const PushPack& pk, int n_tensors, int64_t rows, int dim, int64_t stride, int64_t z_stride,
+                         int op_format, float eps, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((rows + 7) / 8) * n_tensors);
+  ProfScope prof(TCL_K_L2NORM_FWD, st);
+  if (op_format == TCL_OP_F16)
+    l2norm_fwd_push_kernel<TIn, __half><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
+  else
+    l2norm_fwd_push_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+static int launch_push(const PushPack& pk, int n_tensors, int x_dtype, int64_t rows, int dim, int64_t stride,
+                       int64_t z_stride, int op_format, float eps, cudaStream_t st) {
   switch (x_dtype) {
-    case TCL_DT_F32: return launch_bcast_t<float>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
-    case TCL_DT_F64: return launch_bcast_t<double>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
-    case TCL_DT_F16: return launch_bcast_t<__half>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
-    case TCL_DT_BF16: return launch_bcast_t<__nv_bfloat16>(pk, n_tensors, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps, st);
+    case TCL_DT_F32: return launch_push_t<float>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
+    case TCL_DT_F64: return launch_push_t<double>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
+    case TCL_DT_F16: return launch_push_t<__half>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
+    case TCL_DT_BF16: return launch_push_t<__nv_bfloat16>(pk, n_tensors, rows, dim, stride, z_stride, op_format, eps, st);
   }
   return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
+}
+
+extern "C" size_t tcl_shard_sync_bytes(void) { return sizeof(uint32_t) * ShardSync::kWords; }
+
+extern "C" int tcl_l2norm_fwd_push(int n_tensors, const void* const* x, int x_dtype, int64_t rows, int64_t dim,
+                                   int64_t x_row_stride, int rank, int world, void* const* z_dst, int64_t z_row_stride,
+                                   int op_format, float* const* inv_norm, float eps, void* const* sync_ptrs,
+                                   int remote, void* stream) {
+  if (z_row_stride == 0) z_row_stride = dim;
+  TCL_REQUIRE(z_row_stride >= dim && z_row_stride % 8 == 0, TCL_ERR_BAD_ALIGN, "l2norm_push: z_row_stride");
+  TCL_REQUIRE(n_tensors >= 1 && n_tensors <= TCL_MAX_TENSORS, TCL_ERR_BAD_ARG, "n_tensors %d", n_tensors);
+  TCL_REQUIRE(world >= 1 && world <= TCL_MAX_PEERS && rank >= 0 && rank < world, TCL_ERR_BAD_ARG, "l2norm_push: rank %d of %d", rank, world);
+  TCL_REQUIRE(rows >= 1 && rows <= 128 * ShardSync::kMaxChunks && dim >= 8 && dim % 8 == 0 && dim <= 512, TCL_ERR_BAD_SHAPE,
+              "l2norm_push: rows in [1, %d], dim a multiple of 8 in [8, 512] (got %lld x %lld)", 128 * ShardSync::kMaxChunks,
+              (long long)rows, (long long)dim);
+  TCL_REQUIRE(x_row_stride >= dim && (x_row_stride * dtype_size(x_dtype)) % 16 == 0, TCL_ERR_BAD_ALIGN, "l2norm_push: row stride");
+  TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
+  TCL_REQUIRE(x && z_dst && inv_norm && sync_ptrs, TCL_ERR_BAD_ARG, "l2norm_push: null pointer");
+  if (int e = require_sm100()) return e;
+  PushPack pk{};
+  pk.rank = rank;
+  pk.world = world;
+  pk.n_tensors = n_tensors;
+  pk.remote = remote != 0;
+  for (int r = 0; r < world; ++r) {
+    TCL_REQUIRE(sync_ptrs[r] && aligned_to(sync_ptrs[r], 16), TCL_ERR_BAD_ALIGN, "l2norm_push: sync pad %d", r);
+    pk.sync[r] = static_cast<uint32_t*>(sync_ptrs[r]);
+  }
+  for (int i = 0; i < n_tensors; ++i) {
+    TCL_REQUIRE(x[i] && inv_norm[i] && aligned_to(x[i], 16), TCL_ERR_BAD_ALIGN, "l2norm_push: input %d", i);
+    pk.in[i] = x[i];
+    pk.aux[i] = inv_norm[i];
+    for (int d = 0; d < world; ++d) {
+      void* p = z_dst[d * n_tensors + i];
+      TCL_REQUIRE(p && aligned_to(p, 16), TCL_ERR_BAD_ALIGN, "l2norm_push: destination %d of tensor %d", d, i);
+      pk.out[d][i] = p;
+    }
+  }
+  return launch_push(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
+                     static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tcl_peer_sum_f32(int n_src, const float* const* src, int64_t n, float* out, void* stream) {

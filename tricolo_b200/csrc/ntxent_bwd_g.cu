@@ -395,6 +395,10 @@ struct GBParams {
   int unit_tiles[GB_MAX_JOBS];  // n_seg * k_tiles
   int dim, n_dsplit;
   uint32_t idesc_row, idesc_col;  // M=128, N=256, B MN-major; A K-major / MN-major
+  // sharded: when the LAST CTA has finished (all partials stored, also those that crossed NVLink) it signals
+  // kGrads[rank] = epoch to every rank and publishes the backward epoch (host_common.h: ShardSync); world = 0: off
+  uint32_t* sync[TCL_MAX_PEERS];
+  int rank, world;
 };
 
 struct GBPiece {
@@ -644,7 +648,11 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
       GT_END(8);
       ++piece;
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) {
+      bulk_wait_all();               // every TMA store of this warp is complete ...
+      fence_proxy_async_generic();   // ... and ordered before the generic-proxy signalling below
+      __threadfence_system();
+    }
 #ifdef TCL_PAIR_TRACE
     GT_ADD(9, clock64() - gt_w0);
 #endif
@@ -652,6 +660,17 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (P.world > 0 && threadIdx.x == 0) {
+    uint32_t* sy = P.sync[P.rank];
+    const uint32_t e = ld_relaxed_u32(sy + ShardSync::kBwdEpoch) + 1u;  // written only by the last CTA, below
+    __threadfence_system();
+    if (atomicAdd(sy + ShardSync::kGemmDone, 1u) + 1u == gridDim.x) {
+      sy[ShardSync::kGemmDone] = 0u;
+      __threadfence_system();
+      for (int p = 0; p < P.world; ++p) st_release_sys_u32(P.sync[p] + ShardSync::kGrads + P.rank, e);
+      *reinterpret_cast<volatile uint32_t*>(sy + ShardSync::kBwdEpoch) = e;
+    }
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -952,7 +971,7 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
                                            float inv_tau, float alpha, const float* lse_row, const float* lse_col,
                                            const float* grad_losses, const uint8_t* need_grad, void* workspace,
                                            size_t workspace_bytes, void* const* recv_ptrs, size_t recv_bytes,
-                                           void* stream) {
+                                           void* const* sync_ptrs, void* stream) {
   TCL_REQUIRE(z_all && pair_row && pair_col && lse_row && lse_col && grad_losses && need_grad && workspace && recv_ptrs,
               TCL_ERR_BAD_ARG, "bwd_sharded_gemm: null pointer");
   TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
@@ -1059,6 +1078,14 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
   B.n_dsplit = S.n_dsplit;
   B.idesc_row = umma_idesc_f16(BW_BM, 256, op_format) | (1u << 16);
   B.idesc_col = B.idesc_row | (1u << 15);
+  if (sync_ptrs != nullptr) {
+    for (int r = 0; r < world; ++r) {
+      TCL_REQUIRE(sync_ptrs[r] && aligned_to(sync_ptrs[r], 16), TCL_ERR_BAD_ALIGN, "bwd_sharded_gemm: sync pad %d", r);
+      B.sync[r] = static_cast<uint32_t*>(sync_ptrs[r]);
+    }
+    B.rank = rank;
+    B.world = world;
+  }
   return launch_ggemm(B, S.n_ctas, st);
 }
 
@@ -1066,8 +1093,8 @@ extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x
                                              int64_t b_glob, int64_t dim, int64_t x_row_stride, int rank, int world,
                                              int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
                                              const float* inv_norm, const uint8_t* need_grad, float eps,
-                                             const void* workspace, const void* recv_own, void* const* dx,
-                                             void* stream) {
+                                             const void* workspace, const void* recv_own, const void* sync_own,
+                                             void* const* dx, void* stream) {
   TCL_REQUIRE(x && pair_row && pair_col && inv_norm && need_grad && workspace && recv_own && dx, TCL_ERR_BAD_ARG,
               "bwd_sharded_finish: null pointer");
   ShardPlan S;
@@ -1116,6 +1143,7 @@ extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x
   N.n_slots_col = S.n_slots_col;
   N.row_slot_stride = static_cast<int64_t>(S.n_self_pad) * dim;
   N.scales = reinterpret_cast<const float*>(rv);
+  N.sync = static_cast<const uint32_t*>(sync_own);
   return launch_l2norm_bwd_sharded(N, n_out, x_dtype, b_loc, static_cast<int>(dim), x_row_stride, eps,
                                    static_cast<cudaStream_t>(stream));
 }

@@ -42,7 +42,101 @@ struct FwdParams {
   uint32_t idesc_pair;
   const void* z_row[TCL_MAX_PAIRS];
   int64_t z_row_stride;
+  // sharded form (tcl_ntxent_fwd_sharded): the column operand is the gathered buffer that the ranks' K1 kernels are
+  // still filling over NVLink.  A CTA takes every n_jsplit-th tile of the ARRIVAL order (own rows first, then chunk c
+  // of every peer, c = 0, 1, ...) and loads a tile once its chunk's kArrived flag shows this step's epoch.
+  const uint32_t* sync;  // own sync pad (host_common.h: ShardSync); nullptr = not sharded: contiguous tile ranges
+  int rank, world, chunks_per_rank;
+  // fused all-gather (n_push > 0): two extra warps per CTA copy this rank's normalised rows of the pushed modalities
+  // from the own gathered buffer into every peer's (16-byte stores over NVLink) while the MMAs run, chunk by chunk in
+  // row order, and flag each completed 128-row chunk - the transfer overlaps the tile sweep of the same kernel
+  uint16_t* z_peer[TCL_MAX_PEERS];     // every rank's gathered buffer [b_glob, z_row_stride] as mapped here
+  uint32_t* sync_peer[TCL_MAX_PEERS];  // every rank's sync pad
+  int n_push, dim;
+  int n_push_ctas;                     // CTAs (lowest linear ids = first wave, co-resident) that carry push warps' work:
+                                       // a later wave could not start while the first one waits for a peer's rows,
+                                       // and that peer waits for OUR rows
+  int push_off[TCL_MAX_TENSORS];       // element offset of a pushed modality inside a gathered row
 };
+
+// number of column tiles of split js, and the t-th of them
+__device__ __forceinline__ int fwd_n_tiles(const FwdParams& P, int js) {
+  if (P.sync == nullptr)
+    return static_cast<int>((static_cast<int64_t>(P.n_jtiles) * (js + 1)) / P.n_jsplit) -
+           static_cast<int>((static_cast<int64_t>(P.n_jtiles) * js) / P.n_jsplit);
+  return (P.n_jtiles - js + P.n_jsplit - 1) / P.n_jsplit;
+}
+__device__ __forceinline__ int fwd_tile(const FwdParams& P, int js, int t) {
+  if (P.sync == nullptr) return static_cast<int>((static_cast<int64_t>(P.n_jtiles) * js) / P.n_jsplit) + t;
+  int k = js + t * P.n_jsplit;  // position in the arrival order
+  const int nct = P.chunks_per_rank;
+  if (k < nct || P.world == 1) return P.rank * nct + k;
+  k -= nct;
+  const int c = k / (P.world - 1);
+  int peer = P.rank + 1 + (k - c * (P.world - 1));
+  if (peer >= P.world) peer -= P.world;
+  return peer * nct + c;
+}
+// push warps: units (row, pushed modality) in row order, strided over all push warps of the grid, so that every warp
+// works on chunk 0 first: chunks complete - and are flagged - progressively
+__device__ __forceinline__ void fwd_push_flush(const FwdParams& P, uint32_t* sy, int chunk, uint32_t cnt, uint32_t e, int lane) {
+  if (chunk < 0 || cnt == 0) return;
+  __threadfence_system();  // this lane's stores are performed system-wide
+  __syncwarp();
+  if (lane == 0) {
+    const int left = P.n_rows - chunk * 128;
+    const uint32_t per_chunk = static_cast<uint32_t>(left < 128 ? left : 128) * P.n_push;
+    if (atomicAdd(sy + ShardSync::kChunkCnt + chunk, cnt) + cnt == per_chunk) {  // this warp completed the chunk
+      sy[ShardSync::kChunkCnt + chunk] = 0u;
+      __threadfence_system();
+      for (int p = 0; p < P.world; ++p)
+        if (p != P.rank) st_release_sys_u32(P.sync_peer[p] + ShardSync::kArrived + P.rank * ShardSync::kMaxChunks + chunk, e);
+    }
+  }
+}
+__device__ __forceinline__ void fwd_push_rows(const FwdParams& P, int pusher, int n_pushers, int lane) {
+  uint32_t* sy = P.sync_peer[P.rank];
+  const uint32_t e = ld_acquire_sys_u32(sy + ShardSync::kFwdEpoch);
+  const int total = P.n_rows * P.n_push;
+  uint32_t ready = 0, cnt = 0;
+  int cur = -1;
+  for (int u = pusher; u < total; u += n_pushers) {
+    const int row = u / P.n_push, mi = u - row * P.n_push;
+    if ((row >> 7) != cur) {
+      fwd_push_flush(P, sy, cur, cnt, e, lane);
+      cur = row >> 7;
+      cnt = 0;
+    }
+    const size_t off = static_cast<size_t>(P.row_offset + row) * P.z_row_stride + P.push_off[mi];
+    const uint4* src = reinterpret_cast<const uint4*>(P.z_peer[P.rank] + off);
+    const bool h0 = lane * 8 < P.dim, h1 = (lane + 32) * 8 < P.dim;
+    const uint4 v0 = h0 ? src[lane] : make_uint4(0, 0, 0, 0);
+    const uint4 v1 = h1 ? src[lane + 32] : make_uint4(0, 0, 0, 0);
+    for (int d = 1; d < P.world; ++d) {
+      int p = P.rank + d;
+      if (p >= P.world) p -= P.world;
+      if (!((ready >> p) & 1u)) {  // the peer no longer reads its buffer of the previous step
+        if (lane == 0) flag_wait_ge(sy + ShardSync::kReady + p, e);
+        __syncwarp();
+        ready |= 1u << p;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(P.z_peer[p] + off);
+      if (h0) dst[lane] = v0;
+      if (h1) dst[lane + 32] = v1;
+    }
+    ++cnt;
+  }
+  fwd_push_flush(P, sy, cur, cnt, e, lane);
+}
+
+// producer side: tile jt's rows have landed (rank-local tiles were written by this rank's own K1)
+__device__ __forceinline__ void fwd_wait_tile(const FwdParams& P, int jt, uint32_t epoch) {
+  if (P.sync == nullptr) return;
+  const int owner = jt / P.chunks_per_rank;
+  if (owner == P.rank) return;
+  flag_wait_ge(P.sync + ShardSync::kArrived + owner * ShardSync::kMaxChunks + (jt - owner * P.chunks_per_rank), epoch);
+  fence_proxy_async_generic();
+}
 
 // shared memory map (offsets from the 1024-aligned base)
 struct FwdSmem {
@@ -173,7 +267,8 @@ __device__ __forceinline__ void fwd_row_sums(float (&rs)[4], int q, int ch, int 
   }
 }
 
-__global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_constant__ FwdParams P) {
+static constexpr int FW_PUSH_WARPS = 2;
+__global__ void __launch_bounds__(FW_THREADS + FW_PUSH_WARPS * 32, 1) ntxent_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -194,10 +289,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ib = blockIdx.x, js = blockIdx.y, pair = blockIdx.z;
   const int i0 = ib * FW_BM;
-  // contiguous range of column tiles for this split
-  const int t_begin = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * js) / P.n_jsplit);
-  const int t_end = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * (js + 1)) / P.n_jsplit);
-  const int n_tiles = t_end - t_begin;
+  const int n_tiles = fwd_n_tiles(P, js);  // contiguous range of column tiles (sharded: strided arrival order)
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&P.tm_row[pair]);
@@ -229,8 +321,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
       for (int kb = 0; kb < num_kb; ++kb)
         tma_load_2d(x_smem + kb * FW_KB_BYTES, &P.tm_row[pair], x_full_bar, kb * FW_BK, i0);
       int it = 0;
+      const uint32_t epoch = P.sync ? ld_acquire_sys_u32(P.sync + ShardSync::kFwdEpoch) : 0u;
       for (int t = 0; t < n_tiles; ++t) {
-        const int j0 = (t_begin + t) * FW_BN;
+        const int jt = fwd_tile(P, js, t);
+        const int j0 = jt * FW_BN;
+        fwd_wait_tile(P, jt, epoch);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % FW_STAGES;
           const uint32_t ph = (it / FW_STAGES) & 1;
@@ -264,6 +359,11 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
         tc_commit(tmem_full_bar(b));
       }
     }
+  } else if (warp >= 2 + FW_EPI_WARPS) {
+    // push warps (only launched for the sharded form with n_push > 0)
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (cta < P.n_push_ctas)
+      fwd_push_rows(P, cta * FW_PUSH_WARPS + (warp - 2 - FW_EPI_WARPS), P.n_push_ctas * FW_PUSH_WARPS, lane);
   } else {
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int ch = (warp - 2) >> 2;  // column half of the tile (64 columns)
@@ -275,7 +375,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) ntxent_fwd_kernel(const __grid_
     const bool row_edge = i0 + FW_BM > P.n_rows;
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t & 1;
-      const int j0 = (t_begin + t) * FW_BN;
+      const int j0 = fwd_tile(P, js, t) * FW_BN;
       mbar_wait(tmem_full_bar(b), (t >> 1) & 1);
       tc_fence_after();
       // diagonal: global row = row_offset + i0 + r, global col = j0 + c  ->  c = r + delta
@@ -366,9 +466,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ntxent_fwd_pair_kernel(const __
   FT_DECL
   const int ib = blockIdx.x, js = blockIdx.y, pair = blockIdx.z;  // cluster = two CTAs adjacent in x
   const int i0 = ib * FW_BM;
-  const int t_begin = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * js) / P.n_jsplit);
-  const int t_end = static_cast<int>((static_cast<int64_t>(P.n_jtiles) * (js + 1)) / P.n_jsplit);
-  const int n_tiles = t_end - t_begin;
+  const int n_tiles = fwd_n_tiles(P, js);
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&P.tm_col[pair]);
@@ -431,8 +529,11 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ntxent_fwd_pair_kernel(const __
     if (elect_one()) {
       // this CTA's half of every K-block (tile rows 64 * rank .. + 64), multicast into both CTAs' slots
       uint32_t it = 0;
+      const uint32_t epoch = P.sync ? ld_acquire_sys_u32(P.sync + ShardSync::kFwdEpoch) : 0u;
       for (int t = 0; t < n_tiles; ++t) {
-        const int j0 = (t_begin + t) * FW_BN + static_cast<int>(crank) * 64;
+        const int jt = fwd_tile(P, js, t);
+        const int j0 = jt * FW_BN + static_cast<int>(crank) * 64;
+        fwd_wait_tile(P, jt, epoch);
         for (int kb = 0; kb < num_kb; kb += 2, ++it) {
           const int nk = kb + 1 < num_kb ? 2 : 1;
           const int s = it % F2_STAGES;
@@ -496,7 +597,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ntxent_fwd_pair_kernel(const __
     float* diag_out = P.diag2 + static_cast<int64_t>(pair) * P.n_rows + i0;
     const bool row_edge = i0 + FW_BM > P.n_rows;
     for (int t = gi; t < n_tiles; t += 2) {
-      const int j0 = (t_begin + t) * FW_BN;
+      const int j0 = fwd_tile(P, js, t) * FW_BN;
       FT_BEGIN();
       mbar_wait(tmem_full_bar(gi), (t >> 1) & 1);
       FT_END(crank == 0 ? 7 : 11);
@@ -652,6 +753,132 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded statistics exchange (replaces fwd_reduce + zero/copy kernels + barrier + peer_sum of the first version):
+//   fwd_reduce_push   reduces the tile kernel's partials and stores this rank's column sum-exp partials [P][B], row
+//                     sum-exp [P][b_loc] and positives [P][b_loc] into slot `rank` of EVERY rank's statistics buffer
+//                     (plain stores over NVLink); the last block signals kStats[rank] = epoch to every rank;
+//   fwd_finalize_sharded  waits for the W flags, adds the column partials in rank order (bit-identical on every
+//                     rank), and finalises ALL rows: lse2_row [P][B], lse2_col [P][B], loss [P].
+// Slot layout (floats): col [P][B] | row [P][b_loc] | diag [P][b_loc], padded to a multiple of 4.
+// ---------------------------------------------------------------------------------------------------------------
+static inline int64_t shard_stats_slot_floats(int n_pairs, int64_t b_loc, int64_t b_glob) {
+  return (static_cast<int64_t>(n_pairs) * (b_glob + 2 * b_loc) + 3) / 4 * 4;
+}
+struct StatsPushParams {
+  float* dst[TCL_MAX_PEERS];
+  uint32_t* sync[TCL_MAX_PEERS];
+  const float* row_part;
+  const float* col_part;
+  const float* diag2;
+  int64_t slot_floats;
+  int n_pairs, n_rows, n_cols, n_row_slots, n_iblocks, rank, world;
+  int local_only;  // 1: slot `rank` of the OWN buffer only, no flag: the ranks pull after a barrier (tcl_ntxent_finalize_sharded)
+};
+__global__ void __launch_bounds__(256) fwd_reduce_push_kernel(const __grid_constant__ StatsPushParams P) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t* sy = P.sync[P.rank];
+  const uint32_t e = P.local_only ? 0u : ld_relaxed_u32(sy + ShardSync::kFwdEpoch);  // published by this step's K1
+  const int64_t slot = static_cast<int64_t>(P.rank) * P.slot_floats;
+  const int n_dst = P.local_only ? 1 : P.world;
+  if (i < P.n_cols) {
+    float a = 0.f;
+    for (int b = 0; b < P.n_iblocks; ++b) a += P.col_part[(static_cast<int64_t>(pair) * P.n_iblocks + b) * P.n_cols + i];
+    for (int d = 0; d < n_dst; ++d) {
+      const int p = (P.rank + d) % P.world;
+      P.dst[p][slot + static_cast<int64_t>(pair) * P.n_cols + i] = a;
+    }
+  }
+  if (i < P.n_rows) {
+    float a = 0.f;
+    for (int s = 0; s < P.n_row_slots; ++s) a += P.row_part[(static_cast<int64_t>(pair) * P.n_row_slots + s) * P.n_rows + i];
+    const float dg = P.diag2[static_cast<int64_t>(pair) * P.n_rows + i];
+    const int64_t ro = slot + static_cast<int64_t>(P.n_pairs) * P.n_cols + static_cast<int64_t>(pair) * P.n_rows + i;
+    for (int d = 0; d < n_dst; ++d) {
+      const int p = (P.rank + d) % P.world;
+      P.dst[p][ro] = a;
+      P.dst[p][ro + static_cast<int64_t>(P.n_pairs) * P.n_rows] = dg;
+    }
+  }
+  if (P.local_only) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(sy + ShardSync::kStatsDone, 1u) + 1u == gridDim.x * gridDim.y) {
+    sy[ShardSync::kStatsDone] = 0u;
+    __threadfence_system();
+    for (int p = 0; p < P.world; ++p) st_release_sys_u32(P.sync[p] + ShardSync::kStats + P.rank, e);
+  }
+}
+
+struct StatsSrc {
+  const float* slot[TCL_MAX_PEERS];  // slot s = rank s's statistics: in the own buffer (flags) or in rank s's (pull)
+};
+__global__ void __launch_bounds__(1024) fwd_finalize_sharded_kernel(
+    int b_loc, int b_glob, int n_pairs, int world, float c1, float alpha, const __grid_constant__ StatsSrc src,
+    const uint32_t* __restrict__ sync, float* __restrict__ lse2_row, float* __restrict__ lse2_col,
+    float* __restrict__ loss) {
+  const int pair = blockIdx.y;
+  const int crank = static_cast<int>(cluster_ctarank());
+  if (sync != nullptr) {
+    const uint32_t e = ld_relaxed_u32(sync + ShardSync::kFwdEpoch);
+    if (static_cast<int>(threadIdx.x) < world) flag_wait_ge(sync + ShardSync::kStats + threadIdx.x, e);
+    __syncthreads();
+  }
+  float* lr = lse2_row + static_cast<int64_t>(pair) * b_glob;
+  float* lc = lse2_col + static_cast<int64_t>(pair) * b_glob;
+  const int tid = crank * blockDim.x + threadIdx.x, nth = FIN_CTAS * blockDim.x;
+  const int64_t row_base = static_cast<int64_t>(n_pairs) * b_glob + static_cast<int64_t>(pair) * b_loc;
+  const int64_t diag_base = row_base + static_cast<int64_t>(n_pairs) * b_loc;
+  double a = 0.0, b = 0.0;
+  for (int j = tid; j < b_glob; j += nth) {
+    float part[TCL_MAX_PEERS];  // column j: partials of all ranks (all loads in flight: they may cross NVLink)
+#pragma unroll
+    for (int s = 0; s < TCL_MAX_PEERS; ++s)
+      part[s] = s < world ? __ldcv(src.slot[s] + static_cast<int64_t>(pair) * b_glob + j) : 0.f;
+    const int so = j / b_loc, i = j - so * b_loc;  // row j belongs to rank so
+    const float rsum = __ldcv(src.slot[so] + row_base + i);
+    const float dg = __ldcv(src.slot[so] + diag_base + i);
+    float cs = 0.f;  // rank order: bit-identical on every rank
+#pragma unroll
+    for (int s = 0; s < TCL_MAX_PEERS; ++s)
+      if (s < world) cs += part[s];
+    const float lcj = log2f(cs) + c1;
+    lc[j] = lcj;
+    const float l = log2f(rsum) + c1;
+    lr[j] = l;
+    a += static_cast<double>(l - dg);
+    b += static_cast<double>(lcj - dg);
+  }
+  __shared__ double sa[1024], sb[1024];
+  __shared__ double part[2 * FIN_CTAS];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sb[threadIdx.x] += sb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t dst = map_to_peer(smem_u32(part), 0u) + 16u * crank;
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst), "d"(sa[0]) : "memory");
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst + 8u), "d"(sb[0]) : "memory");
+  }
+  cluster_sync_all();
+  if (crank == 0 && threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int r = 0; r < FIN_CTAS; ++r) {
+      ta += part[2 * r];
+      tb += part[2 * r + 1];
+    }
+    const double ln2 = 0.69314718055994530942;
+    loss[pair] = static_cast<float>((alpha * ta * ln2 + (1.0 - alpha) * tb * ln2) / b_glob);
+  }
+}
+
 static int fwd_split(int n_pairs, int n_iblocks, int n_jtiles) {
   // One CTA per SM.  Cost model of a split s of the column sweep: waves(s) x (prologue + tiles per CTA), the
   // prologue (row block into shared memory / TMEM, pipeline fill) being worth about two tiles.  Small problems end up
@@ -686,10 +913,20 @@ extern "C" size_t tcl_ntxent_fwd_workspace_bytes(int n_pairs, int64_t n_rows, in
          (static_cast<size_t>(2 * n_jsplit) * n_rows + static_cast<size_t>(n_iblocks) * n_cols);
 }
 
+struct FwdShard {
+  const uint32_t* sync;  // own sync pad
+  int rank, world;
+  // fused all-gather (n_push > 0)
+  void* const* z_base;     // [world] gathered buffers
+  void* const* sync_all;   // [world] sync pads
+  int n_push;
+  const int64_t* push_off;
+};
 static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* const* zcol,
                            int64_t n_rows, int64_t n_cols, int64_t dim, int64_t z_row_stride, int64_t row_offset,
                            int op_format, float inv_tau, float* row_sumexp, float* col_sumexp,
-                           float* diag2, void* workspace, size_t workspace_bytes, void* stream, FwdPartials* parts) {
+                           float* diag2, void* workspace, size_t workspace_bytes, void* stream, FwdPartials* parts,
+                           const FwdShard* shard = nullptr) {
   TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "ntxent_fwd: n_pairs %d", n_pairs);
   TCL_REQUIRE(n_rows >= 1 && n_cols >= 1 && n_rows < (1 << 24) && n_cols < (1 << 24), TCL_ERR_BAD_SHAPE,
               "ntxent_fwd: batch sizes out of range (%lld x %lld)", (long long)n_rows, (long long)n_cols);
@@ -702,7 +939,7 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
   const float c1 = inv_tau * 1.4426950408889634f;
   TCL_REQUIRE(inv_tau > 0.f && 2.f * c1 < 120.f, TCL_ERR_BAD_ARG,
               "ntxent_fwd: temperature %g too small for the fixed-shift sum-exp (need tau >= 0.025)", 1.0 / inv_tau);
-  TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && workspace, TCL_ERR_BAD_ARG, "ntxent_fwd: null pointer");
+  TCL_REQUIRE((parts || (row_sumexp && col_sumexp)) && diag2 && workspace, TCL_ERR_BAD_ARG, "ntxent_fwd: null pointer");
   TCL_REQUIRE(workspace_bytes >= tcl_ntxent_fwd_workspace_bytes(n_pairs, n_rows, n_cols), TCL_ERR_WORKSPACE,
               "ntxent_fwd: workspace too small");
   if (z_row_stride == 0) z_row_stride = dim;
@@ -717,7 +954,8 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
     const char* e = getenv("TRICOLO_B200_FWD");
     return e && !strcmp(e, "single") ? 1 : (e && !strcmp(e, "pair") ? 2 : 0);
   }();
-  const bool use_pair = fwd_mode == 2 || (fwd_mode == 0 && n_rows >= 2048);
+  // (the push warps of the fused all-gather live in the one-CTA-per-row-block kernel)
+  const bool use_pair = (fwd_mode == 2 || (fwd_mode == 0 && n_rows >= 2048)) && !(shard != nullptr && shard->n_push > 0);
   for (int p = 0; p < n_pairs; ++p) {
     TCL_REQUIRE(zrow[p] && zcol[p], TCL_ERR_BAD_ARG, "ntxent_fwd: null operand (pair %d)", p);
     TCL_REQUIRE(aligned_to(zrow[p], 16), TCL_ERR_BAD_ALIGN, "ntxent_fwd: operands must be 16-byte aligned");
@@ -738,6 +976,21 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
   P.row_part = static_cast<float*>(workspace);
   P.col_part = P.row_part + static_cast<size_t>(n_pairs) * 2 * P.n_jsplit * n_rows;
   P.diag2 = diag2;
+  if (shard != nullptr) {
+    TCL_REQUIRE(n_rows % FW_BM == 0 && n_cols == n_rows * shard->world && row_offset == n_rows * shard->rank, TCL_ERR_BAD_SHAPE,
+                "ntxent_fwd_sharded: rows per rank must be a multiple of 128 and n_cols = world * n_rows");
+    P.sync = shard->sync;
+    P.rank = shard->rank;
+    P.world = shard->world;
+    P.chunks_per_rank = static_cast<int>(n_rows / FW_BM);
+    P.n_push = shard->n_push;
+    P.dim = static_cast<int>(dim);
+    for (int r = 0; r < shard->world && shard->n_push > 0; ++r) {
+      P.z_peer[r] = static_cast<uint16_t*>(shard->z_base[r]);
+      P.sync_peer[r] = static_cast<uint32_t*>(shard->sync_all[r]);
+    }
+    for (int m = 0; m < shard->n_push; ++m) P.push_off[m] = static_cast<int>(shard->push_off[m]);
+  }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_pair) {
@@ -761,8 +1014,15 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
     const int smem = (int)FwdSmem::total(P.num_kb);
     if (int e = ensure_dyn_smem(ntxent_fwd_kernel, smem)) return e;
     dim3 grid(P.n_iblocks, P.n_jsplit, n_pairs);
+    if (P.n_push > 0) {
+      int dev = 0, n_sm = 0;
+      TCL_CHECK_CUDA(cudaGetDevice(&dev));
+      TCL_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+      const int64_t total = static_cast<int64_t>(grid.x) * grid.y * grid.z;
+      P.n_push_ctas = static_cast<int>(total < n_sm ? total : n_sm);
+    }
     ProfScope prof(TCL_K_NTXENT_FWD, st);
-    ntxent_fwd_kernel<<<grid, FW_THREADS, smem, st>>>(P);
+    ntxent_fwd_kernel<<<grid, FW_THREADS + (P.n_push > 0 ? FW_PUSH_WARPS * 32 : 0), smem, st>>>(P);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   if (parts != nullptr) {  // the caller reduces the partials itself (fused into the finalise kernel)
@@ -851,3 +1111,99 @@ int ntxent_fwd_finalize_fused(int n_pairs, const void* const* zrow, const void* 
                               loss_parts, loss, stream, fuse ? &parts : nullptr);
 }
 }  // namespace tcl
+
+// ---------------------------------------------------------------------------------------------------------------
+// sharded forward: tile kernel gated on the arrival flags + statistics push, then the waiting finalise
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" size_t tcl_shard_stats_bytes(int n_pairs, int64_t b_loc, int world) {
+  if (n_pairs < 1 || n_pairs > TCL_MAX_PAIRS || b_loc < 1 || world < 1 || world > TCL_MAX_PEERS) return 0;
+  return static_cast<size_t>(world) * tcl::shard_stats_slot_floats(n_pairs, b_loc, b_loc * world) * sizeof(float);
+}
+
+extern "C" int tcl_ntxent_fwd_sharded(int n_pairs, const void* const* zrow, const void* const* zcol, int64_t b_loc,
+                                      int64_t b_glob, int64_t dim, int64_t z_row_stride, int rank, int world,
+                                      int op_format, float inv_tau, float* diag2, void* workspace,
+                                      size_t workspace_bytes, void* const* stats_ptrs, void* const* sync_ptrs,
+                                      void* const* z_base_ptrs, int n_push, const int64_t* push_offsets, void* stream) {
+  TCL_REQUIRE(world >= 1 && world <= TCL_MAX_PEERS && rank >= 0 && rank < world, TCL_ERR_BAD_ARG, "fwd_sharded: rank %d of %d", rank, world);
+  TCL_REQUIRE(stats_ptrs && diag2, TCL_ERR_BAD_ARG, "fwd_sharded: null pointer");
+  TCL_REQUIRE(b_loc >= 1 && b_loc <= 128 * ShardSync::kMaxChunks && b_glob == b_loc * world, TCL_ERR_BAD_SHAPE, "fwd_sharded: sizes");
+  const bool flags = sync_ptrs != nullptr;  // else: the caller brackets the calls with cross-rank barriers
+  TCL_REQUIRE(flags || n_push == 0, TCL_ERR_BAD_ARG, "fwd_sharded: the fused all-gather needs the sync pads");
+  for (int r = 0; r < world; ++r)
+    TCL_REQUIRE(stats_ptrs[r] && aligned_to(stats_ptrs[r], 16) && (!flags || (sync_ptrs[r] && aligned_to(sync_ptrs[r], 16))),
+                TCL_ERR_BAD_ALIGN, "fwd_sharded: buffers of rank %d", r);
+  TCL_REQUIRE(n_push >= 0 && n_push <= TCL_MAX_TENSORS && (n_push == 0 || (z_base_ptrs && push_offsets)), TCL_ERR_BAD_ARG,
+              "fwd_sharded: n_push %d", n_push);
+  for (int r = 0; r < world && n_push > 0; ++r)
+    TCL_REQUIRE(z_base_ptrs[r] && aligned_to(z_base_ptrs[r], 16), TCL_ERR_BAD_ALIGN, "fwd_sharded: gathered buffer of rank %d", r);
+  for (int m = 0; m < n_push; ++m)
+    TCL_REQUIRE(push_offsets[m] >= 0 && push_offsets[m] % 8 == 0, TCL_ERR_BAD_ALIGN, "fwd_sharded: push offset %d", m);
+  FwdShard sh{flags ? static_cast<const uint32_t*>(sync_ptrs[rank]) : nullptr, rank, world, z_base_ptrs, sync_ptrs, n_push,
+              push_offsets};
+  FwdPartials parts;
+  if (int e = ntxent_fwd_impl(n_pairs, zrow, zcol, b_loc, b_glob, dim, z_row_stride, b_loc * rank, op_format, inv_tau, nullptr,
+                              nullptr, diag2, workspace, workspace_bytes, stream, &parts, flags ? &sh : nullptr))
+    return e;
+  StatsPushParams S;
+  memset(&S, 0, sizeof(S));
+  for (int r = 0; r < world; ++r) {
+    S.dst[r] = static_cast<float*>(stats_ptrs[r]);
+    S.sync[r] = flags ? static_cast<uint32_t*>(sync_ptrs[r]) : nullptr;
+  }
+  S.local_only = flags ? 0 : 1;
+  S.row_part = parts.row_part;
+  S.col_part = parts.col_part;
+  S.diag2 = diag2;
+  S.slot_floats = shard_stats_slot_floats(n_pairs, b_loc, b_glob);
+  S.n_pairs = n_pairs;
+  S.n_rows = static_cast<int>(b_loc);
+  S.n_cols = static_cast<int>(b_glob);
+  S.n_row_slots = parts.n_row_slots;
+  S.n_iblocks = parts.n_iblocks;
+  S.rank = rank;
+  S.world = world;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    ProfScope prof(TCL_K_FWD_REDUCE, st);
+    fwd_reduce_push_kernel<<<dim3(static_cast<unsigned>((b_glob + 255) / 256), n_pairs), 256, 0, st>>>(S);
+  }
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+extern "C" int tcl_ntxent_finalize_sharded(int n_pairs, int64_t b_loc, int64_t b_glob, int rank, int world, float inv_tau,
+                                           float alpha, void* const* stats_ptrs, const void* sync_own, float* lse2_row,
+                                           float* lse2_col, float* loss, void* stream) {
+  TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS && world >= 1 && world <= TCL_MAX_PEERS && b_glob == b_loc * world &&
+                  rank >= 0 && rank < world, TCL_ERR_BAD_ARG, "finalize_sharded: sizes");
+  TCL_REQUIRE(stats_ptrs && lse2_row && lse2_col && loss, TCL_ERR_BAD_ARG, "finalize_sharded: null pointer");
+  // flags: every rank pushed its statistics into slot s of THIS rank's buffer; pull: slot s is read from rank s's buffer
+  StatsSrc src;
+  memset(&src, 0, sizeof(src));
+  const int64_t slot_floats = shard_stats_slot_floats(n_pairs, b_loc, b_glob);
+  for (int s2 = 0; s2 < world; ++s2) {
+    TCL_REQUIRE(stats_ptrs[s2] != nullptr, TCL_ERR_BAD_ARG, "finalize_sharded: statistics buffer %d", s2);
+    src.slot[s2] = static_cast<const float*>(stats_ptrs[sync_own ? rank : s2]) + s2 * slot_floats;
+  }
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(TCL_K_FWD_FINALIZE, st);
+  int threads = 32;
+  while (threads < 1024 && threads * FIN_CTAS < b_glob) threads <<= 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(FIN_CTAS, n_pairs, 1);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = FIN_CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_finalize_sharded_kernel, (int)b_loc, (int)b_glob, n_pairs, world,
+                                    inv_tau * 1.4426950408889634f, alpha, src, static_cast<const uint32_t*>(sync_own), lse2_row,
+                                    lse2_col, loss));
+  return TCL_OK;
+}

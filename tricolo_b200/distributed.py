@@ -42,8 +42,9 @@ from .loss.nt_xent import DEFAULT_OP_FORMAT
 # symmetric-memory allocations mapped into every peer:
 #   * K1 writes each normalised row straight into all ranks' gathered buffers (tcl_l2norm_fwd_bcast: the all-gather
 #     is the kernel's own store traffic over NVLink), bracketed by two device-side barriers;
-#   * the sum-exp statistics are reduced one-shot: barrier, then every rank adds all ranks' partials in rank order
-#     (tcl_peer_sum_f32) - bit-identical sums everywhere, no NCCL launch.
+#   * the sum-exp statistics are exchanged through per-rank slots: every rank writes its slot, one barrier, then the
+#     finalise kernel pulls all slots over NVLink and adds them in rank order (tcl_ntxent_finalize_sharded) -
+#     bit-identical sums everywhere, no NCCL launch.
 # Buffers are cached per (group, shapes); a forward that needs gradients holds its buffer until its backward ran.
 # ---------------------------------------------------------------------------------------------------------------
 _SYMM_CACHE = {}
@@ -56,10 +57,15 @@ class _SymmWorkspace:
         b_glob = b_loc * world
         self.z = symm_mem.empty((b_glob, n * dim), dtype=dt, device=dev)
         self.hz = symm_mem.rendezvous(self.z, group if group is not None else dist.group.WORLD)
-        self.stats = symm_mem.empty((3, p, b_glob), dtype=torch.float32, device=dev)
-        self.hs = symm_mem.rendezvous(self.stats, group if group is not None else dist.group.WORLD)
         self.z_peers = [self.hz.get_buffer(r, self.z.shape, dt) for r in range(world)]
-        self.stats_peers = [self.hs.get_buffer(r, self.stats.shape, torch.float32) for r in range(world)]
+        # statistics slots [world][col P x B | row P x b_loc | diag P x b_loc]: a rank writes slot `rank` of its own
+        # buffer and every rank pulls slot s from rank s (barrier form), or pushes it into every buffer (flag form)
+        g = group if group is not None else dist.group.WORLD
+        nst = ops.shard_stats_bytes(p, b_loc, world) // 4
+        self.stats_slots = symm_mem.empty((nst,), dtype=torch.float32, device=dev)
+        self.hstats = symm_mem.rendezvous(self.stats_slots, g)
+        self.stats_addrs = [int(self.hstats.get_buffer(r, self.stats_slots.shape, torch.float32).data_ptr())
+                            for r in range(world)]
         lo = rank * b_loc
         esz = self.z.element_size()
         self.z_row_stride = n * dim
@@ -70,9 +76,21 @@ class _SymmWorkspace:
         bases = [mc] if mc else [int(zp.data_ptr()) for zp in self.z_peers]
         self.multicast = bool(mc)
         self.dsts = [[base + (lo * n * dim + m * dim) * esz for m in range(n)] for base in bases]
+        if not mc:  # own buffer first, then the peers in a rank-staggered order (no all-to-one bursts)
+            self.dsts = self.dsts[rank:] + self.dsts[:rank]
         self.busy = False  # a forward with autograd holds the gathered operands until its backward
         self.group, self.world, self.rank, self.b_loc, self.n, self.dim = group, world, rank, b_loc, n, dim
         self._bwd = {}
+        # flag-based protocol (no barrier kernels): sync pad + statistics slots, peer-mapped
+        self.flags_ok = b_loc % 128 == 0 and b_loc <= 8192 and dim <= 512 and dim % 64 == 0
+        if self.flags_ok:
+            self.sync = symm_mem.empty((ops.shard_sync_bytes() // 4,), dtype=torch.int32, device=dev)
+            self.hsync = symm_mem.rendezvous(self.sync, g)
+            self.sync.zero_()
+            self.hsync.barrier(channel=0)  # every pad is zero before any rank signals into it
+            self.sync_addrs = [int(self.hsync.get_buffer(r, self.sync.shape, torch.int32).data_ptr()) for r in range(world)]
+            self.dsts_all = [[int(zp.data_ptr()) + (lo * n * dim + m * dim) * esz for m in range(n)] for zp in self.z_peers]
+            self.z_base_addrs = [int(zp.data_ptr()) for zp in self.z_peers]
 
     def sharded_bwd(self, pairs, need_grad):
         """(plan, local workspace, receive-buffer addresses per rank, symmetric handle) of the sharded shared-G backward.
@@ -116,6 +134,17 @@ def _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev):
     return ws
 
 
+def _flags_enabled() -> bool:
+    """TRICOLO_B200_SHARD_SYNC=barrier keeps the first version's cross-device barrier kernels (same results)."""
+    return os.environ.get("TRICOLO_B200_SHARD_SYNC", "flags") != "barrier"
+
+
+def _fused_push_enabled() -> bool:
+    """TRICOLO_B200_PUSH=k1: the normalise kernel stores the rows to the peers itself (gather before the tile kernel);
+    default: the tile kernel's push warps do it while its MMAs run."""
+    return os.environ.get("TRICOLO_B200_PUSH", "fwd") != "k1"
+
+
 def _sharded_g_enabled() -> bool:
     return os.environ.get("TRICOLO_B200_SHARDED_BWD", "sharedg") != "pc"
 
@@ -143,13 +172,60 @@ class _GlobalNTXent(torch.autograd.Function):
         # stride n*dim, so ONE gathered buffer yields every [B, dim] operand without a copy
         needs_grad = any(ctx.needs_input_grad[6:])
         ws = _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev)
+        ctx.flags = False
+        if ws is not None and ws.flags_ok and _flags_enabled():
+            # no barrier kernels: K1 stores every row into all ranks' buffers as soon as the destination is ready and
+            # flags each 128-row chunk; the tile kernel consumes column tiles in arrival order; statistics are pushed
+            # into per-source slots and the finalise kernel waits for the W flags
+            use_sg = _sharded_g_enabled() and ops.ShardedBwdPlan.supported(b_loc, dim, world)
+            fused = _fused_push_enabled()
+            inv_all, xs = ops.l2norm_fwd_push(feats, ws.dsts_all, ws.z_row_stride, rank, world, ws.sync_addrs, op_format,
+                                              remote=not fused)
+            invs = [inv_all[m] for m in range(n)]
+            z_glob3 = ws.z.view(b_glob, n, dim)
+            z_all = [z_glob3[:, m] for m in range(n)]
+            z_own = [z[row_offset:row_offset + b_loc] for z in z_all]
+            # modalities whose remote rows anyone reads: the column side of a pair (forward, G recompute, row-side
+            # gradient GEMM); the directional backward also reads the row side of every pair from all ranks
+            cols = sorted({b for _, b in pairs})
+            push_mods = cols if (use_sg or not needs_grad) else list(range(n))
+            ops.ntxent_fwd_sharded([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs], rank, world, inv_tau,
+                                   ws.stats_addrs, ws.sync_addrs, op_format, z_base_addrs=ws.z_base_addrs,
+                                   push_offsets=[m * dim for m in push_mods] if fused else ())
+            ctx.use_sg = use_sg
+            lse2_row_all, lse2_col, loss = ops.ntxent_finalize_sharded(p, b_loc, rank, world, inv_tau, alpha, ws.stats_addrs,
+                                                                       ws.sync_addrs[rank], dev)
+            if needs_grad:
+                ws.busy = True
+                ctx.symm_ws = ws
+                ctx.flags = True
+            ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
+            ctx.save_for_backward(lse2_row_all, lse2_col, ws.z, *xs, *invs)
+            return loss
         if ws is not None:
             # peer-memory transport: K1 stores every row into all ranks' buffers; barriers before (nobody still reads
             # the previous step's operands) and after (every rank's rows have landed everywhere)
             ws.hz.barrier(channel=0)
             invs, xs = ops.l2norm_fwd_bcast(feats, ws.dsts, ws.z_row_stride, op_format)
             ws.hz.barrier(channel=0)
-            z_glob = ws.z
+            z_glob3 = ws.z.view(b_glob, n, dim)
+            z_all = [z_glob3[:, m] for m in range(n)]
+            z_own = [z[row_offset:row_offset + b_loc] for z in z_all]
+            # statistics exchange: the reduce kernel writes this rank's slot (column sum-exp partials, row sum-exp and
+            # positives of its rows), ONE barrier, then the finalise kernel pulls every rank's slot over NVLink, adds
+            # the column partials in rank order (bit-identical everywhere) and finalises ALL rows - the row LSEs of all
+            # ranks are needed by the backward
+            ops.ntxent_fwd_sharded([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs], rank, world, inv_tau,
+                                   ws.stats_addrs, None, op_format)
+            ws.hstats.barrier(channel=0)
+            lse2_row_all, lse2_col, loss = ops.ntxent_finalize_sharded(p, b_loc, rank, world, inv_tau, alpha, ws.stats_addrs,
+                                                                       0, dev)
+            if needs_grad:
+                ws.busy = True
+                ctx.symm_ws = ws
+            ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
+            ctx.save_for_backward(lse2_row_all, lse2_col, ws.z, *xs, *invs)
+            return loss
         else:
             z_loc = torch.empty((b_loc, n * dim), dtype=dt, device=dev)
             z_loc3 = z_loc.view(b_loc, n, dim)
@@ -161,24 +237,16 @@ class _GlobalNTXent(torch.autograd.Function):
         z_own = [z[row_offset:row_offset + b_loc] for z in z_all]  # local rows inside the gathered buffer
         row_sum, col_sum, diag2 = ops.ntxent_fwd([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs],
                                                  row_offset, inv_tau, op_format)
-        # ONE reduction carries the column sum-exp partials and, each rank writing only its own row range of a zeroed
-        # buffer, every rank's row sums and positives: afterwards every rank finalises ALL rows itself (row LSEs of
-        # all ranks are needed by the backward when a local column block is "self"), no second exchange
-        stats = ws.stats if ws is not None else torch.empty((3, p, b_glob), dtype=torch.float32, device=dev)
+        # NCCL: ONE all-reduce carries the column sum-exp partials and, each rank writing only its own row range of a
+        # zeroed buffer, every rank's row sums and positives: afterwards every rank finalises ALL rows itself
+        stats = torch.empty((3, p, b_glob), dtype=torch.float32, device=dev)
         stats.zero_()
         stats[0].copy_(col_sum)
         stats[1, :, row_offset:row_offset + b_loc].copy_(row_sum)
         stats[2, :, row_offset:row_offset + b_loc].copy_(diag2)
-        if ws is not None:
-            ws.hs.barrier(channel=0)
-            stats = ops.peer_sum(ws.stats_peers)  # fixed rank order: identical on every rank
-        else:
-            dist.all_reduce(stats, group=group)
+        dist.all_reduce(stats, group=group)
         lse2_row_all, lse2_col, _, loss = ops.ntxent_finalize(stats[1], stats[0], stats[2], 0, inv_tau, alpha,
                                                               want_loss=True)
-        if ws is not None and needs_grad:
-            ws.busy = True
-            ctx.symm_ws = ws
         ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
         ctx.save_for_backward(lse2_row_all, lse2_col, z_glob, *xs, *invs)
         return loss
@@ -199,15 +267,19 @@ class _GlobalNTXent(torch.autograd.Function):
         grad_losses = grad_losses.contiguous()
         ws = getattr(ctx, "symm_ws", None)
         need = [bool(ctx.needs_input_grad[6 + m]) for m in range(n)]
-        if ws is not None and any(need) and _sharded_g_enabled() and ops.ShardedBwdPlan.supported(b_loc, dim, ws.world):
+        use_sg = getattr(ctx, "use_sg", _sharded_g_enabled() and ops.ShardedBwdPlan.supported(b_loc, dim, ws.world if ws else 1))
+        if ws is not None and any(need) and use_sg:
             # row block of G once per pair; column-side partials land in their owners' receive buffers over NVLink
             plan, work, addrs, hr = ws.sharded_bwd(pairs, need)
             rank = row_offset // b_loc
+            flags = getattr(ctx, "flags", False)
             ops.ntxent_bwd_sharded_gemm(plan, z_all, rank, inv_tau, alpha, lse2_row_all, lse2_col, grad_losses, work,
-                                        addrs, op_format)
-            hr.barrier(channel=0)  # every rank's partials have landed
+                                        addrs, op_format, sync_addrs=ws.sync_addrs if flags else None)
+            if not flags:
+                hr.barrier(channel=0)  # every rank's partials have landed
             inv_all = invs[0]._base if invs[0]._base is not None and invs[0]._base.shape == (n, b_loc) else torch.stack(list(invs))
-            grads = ops.ntxent_bwd_sharded_finish(plan, list(xs), inv_all, rank, work, addrs[rank])
+            grads = ops.ntxent_bwd_sharded_finish(plan, list(xs), inv_all, rank, work, addrs[rank],
+                                                  sync_own_addr=ws.sync_addrs[rank] if flags else 0)
             ws.busy = False
             return (None, None, None, None, None, None, *grads)
         zts, ld_t = ops.transpose_for_bwd(z_all)  # none for the default dim-512 kernel

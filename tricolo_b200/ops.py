@@ -83,6 +83,84 @@ def l2norm_fwd_bcast(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence], z_row
     return invs, xs
 
 
+def shard_sync_bytes() -> int:
+    return int(LIB.tcl_shard_sync_bytes())
+
+
+def shard_stats_bytes(n_pairs: int, b_loc: int, world: int) -> int:
+    return int(LIB.tcl_shard_stats_bytes(n_pairs, b_loc, world))
+
+
+def _addr_array(addrs):
+    return (C.c_void_p * len(addrs))(*[int(a) for a in addrs])
+
+
+def l2norm_fwd_push(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence], z_row_stride: int, rank: int, world: int,
+                    sync_addrs: Sequence[int], op_format: int = F16, eps: float = EPS, remote: bool = True):
+    """K1 (+ all-gather + arrival flags when remote) (tcl_l2norm_fwd_push): dsts[r][m] = address of THIS rank's first
+    row of modality m inside rank r's gathered buffer (r = 0..world-1, the own buffer included), sync_addrs[r] = rank
+    r's sync pad.  remote=False: rows go to the own buffer only; the forward tile kernel's push warps do the gather.
+    Returns (inv_norm [n, rows] fp32, xs).  No barrier: the kernel waits for each peer's "ready" flag itself."""
+    dev = L.require_cuda(*xs)
+    xs = [_rows_2d(x) for x in xs]
+    rows, dim = xs[0].shape
+    for x in xs:
+        if x.shape != xs[0].shape or x.dtype != xs[0].dtype:
+            raise ValueError("l2norm_fwd_push: all tensors must share shape and dtype")
+    if not all(x.stride(0) == xs[0].stride(0) for x in xs):
+        xs = [x.contiguous() for x in xs]
+    flat = [int(d) for per_dst in dsts for d in per_dst]
+    if len(dsts) != world or len(flat) != world * len(xs):
+        raise ValueError("l2norm_fwd_push: one destination address per (rank, modality)")
+    inv_all = torch.empty((len(xs), rows), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_l2norm_fwd_push(len(xs), L.ptr_array(xs), L.dtype_code(xs[0]), rows, dim, xs[0].stride(0), rank, world,
+                                        _addr_array(flat), z_row_stride, op_format,
+                                        L.ptr_array([inv_all[m] for m in range(len(xs))]), eps, _addr_array(sync_addrs),
+                                        1 if remote else 0, L.stream_ptr(dev)))
+    return inv_all, xs
+
+
+def ntxent_fwd_sharded(zrows: Sequence[torch.Tensor], zcols: Sequence[torch.Tensor], rank: int, world: int, inv_tau: float,
+                       stats_addrs: Sequence[int], sync_addrs: Optional[Sequence[int]], op_format: int = F16,
+                       z_base_addrs: Optional[Sequence[int]] = None, push_offsets: Sequence[int] = ()) -> None:
+    """K2 on the local row block, column tiles gated on the arrival flags, then this rank's sum-exp statistics stored
+    into every rank's statistics buffer (+ flag).  push_offsets (element offsets of modalities inside a gathered row)
+    + z_base_addrs (every rank's gathered buffer): the all-gather of those modalities is fused into the kernel (push
+    warps).  Results: ntxent_finalize_sharded."""
+    dev = L.require_cuda(*zrows, *zcols)
+    p = len(zrows)
+    b_loc, dim = zrows[0].shape
+    b_glob = zcols[0].shape[0]
+    diag2 = torch.empty((p, b_loc), dtype=torch.float32, device=dev)
+    ws_bytes = LIB.tcl_ntxent_fwd_workspace_bytes(p, b_loc, b_glob)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_ntxent_fwd_sharded(p, L.ptr_array(list(zrows)), L.ptr_array(list(zcols)), b_loc, b_glob, dim,
+                                           _z_stride(list(zrows) + list(zcols)), rank, world, op_format, inv_tau,
+                                           L.ptr(diag2), L.ptr(ws), ws_bytes, _addr_array(stats_addrs),
+                                           None if sync_addrs is None else _addr_array(sync_addrs),
+                                           None if not push_offsets else _addr_array(z_base_addrs), len(push_offsets),
+                                           (C.c_int64 * max(len(push_offsets), 1))(*[int(o) for o in push_offsets]),
+                                           L.stream_ptr(dev)))
+
+
+def ntxent_finalize_sharded(n_pairs: int, b_loc: int, rank: int, world: int, inv_tau: float, alpha: float,
+                            stats_addrs: Sequence[int], sync_own_addr: int, device):
+    """lse2_row [P, B], lse2_col [P, B], loss [P] of the global batch.  sync_own_addr != 0: waits on the device for every
+    rank's statistics flag (they were pushed into this rank's buffer); 0: pulls slot s from rank s's buffer
+    (stats_addrs[s]) - the caller ran a barrier after ntxent_fwd_sharded."""
+    b_glob = b_loc * world
+    lse2_row = torch.empty((n_pairs, b_glob), dtype=torch.float32, device=device)
+    lse2_col = torch.empty((n_pairs, b_glob), dtype=torch.float32, device=device)
+    loss = torch.empty((n_pairs,), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        L.check(LIB.tcl_ntxent_finalize_sharded(n_pairs, b_loc, b_glob, rank, world, inv_tau, alpha, _addr_array(stats_addrs),
+                                                C.c_void_p(int(sync_own_addr)), L.ptr(lse2_row), L.ptr(lse2_col), L.ptr(loss),
+                                                L.stream_ptr(device)))
+    return lse2_row, lse2_col, loss
+
+
 def peer_sum(srcs: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = srcs[0] + srcs[1] + ... in that order (fp32, same shape): one-shot all-reduce over peer-mapped buffers."""
     dev = L.require_cuda(srcs[0])
@@ -266,7 +344,8 @@ class ShardedBwdPlan:
 
 def ntxent_bwd_sharded_gemm(plan: ShardedBwdPlan, z_all: Sequence[torch.Tensor], rank: int, inv_tau: float, alpha: float,
                             lse2_row: torch.Tensor, lse2_col: torch.Tensor, grad_losses: torch.Tensor,
-                            workspace: torch.Tensor, recv_addrs: Sequence[int], op_format: int = F16) -> None:
+                            workspace: torch.Tensor, recv_addrs: Sequence[int], op_format: int = F16,
+                            sync_addrs: Optional[Sequence[int]] = None) -> None:
     """Kernel A (row block of G per pair) + kernel B (row-side gradients into local partials, column-side partials
     stored into every owner's receive buffer, recv_addrs[r] = device address of rank r's buffer as mapped here)."""
     dev = L.require_cuda(*z_all, lse2_row, lse2_col, grad_losses, workspace)
@@ -280,13 +359,16 @@ def ntxent_bwd_sharded_gemm(plan: ShardedBwdPlan, z_all: Sequence[torch.Tensor],
                                                 _z_stride(list(z_all)), rank, plan.world, len(plan.pairs), plan.pair_row,
                                                 plan.pair_col, op_format, inv_tau, alpha, L.ptr(lse2_row), L.ptr(lse2_col),
                                                 L.ptr(grad_losses), plan.need, L.ptr(workspace), workspace.numel(), recv,
-                                                plan.recv_bytes, L.stream_ptr(dev)))
+                                                plan.recv_bytes, None if sync_addrs is None else _addr_array(sync_addrs),
+                                                L.stream_ptr(dev)))
 
 
 def ntxent_bwd_sharded_finish(plan: ShardedBwdPlan, xs: Sequence[torch.Tensor], invs: torch.Tensor, rank: int,
-                              workspace: torch.Tensor, recv_own_addr: int, eps: float = EPS) -> List[Optional[torch.Tensor]]:
+                              workspace: torch.Tensor, recv_own_addr: int, eps: float = EPS,
+                              sync_own_addr: int = 0) -> List[Optional[torch.Tensor]]:
     """Sum of the local and received gradient partials + normalise backward.  Returns dx per tensor (None where no
-    gradient was requested).  The caller has made sure every rank's gemm call completed (cross-rank barrier)."""
+    gradient was requested).  Every rank's gemm call must have completed: either the caller ran a cross-rank barrier,
+    or both calls were given the sync pads (sync_own_addr: the kernel waits for the ranks' flags itself)."""
     dev = L.require_cuda(*xs, invs, workspace)
     x0 = xs[0]
     if any(x.shape != x0.shape or x.dtype != x0.dtype or x.stride(0) != x0.stride(0) or x.stride(1) != 1 for x in xs):
@@ -299,7 +381,8 @@ def ntxent_bwd_sharded_finish(plan: ShardedBwdPlan, xs: Sequence[torch.Tensor], 
         L.check(LIB.tcl_ntxent_bwd_sharded_finish(plan.n_tensors, L.ptr_array(list(xs)), L.dtype_code(x0), plan.b_loc,
                                                   plan.b_glob, plan.dim, x0.stride(0), rank, plan.world, len(plan.pairs),
                                                   plan.pair_row, plan.pair_col, L.ptr(invs), plan.need, eps, L.ptr(workspace),
-                                                  C.c_void_p(int(recv_own_addr)), dx_arr, L.stream_ptr(dev)))
+                                                  C.c_void_p(int(recv_own_addr)), C.c_void_p(int(sync_own_addr)), dx_arr,
+                                                  L.stream_ptr(dev)))
     return dxs
 
 
