@@ -2,16 +2,22 @@
 """Benchmark of the TriCoLo embedding-similarity hot path on B200 (contract: task spec, "bench.py").
 
     python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU port of the reference path
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference path on the host cores
     torchrun-style launch for N > 1 (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env).
 
-Workload (config.workload = "c4"): BASELINE.json configs[3] — global-negative trimodal InfoNCE, global
+Workload (config.workload = "c4"): BASELINE.json configs[3] - global-negative trimodal InfoNCE, global
 batch 8192, dim 512, tau 0.1, alpha 0.25, forward + backward, STRONG scaling: the global batch is fixed and
 each of the N ranks owns B/N rows (at N=1 the whole problem runs on one GPU).  metric = pairs/s =
-global batch / time of one fwd+bwd of the whole three-term loss.  A secondary object "retrieval" reports
-configs[4]-shaped sharded top-5 retrieval (queries/s); "small_batch" reports configs[1] (B=256) latency.
+global batch / time of one fwd+bwd of the whole three-term loss.
 
-One JSON line on stdout (rank 0).  Nothing here reads /root/reference.
+One JSON line on stdout (rank 0).  Beside the contract's keys it carries
+    parity       loss / gradients of THIS run's inputs against the committed golden output of the unmodified reference
+                 (tests/golden/large_outputs.json), retrieval against its own unsharded / two-kernel form; computed
+                 outside the timed region; the run exits non-zero above rtol 1e-3 or on any index mismatch
+    retrieval    configs[4] (1M queries x 200k shapes sharded over the ranks) and configs[2] (7424 x 1486), with its
+                 own roofline, e2e (host arrays -> metrics dict on the host) and cpu_baseline
+    small_batch  configs[0] / configs[1] (B = 128 bimodal, B = 256 trimodal) latency, eager PyTorch on the GPU beside it
+Nothing here reads /root/reference at run time on the GPU box (the reference arm uses it only where it exists).
 """
 from __future__ import annotations
 
@@ -40,6 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="override the global batch")
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small-batch", action="store_true")
     ap.add_argument("--retrieval-queries", type=int, default=1_000_000)
     ap.add_argument("--retrieval-gallery", type=int, default=200_000)
     ap.add_argument("--op-format", default="f16", choices=["f16", "bf16"])
@@ -56,10 +63,17 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
 
 
+def shared_config(workload, batch):
+    """The keys both arms (ours / reference) must agree on."""
+    name = ("c4: global-negative trimodal InfoNCE fwd+bwd (BASELINE configs[3])" if workload == "c4"
+            else "c2: Tri(I+V) trimodal loss fwd+bwd, batch 256 (BASELINE configs[1])")
+    return {"workload": name, "global_batch": batch, "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA, "pairs": 3}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.004):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period_s, [], set(), None
         self._stop_evt = threading.Event()
@@ -117,55 +131,68 @@ def make_features(batch, rows, row0, seed=7, device="cpu", dtype=None):
     return out
 
 
+def reference_loss_step():
+    """(step(feature dict) -> float, kind): the reference's own TriCoLoNet._calculate_losses + autograd when the
+    reference is importable here (build container), else the oracle's PyTorch port of the same ops."""
+    from oracle import ntxent_oracle as NO
+    from oracle import reference_shim as RS
+
+    fn = RS.trimodal_loss_fn(TAU, ALPHA)
+    kind = "reference" if fn is not None else "port"
+    if fn is None:
+        fn = lambda fd: NO.torch_trimodal(fd, TAU, ALPHA)  # noqa: E731
+
+    def step(fd):
+        fd = {k: v.clone().requires_grad_(True) for k, v in fd.items()}
+        out = fn(fd)
+        out["train_loss/total_loss"].backward()
+        return float(out["train_loss/total_loss"].detach())
+
+    return step, kind
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
-    """CPU port of the reference path (oracle.torch_trimodal = the same PyTorch ops as nt_xent.py, autograd
-    backward) on the host cores; rank 0 only."""
+    """The reference path on the host cores (rank 0 only): the unmodified reference where it is importable, else the
+    oracle's port of the same PyTorch ops; the full workload per step (same at every N)."""
     if rank != 0:
         return
     import torch
 
-    from oracle import ntxent_oracle as NO
-
     batch = args.batch or (8192 if args.workload == "c4" else 256)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    step, kind = reference_loss_step()
     feats = make_features(batch, batch, 0)
-
-    def step(fd):
-        fd = {k: v.clone().requires_grad_(True) for k, v in fd.items()}
-        out = NO.torch_trimodal(fd, TAU, ALPHA)
-        out["train_loss/total_loss"].backward()
-        return float(out["train_loss/total_loss"])
-
-    # probe once; if a full-size step is too slow, time a bounded sample: a smaller global batch
     t0 = time.perf_counter()
     step(feats)
     probe = time.perf_counter() - t0
+    steps, warm = args.steps, max(args.warmup - 1, 0)
     sample_batch = batch
+    # bound the run to a few minutes: fewer steps first, a quadratic-cost sub-batch only if ONE step is too slow
     budget_s = 150.0
-    while probe * (sample_batch / batch) ** 2 * (args.steps + args.warmup) > budget_s and sample_batch > 1024:
+    if probe * (steps + warm) > budget_s:
+        steps, warm = max(3, int(budget_s / probe) - 1), 1
+    while probe * (sample_batch / batch) ** 2 * (steps + warm) > budget_s and sample_batch > 1024:
         sample_batch //= 2
     if sample_batch != batch:
         feats = make_features(sample_batch, sample_batch, 0)
-    for _ in range(max(args.warmup - 1, 1)):
+    for _ in range(warm):
         step(feats)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(feats)
-    dt = (time.perf_counter() - t0) / args.steps
-    # cost is quadratic in the batch: a full-size step costs (batch/sample)^2 sample steps
+    dt = (time.perf_counter() - t0) / steps
     full_step = dt * (batch / sample_batch) ** 2
     value = batch / full_step
-    sample = (f"full workload per step (B={batch}, 3 pair terms, fwd+bwd, fp32)" if sample_batch == batch else
-              f"B={sample_batch} sub-batch per step, extrapolated x{(batch // sample_batch) ** 2} (cost is quadratic in B)")
+    sample = (f"{steps} full-workload steps (B={batch}, 3 pair terms, fwd+bwd, fp32, {cores} threads)" if sample_batch == batch else
+              f"{steps} steps of a B={sample_batch} sub-batch, extrapolated x{(batch // sample_batch) ** 2} (cost is quadratic in B)")
     line = {
         "impl": "reference", "metric": "infonce_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd", "global_batch": batch,
-                   "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA, "pairs": 3},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": shared_config(args.workload, batch),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -237,9 +264,9 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---------------- main timed region: K steps, kernel events + clocks sampled meanwhile
-    # The step is captured once in a CUDA graph and replayed (same kernels, same NCCL collectives, no host work
-    # between launches); the eager number is reported next to it.  The per-kernel event profile is taken on
-    # eager steps (events recorded inside a capture would be baked into the graph).
+    # The step is captured once in a CUDA graph and replayed (same kernels, same collectives, no host work between
+    # launches); the eager number is reported next to it.  The per-kernel event profile is taken on eager steps
+    # (events recorded inside a capture would be baked into the graph).
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step(feats)
@@ -271,6 +298,9 @@ def run_ours(args, rank, world, local_rank):
         ms_per_step, launch_mode = eager_ms, "eager"
     value = batch / (ms_per_step * 1e-3)
 
+    # ---------------- parity of THIS run's inputs (outside the timed region)
+    parity = loss_parity(args, rank, world, dev, batch, b_loc, row0, feats, step, dist)
+
     # ---------------- per-kernel numbers and the roofline of the dominant kernel
     pairs = 3
     flops_fwd = 2.0 * b_loc * batch * DIM * pairs           # one similarity GEMM per pair
@@ -278,137 +308,67 @@ def run_ours(args, rank, world, local_rank):
     kern = {}
     for name, (ms, n) in prof.items():
         kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / args.steps}
+
     def tf(flops, name):
         return flops / (kern[name]["ms_per_launch"] * 1e-3) / 1e12 if name in kern else None
+
     bytes_l2n = 3 * (b_loc * DIM * 4 + b_loc * DIM * 2 + b_loc * 4)
     if "ntxent_fwd" in kern:
         kern["ntxent_fwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_fwd, "ntxent_fwd")})
+    bwd_mode = "sharedg" if "ntxent_g" in kern else (os.environ.get("TRICOLO_B200_BWD") or "pc")
     if "ntxent_bwd" in kern:
-        # executed flop of the gradient kernel per algorithmic flop: the producer/consumer and pair kernels recompute
-        # the logits once per direction (2x), the independent-CTA kernel once per dim half (3x)
-        # the shared-G form (one GPU, >= 2048 rows) forms the logits once per pair (1.5x), the producer/consumer
-        # kernel once per direction (2x), the independent-CTA kernel once per dim half (3x)
-        bwd_mode = os.environ.get("TRICOLO_B200_BWD") or ("sharedg" if (world == 1 and batch >= 2048) else "pc")
-        exec_factor = {"indep": 3.0, "sharedg": 1.5}.get(bwd_mode, 2.0)
-        if os.environ.get("TRICOLO_B200_BWD_NOPAIR"):
-            exec_factor = 3.0
-        if bwd_mode == "sharedg" and "ntxent_g" in kern:
-            # two kernels: ntxent_g (logit recompute -> 16-bit G, 2 B^2 D per pair, not algorithmic) and the gradient
-            # GEMMs ntxent_ggemm (event id ntxent_bwd: exactly the algorithmic 4 B^2 D per pair)
+        if bwd_mode == "sharedg":
+            # two kernels: ntxent_g (logit recompute -> 16-bit G, 2 b B D per pair, executed but not algorithmic) and the
+            # gradient GEMMs ntxent_ggemm (event id ntxent_bwd: exactly the algorithmic 4 b B D per pair)
             kern["ntxent_g"].update({"bound": "tensor", "executed_tflops": tf(flops_fwd, "ntxent_g"),
                                      "note": "logit recompute for the backward: executed, not algorithmic"})
             kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
                                        "executed_tflops": tf(flops_bwd, "ntxent_bwd"), "mode": bwd_mode,
                                        "kernel": "ntxent_ggemm_kernel"})
         else:
+            # the producer/consumer kernel recomputes the logits once per direction (2x), the independent-CTA kernel
+            # once per dim half (3x)
+            exec_factor = 3.0 if bwd_mode == "indep" else 2.0
             kern["ntxent_bwd"].update({"bound": "tensor", "algorithmic_tflops": tf(flops_bwd, "ntxent_bwd"),
                                        "executed_tflops": tf(flops_bwd * exec_factor, "ntxent_bwd"), "mode": bwd_mode})
     if "l2norm_fwd" in kern:
-        kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9})
-    peak_tf = peaks["tf_sustained"]
-    bwd_is_sharedg = kern.get("ntxent_bwd", {}).get("mode") == "sharedg"
+        kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm_gbs"]})
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
-    traffic = None
-    try:  # DRAM bytes per launch of the same kernel at the same shapes, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1h_traffic.json")) as f:
+    bwd_kernel = "ntxent_ggemm_kernel" if bwd_mode == "sharedg" else "ntxent_bwd_pc_kernel"
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of the same kernel at the same shapes, from the newest committed ncu capture
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+        with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
             tj = json.load(f)
-            traffic = tj.get("ntxent_ggemm_kernel") if bwd_is_sharedg else tj.get("ntxent_bwd_pc_kernel")
-            if not (world == 1 and batch == 8192):
-                traffic = None
+        if world == 1 and batch == 8192:
+            traffic, traffic_src = tj.get(bwd_kernel), f"profiles/{cands[-1]} (ncu --set full capture of this kernel at these shapes; not re-measured in this run)"
     except Exception:
         traffic = None
-    bwd_kernel = "ntxent_ggemm_kernel" if bwd_is_sharedg else "ntxent_bwd_pc_kernel"
-    roofline = {"kernel": bwd_kernel, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (ach / peak_tf) if ach else None, "traffic": traffic,
-                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+    step_flops = flops_fwd + flops_bwd
+    step_tf = step_flops / (ms_per_step * 1e-3) / 1e12
+    roofline = {"kernel": bwd_kernel, "bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": (ach / peaks["tf_burst"]) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"{peaks['source']} bf16_tflops (burst: the kernel is event-timed alone, L2 flushed, a few ms of load)",
+                "frac_of_sustained_peak": (ach / peaks["tf_sustained"]) if ach else None, "peak_sustained": peaks["tf_sustained"],
                 "algorithmic_flops_per_launch": flops_bwd,
-                "whole_step": {"algorithmic_flops": flops_fwd + flops_bwd,
-                               "achieved": (flops_fwd + flops_bwd) / (ms_per_step * 1e-3) / 1e12,
-                               "frac": (flops_fwd + flops_bwd) / (ms_per_step * 1e-3) / 1e12 / peak_tf}}
+                "whole_step": {"algorithmic_flops": step_flops, "achieved": step_tf, "frac": step_tf / peaks["tf_burst"],
+                               "frac_of_sustained_peak": step_tf / peaks["tf_sustained"]}}
 
     # ---------------- e2e: host buffers in, loss + gradients back to the host, every step
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    out_host = [torch.empty((b_loc, DIM), dtype=torch.float32).pin_memory() for _ in FEATURE_KEYS]
-    loss_host = torch.empty((3,), dtype=torch.float32).pin_memory()
-    d2h = sum(t.numel() * 4 for t in out_host) + 12
+    e2e = bench_e2e(args, world, dev, op, host, b_loc, batch, loss_fn, timed, max_over_ranks, barrier)
 
-    def e2e_step():
-        fs = [host[k].to(dev, non_blocking=True).requires_grad_(True) for k in FEATURE_KEYS]
-        losses = loss_fn(fs)
-        losses.sum().backward()
-        loss_host.copy_(losses.detach(), non_blocking=True)
-        for o, f in zip(out_host, fs):
-            o.copy_(f.grad, non_blocking=True)
-
-    e2e_times = timed(e2e_step, args.steps, max(3, args.warmup))
-    seq_ms = max_over_ranks(sum(e2e_times)) / args.steps
-    e2e = {"value": batch / (seq_ms * 1e-3), "unit": "pairs/s", "ms_per_step": seq_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "tricolo_b200.loss.trimodal_ntxent(...).sum().backward() on pinned host fp32 embeddings"}
-    # The same work through the pipelined public entry: every step still copies its own inputs from pinned host memory
-    # and its own losses + gradients back; the H2D of step k+1, the loss graph of step k and the D2H of step k-1 overlap.
-    try:
-        from tricolo_b200.graphs import HostPipelinedLoss
-
-        depth = 3
-        pipe = HostPipelinedLoss([host[k] for k in FEATURE_KEYS], TAU, ALPHA, depth=depth, distributed=world > 1,
-                                 op_format=op)
-        feats_h = [host[k] for k in FEATURE_KEYS]
-        for _ in range(max(3, args.warmup)):
-            pipe.result(pipe.submit(feats_h))
-        torch.cuda.synchronize(dev)
-        barrier()
-        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_a.record(pipe.s_h2d)
-        tickets = []
-        for k in range(args.steps):
-            tickets.append(pipe.submit(feats_h))
-            if k >= depth - 1:
-                pipe.result(tickets[k - (depth - 1)])
-        for t in tickets[-(depth - 1):]:
-            pipe.result(t)
-        e_b.record(pipe.s_d2h)
-        torch.cuda.synchronize(dev)
-        barrier()
-        pipe_ms = max_over_ranks(e_a.elapsed_time(e_b)) / args.steps
-        e2e.update({"value": batch / (pipe_ms * 1e-3), "ms_per_step": pipe_ms, "sequential_ms_per_step": seq_ms,
-                    "sequential_value": batch / (seq_ms * 1e-3),
-                    "api": "tricolo_b200.graphs.HostPipelinedLoss.submit/result on pinned host fp32 embeddings "
-                           f"(depth {depth}: H2D, loss graph and D2H of consecutive steps overlap; K steps timed from the "
-                           "first H2D to the last D2H); sequential_* = trimodal_ntxent(...).sum().backward() one step at a time"})
-    except Exception as ex:  # report, never hide
-        e2e["pipelined_error"] = repr(ex)[:200]
-
-    # ---------------- secondary: small batch (configs[1]) latency
+    # ---------------- secondary: small batches (configs[0], configs[1]) latency, eager PyTorch on this GPU beside them
     small = None
-    if world == 1 and args.workload == "c4":
-        sf = [x.to(dev).requires_grad_(True) for x in make_features(256, 256, 0, seed=1234).values()]
-        st = timed(lambda: step(sf), 50, 10)
-        small = {"workload": "c2: trimodal B=256 fwd+bwd", "ms_per_step": statistics.median(st),
-                 "pairs_per_s": 256 / (statistics.median(st) * 1e-3)}
-        # the same step captured once in a CUDA graph (what a launch-bound training loop would replay)
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step(sf)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            for f in sf:
-                f.grad = None
-            with torch.cuda.graph(graph):
-                trimodal_ntxent(sf, TAU, ALPHA, op_format=op).sum().backward()
-            gt = timed(graph.replay, 50, 10)
-            small["graph_ms_per_step"] = statistics.median(gt)
-            small["graph_pairs_per_s"] = 256 / (statistics.median(gt) * 1e-3)
-        except Exception as e:  # report, never hide
-            small["graph_error"] = repr(e)[:200]
+    if world == 1 and args.workload == "c4" and not args.no_small_batch:
+        small = bench_small_batches(dev, op, timed, trimodal_ntxent)
 
-    # ---------------- secondary: sharded retrieval (configs[4]-shaped)
+    # ---------------- secondary: retrieval (configs[4] sharded over the ranks; configs[2] at N=1)
     retrieval = None
     if not args.no_retrieval:
         retrieval = bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrieve, sharded_retrieve, _lib)
+        if retrieval.get("parity"):
+            parity.update(retrieval.pop("parity"))
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -421,62 +381,294 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:
             cpu["torch_eager_on_gpu"] = {"error": repr(ex)[:200]}
 
+    ok = bool(parity.get("ok", True) and parity.get("ok_retrieval", True))
     if rank == 0:
+        cfg = shared_config(args.workload, batch)
+        cfg.update({"rows_per_rank": b_loc, "accumulate": "f32", "l2": "flushed (256 MB write) before every timed step",
+                    "launch": launch_mode, "eager_ms_per_step": eager_ms, "parallelism": f"row-block x{world}",
+                    "backward": bwd_mode})
         line = {
             "metric": "infonce_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if op == ops.F16 else "bf16", "data": "synthetic",
-            "config": {"workload": (f"{args.workload}: global-negative trimodal InfoNCE fwd+bwd (BASELINE configs[3])" if args.workload == "c4"
-                                    else f"{args.workload}: Tri(I+V) trimodal loss fwd+bwd, batch 256 (BASELINE configs[1])"),
-                       "global_batch": batch, "rows_per_rank": b_loc, "dim": DIM, "temperature": TAU, "alpha_weight": ALPHA,
-                       "pairs": 3, "accumulate": "f32", "l2": "flushed (256 MB write) before every timed step",
-                       "launch": launch_mode, "eager_ms_per_step": eager_ms,
-                       "parallelism": f"row-block x{world}"},
-            "roofline": roofline, "kernels": kern, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "cpu_baseline": cpu, "small_batch": small, "retrieval": retrieval,
+            "config": cfg, "roofline": roofline, "kernels": kern, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "parity": parity, "cpu_baseline": cpu, "small_batch": small, "retrieval": retrieval,
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)
+    return ok
+
+
+def loss_parity(args, rank, world, dev, batch, b_loc, row0, feats, step, dist):
+    """Loss and gradients of one more (untimed) step against the golden output of the UNMODIFIED reference on the very
+    same inputs (tests/golden/make_golden_large.py: B = 8192, seed 7, 3 losses + every 64th gradient row).  Every rank
+    contributes its rows; rtol 1e-3 (north_star).  Other batch sizes: checked against the oracle's fp64 closed form on
+    rank 0 when the whole batch is small enough to recompute in seconds."""
+    import numpy as np
+    import torch
+
+    out = {"tolerance": 1e-3, "ok": True}
+    losses = step(feats).detach().double().cpu().numpy()
+    names = ["train_loss/text_image_loss", "train_loss/text_voxel_loss", "train_loss/image_voxel_loss"]
+    try:
+        if args.workload == "c4" and batch == 8192:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "large_outputs.json")))["c4"]
+            gg = np.load(os.path.join(ROOT, "tests", "golden", "c4_grads.npz"))
+            ref_losses = np.array([gold["losses"][n] for n in names])
+            rows = np.arange(0, batch, gold["row_stride"])
+            mine = rows[(rows >= row0) & (rows < row0 + b_loc)]
+            num = torch.zeros(3, dtype=torch.float64, device=dev)
+            den = torch.zeros(3, dtype=torch.float64, device=dev)
+            for m, k in enumerate(FEATURE_KEYS):
+                ref = torch.from_numpy(gg[k][mine // gold["row_stride"]]).to(dev).double()
+                got = feats[m].grad[torch.from_numpy(mine - row0).to(dev)].double()
+                num[m], den[m] = ((got - ref) ** 2).sum(), (ref ** 2).sum()
+            if world > 1:
+                dist.all_reduce(num)
+                dist.all_reduce(den)
+            out.update({"against": "golden output of the unmodified reference (tests/golden/large_outputs.json: c4)",
+                        "grad_rows_checked": int(len(rows))})
+            out["grad_rel_err"] = float((num / den).sqrt().max())
+        elif batch <= 2048 and world == 1:
+            from oracle import ntxent_oracle as NO
+
+            ref_l, ref_g = NO.trimodal_forward_backward({k: f.detach().cpu().numpy() for k, f in zip(FEATURE_KEYS, feats)}, TAU, ALPHA)
+            ref_losses = np.array([ref_l[n] for n in names])
+            out["against"] = "oracle fp64 closed form (oracle/ntxent_oracle.py)"
+            out["grad_rel_err"] = max(float(np.linalg.norm(f.grad.double().cpu().numpy() - ref_g[k]) / np.linalg.norm(ref_g[k]))
+                                      for k, f in zip(FEATURE_KEYS, feats))
+        else:
+            return {"ok": True, "skipped": f"no golden for batch {batch} / workload {args.workload}"}
+        out["loss_rel_err"] = float(np.max(np.abs(losses - ref_losses) / np.abs(ref_losses)))
+        out["ok"] = bool(out["loss_rel_err"] <= 1e-3 and out["grad_rel_err"] <= 1e-3)
+    except Exception as ex:  # a missing golden is reported, not hidden
+        out.update({"ok": False, "error": repr(ex)[:200]})
+    return out
+
+
+def bench_e2e(args, world, dev, op, host, b_loc, batch, loss_fn, timed, max_over_ranks, barrier):
+    """Host buffers in, losses + gradients back on the host, every step.  Headline: the pipelined public entry on
+    pinned bf16 host embeddings (north_star: "bf16 inputs"; gradients come back in the inputs' dtype, as autograd
+    would return them); the fp32-host and one-step-at-a-time numbers are reported beside it."""
+    import torch
+
+    out = {}
+
+    def seq(dtype):
+        hs = [host[k].to(dtype).pin_memory() for k in FEATURE_KEYS]
+        out_host = [torch.empty((b_loc, DIM), dtype=dtype).pin_memory() for _ in FEATURE_KEYS]
+        loss_host = torch.empty((3,), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            fs = [h.to(dev, non_blocking=True).requires_grad_(True) for h in hs]
+            losses = loss_fn(fs)
+            losses.sum().backward()
+            loss_host.copy_(losses.detach(), non_blocking=True)
+            for o, f in zip(out_host, fs):
+                o.copy_(f.grad, non_blocking=True)
+
+        t = timed(e2e_step, args.steps, max(3, args.warmup))
+        return max_over_ranks(sum(t)) / args.steps
+
+    def pipelined(dtype, depth=3):
+        from tricolo_b200.graphs import HostPipelinedLoss
+
+        hs = [host[k].to(dtype).pin_memory() for k in FEATURE_KEYS]
+        pipe = HostPipelinedLoss(hs, TAU, ALPHA, depth=depth, distributed=world > 1, op_format=op)
+        for _ in range(max(3, args.warmup)):
+            pipe.result(pipe.submit(hs))
+        torch.cuda.synchronize(dev)
+        barrier()
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record(pipe.s_h2d)
+        tickets = []
+        for k in range(args.steps):
+            tickets.append(pipe.submit(hs))
+            if k >= depth - 1:
+                pipe.result(tickets[k - (depth - 1)])
+        for t in tickets[-(depth - 1):]:
+            pipe.result(t)
+        e_b.record(pipe.s_d2h)
+        torch.cuda.synchronize(dev)
+        barrier()
+        return max_over_ranks(e_a.elapsed_time(e_b)) / args.steps
+
+    variants = {}
+    for name, dtype in (("bf16_host", torch.bfloat16), ("fp32_host", torch.float32)):
+        v = {"h2d_bytes_per_step": 3 * b_loc * DIM * (2 if dtype == torch.bfloat16 else 4),
+             "d2h_bytes_per_step": 3 * b_loc * DIM * (2 if dtype == torch.bfloat16 else 4) + 12}
+        try:
+            ms = pipelined(dtype)
+            v.update({"value": batch / (ms * 1e-3), "ms_per_step": ms})
+        except Exception as ex:  # report, never hide
+            v["pipelined_error"] = repr(ex)[:200]
+        try:
+            sms = seq(dtype)
+            v.update({"sequential_ms_per_step": sms, "sequential_value": batch / (sms * 1e-3)})
+            if "value" not in v:
+                v.update({"value": batch / (sms * 1e-3), "ms_per_step": sms})
+        except Exception as ex:
+            v["sequential_error"] = repr(ex)[:200]
+        variants[name] = v
+    head = variants["bf16_host"] if "value" in variants["bf16_host"] else variants["fp32_host"]
+    out.update({"value": head.get("value"), "unit": "pairs/s", "ms_per_step": head.get("ms_per_step"),
+                "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": head["d2h_bytes_per_step"],
+                "api": "tricolo_b200.graphs.HostPipelinedLoss.submit/result on pinned bf16 host embeddings (north_star: bf16 inputs; "
+                       "losses fp32, gradients in the inputs' dtype; depth 3: H2D, loss graph and D2H of consecutive steps overlap; "
+                       "K steps timed from the first H2D to the last D2H); variants: the same with fp32 host buffers, and "
+                       "sequential_* = trimodal_ntxent(...).sum().backward() one step at a time",
+                "variants": variants})
+    return out
+
+
+def bench_small_batches(dev, op, timed, trimodal_ntxent):
+    """configs[0] (Bi(V), B = 128) and configs[1] (Tri(I+V), B = 256): latency of one fwd+bwd, eager and as a CUDA graph,
+    with the reference's PyTorch ops run eagerly on the same GPU beside them (the regime the reference trains in,
+    config/data/base.yaml:5)."""
+    import torch
+
+    from oracle import ntxent_oracle as NO
+
+    out = {}
+    for name, b, keys in (("c1: Bi(V) B=128 fwd+bwd", 128, ("text_features", "voxel_features")),
+                          ("c2: Tri(I+V) B=256 fwd+bwd", 256, FEATURE_KEYS)):
+        g = torch.Generator().manual_seed(1234)
+        sf = [torch.randn(b, DIM, generator=g).to(dev).requires_grad_(True) for _ in keys]
+
+        def ours():
+            for f in sf:
+                f.grad = None
+            trimodal_ntxent(sf, TAU, ALPHA, op_format=op).sum().backward()
+
+        def ref():
+            fd = {k: f.detach().clone().requires_grad_(True) for k, f in zip(keys, sf)}
+            NO.torch_trimodal(fd, TAU, ALPHA)["train_loss/total_loss"].backward()
+
+        st = statistics.median(timed(ours, 50, 10))
+        rt = statistics.median(timed(ref, 50, 10))
+        rec = {"ms_per_step": st, "pairs_per_s": b / (st * 1e-3),
+               "torch_eager_reference_ops_ms_per_step": rt, "speedup_vs_torch_eager_on_gpu": rt / st}
+        try:  # the same step captured once in a CUDA graph (what a launch-bound training loop would replay)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    ours()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            for f in sf:
+                f.grad = None
+            with torch.cuda.graph(graph):
+                trimodal_ntxent(sf, TAU, ALPHA, op_format=op).sum().backward()
+            gt = statistics.median(timed(graph.replay, 50, 10))
+            rec.update({"graph_ms_per_step": gt, "graph_pairs_per_s": b / (gt * 1e-3), "graph_speedup_vs_torch_eager_on_gpu": rt / gt})
+        except Exception as e:  # report, never hide
+            rec["graph_error"] = repr(e)[:200]
+        out[name] = rec
+    return out
+
+
+def make_retrieval_inputs(n_q, n_g, g_lo, g_hi, dev, seed=0, noise=10.5, chunk=131072):
+    """SURVEY.md §8d C3/C5 recipe on the device: unit-norm Gaussian gallery of n_g shapes (this rank keeps rows
+    [g_lo, g_hi)), every query = normalise(shape[owner] + noise * N(0, I) / sqrt(D)) with owners drawn uniformly; bf16.
+    The same seeds on every rank, so queries and labels are identical everywhere."""
+    import torch
+
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    gal = torch.randn(n_g, DIM, generator=gen, device=dev)
+    gal /= gal.norm(dim=1, keepdim=True)
+    owner = torch.randint(0, n_g, (n_q,), generator=gen, device=dev)
+    text = torch.empty((n_q, DIM), dtype=torch.bfloat16, device=dev)
+    for s in range(0, n_q, chunk):
+        e = min(s + chunk, n_q)
+        t = gal[owner[s:e]] + noise * torch.randn(e - s, DIM, generator=gen, device=dev) / DIM ** 0.5
+        text[s:e] = (t / t.norm(dim=1, keepdim=True)).bfloat16()
+    return text, gal.bfloat16()[g_lo:g_hi].contiguous(), owner, gal.bfloat16()
 
 
 def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrieve, sharded_retrieve, _lib):
-    """configs[4]: Q queries against a gallery of G shapes sharded over the ranks, top-5 + rank.
+    """configs[4]: Q queries against a gallery of G shapes sharded over the ranks, top-5 + rank -> RR@k / NDCG@5 / MRR.
     Headline = the fused kernel (similarities stay on chip, tensor-bound).  The two-kernel form the north star
     describes (GEMM -> fp32 block in HBM -> top-k kernel) is timed on a slice of the same queries so that the
-    top-k kernel's HBM fraction and the GEMM's numbers stay on record."""
+    top-k kernel's HBM fraction and the GEMM's numbers stay on record.  At N=1 also configs[2] (7424 x 1486)."""
+    import numpy as np
     import torch
+
+    from tricolo_b200.evaluation import metrics_from_ranks
 
     n_q, n_g = args.retrieval_queries, args.retrieval_gallery
     g_loc = n_g // world
     base = rank * g_loc
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    gal = torch.randn(g_loc, DIM, generator=gen, device=dev).bfloat16()
-    genq = torch.Generator(device=dev).manual_seed(99)  # same queries / labels on every rank
-    text = torch.randn(n_q, DIM, generator=genq, device=dev).bfloat16()
-    labels = torch.randint(0, n_g, (n_q,), generator=genq, device=dev)
+    text, gal, labels, gal_full = make_retrieval_inputs(n_q, n_g, base, base + g_loc, dev)
 
     def run(fused, nq, block=None):
         if world > 1:
             return sharded_retrieve(text[:nq], gal, labels[:nq], base, 5, block_queries=block, fused=fused)
         return retrieve(text[:nq], gal, labels[:nq], 5, block_queries=block, fused=fused)
 
-    steps = 2
+    def to_metrics(res, nq):  # "to final metrics on host" (SURVEY 8d): D2H of indices and ranks + the fp64 finalise
+        _, idx, rk = res
+        return metrics_from_ranks(idx.cpu().numpy().astype(np.int64), rk.cpu().numpy().astype(np.int64),
+                                  labels[:nq].cpu().numpy(), 5, np.arange(n_g))
+
+    steps = 5
     run(True, n_q)  # warm-up outside the kernel profile (its launches must not enter the per-launch flop count)
     _lib.profile_enable(True)
     t = timed(lambda: run(True, n_q), steps, 0)
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     ms = max_over_ranks(sum(t)) / steps
-    out = {"metric": "retrieval_queries_per_s", "value": n_q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
-           "config": {"workload": "c5: sharded top-5 retrieval (BASELINE configs[4]), fused GEMM+top-k kernel",
-                      "queries": n_q, "gallery": n_g, "gallery_per_rank": g_loc, "dim": DIM, "k": 5, "operands": "bf16"}}
+    # device tensors -> metrics dict on the host, wall clock (includes the D2H and the host finalise)
+    torch.cuda.synchronize(dev)
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        metrics = to_metrics(run(True, n_q), n_q)
+    torch.cuda.synchronize(dev)
+    ms_metrics = max_over_ranks((time.perf_counter() - w0) / steps * 1e3)
+    out = {"metric": "retrieval_queries_per_s", "value": n_q / (ms_metrics * 1e-3), "unit": "queries/s", "ms_per_step": ms_metrics,
+           "steps": steps, "device_only_ms_per_step": ms, "device_only_queries_per_s": n_q / (ms * 1e-3),
+           "config": {"workload": "c5: sharded top-5 retrieval (BASELINE configs[4]), fused GEMM+top-k kernel, device-resident "
+                                  "text/gallery/labels -> metrics dict on the host",
+                      "queries": n_q, "gallery": n_g, "gallery_per_rank": g_loc, "dim": DIM, "k": 5, "operands": "bf16",
+                      "inputs": "SURVEY 8d recipe: unit-norm Gaussian shapes, text = normalise(shape[owner] + 10.5 N/sqrt(D)), owners uniform"},
+           "metrics": {"RR@1": float(metrics["recall_rate"][0]), "RR@5": float(metrics["recall_rate"][4]),
+                       "NDCG@5": float(metrics["ndcg"][4]), "MRR": float(metrics["mrr"])}}
     if "sim_topk_fused" in prof:
         ms_f, n_f = prof["sim_topk_fused"]
         fl = 2.0 * n_q * g_loc * DIM / (n_f / steps)  # per launch
         tfs = fl / (ms_f / n_f * 1e-3) / 1e12
-        out["fused_roofline"] = {"kernel": "sim_topk_fused_kernel", "bound": "tensor", "achieved": tfs,
-                                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tfs / peaks["tf_sustained"],
-                                 "ms_per_launch": ms_f / n_f, "launches_per_step": n_f / steps}
+        out["roofline"] = {"kernel": "sim_topk_fused_kernel", "bound": "tensor", "achieved": tfs,
+                           "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tfs / peaks["tf_sustained"],
+                           "peak_source": "bf16_tflops_sustained (a 0.1-0.2 s kernel at the power cap)",
+                           "frac_of_burst_peak": tfs / peaks["tf_burst"], "traffic": None,
+                           "ms_per_launch": ms_f / n_f, "launches_per_step": n_f / steps}
+    # e2e: pinned host arrays (fp32 text as validation_step hands it over, tricolo_net.py:79-80) -> H2D -> retrieval ->
+    # D2H -> metrics dict on the host; a bounded slice of the queries, gallery included
+    nq_e = min(n_q, 262144)
+    text_h = text[:nq_e].float().cpu().pin_memory()
+    gal_h = gal.float().cpu().pin_memory()
+    lab_h = labels[:nq_e].cpu().pin_memory()
+
+    def e2e_once():
+        td, gd, ld = text_h.to(dev, non_blocking=True), gal_h.to(dev, non_blocking=True), lab_h.to(dev, non_blocking=True)
+        if world > 1:
+            res = sharded_retrieve(td, gd, ld, base, 5)
+        else:
+            res = retrieve(td, gd, ld, 5)
+        return to_metrics(res, nq_e)
+
+    e2e_once()
+    torch.cuda.synchronize(dev)
+    w0 = time.perf_counter()
+    for _ in range(3):
+        e2e_once()
+    torch.cuda.synchronize(dev)
+    ms_e = max_over_ranks((time.perf_counter() - w0) / 3 * 1e3)
+    out["e2e"] = {"value": nq_e / (ms_e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e, "queries": nq_e,
+                  "h2d_bytes_per_step": int(text_h.numel() * 4 + gal_h.numel() * 4 + lab_h.numel() * 8),
+                  "d2h_bytes_per_step": int(nq_e * (5 * 4 + 4)),
+                  "api": "tricolo_b200.evaluation.retrieve / distributed.sharded_retrieve on pinned fp32 host arrays + "
+                         "metrics_from_ranks on the host (wall clock, host finalise included)"}
     # two-kernel form on a slice (bounded: block x G_loc x 4 bytes of fp32 similarities per block)
     block = 8192
     nq2 = min(n_q, 16 * block)
@@ -502,50 +694,147 @@ def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrie
                                 "ms_per_launch": ms_g / n_g_l,
                                 "hbm_write_gbs": block * g_loc * 4 / (ms_g / n_g_l * 1e-3) / 1e9}
     out["two_kernel_form"] = two
+    # parity of this run: the sharded result equals the unsharded one on the same queries (N > 1); the fused form equals
+    # the two-kernel form (N = 1): indices and ranks, exactly
+    nqp = min(n_q, 16384)
+    a = run(True, nqp)
+    if world > 1:
+        b = retrieve(text[:nqp], gal_full, labels[:nqp], 5)
+        out["parity"] = {"retrieval_sharded_equals_unsharded": bool(torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])),
+                         "retrieval_queries_checked": nqp}
+        out["parity"]["ok_retrieval"] = out["parity"]["retrieval_sharded_equals_unsharded"]
+    else:
+        b = run(False, nqp, 8192)
+        out["parity"] = {"retrieval_fused_equals_two_kernel": bool(torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])),
+                         "retrieval_queries_checked": nqp}
+        out["parity"]["ok_retrieval"] = out["parity"]["retrieval_fused_equals_two_kernel"]
     if world > 1:
         # SURVEY 8(e) comparison: QUERY sharding (gallery replicated, every rank scores Q/W queries, no merge, no
         # collective) against the gallery sharding above
         try:
-            gen_full = torch.Generator(device=dev).manual_seed(1234)
-            gal_full = torch.randn(n_g, DIM, generator=gen_full, device=dev).bfloat16()
             q_loc = (n_q + world - 1) // world
             lo, hi = rank * q_loc, min((rank + 1) * q_loc, n_q)
-            fq = lambda: retrieve(text[lo:hi], gal_full, labels[lo:hi], 5)
+            fq = lambda: retrieve(text[lo:hi], gal_full, labels[lo:hi], 5)  # noqa: E731
             fq()
             tq = timed(fq, steps, 0)
             msq = max_over_ranks(sum(tq)) / steps
             out["query_sharded_comparison"] = {"ms_per_step": msq, "queries_per_s": n_q / (msq * 1e-3),
-                                               "note": "gallery replicated on every rank, Q/W queries per rank, no merge"}
+                                               "note": "gallery replicated on every rank, Q/W queries per rank, no merge (device tensors only)"}
         except Exception as ex:
             out["query_sharded_comparison"] = {"error": repr(ex)[:200]}
+    del gal_full
+    if world == 1:
+        out["c3"] = bench_retrieval_c3(dev, timed)
+        if rank == 0 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = retrieval_cpu_baseline(n_q, n_g)
+    return out
+
+
+def bench_retrieval_c3(dev, timed):
+    """configs[2]: the chair_table validation shape (7424 captions x 1486 shapes) through the reference-facing entry
+    compute_metrics(dataset, embeddings_dict) - list of tuples in, metric dict out (host construct + H2D + kernels +
+    D2H + fp64 finalise) - and through the tensor-in entry."""
+    import numpy as np
+    import torch
+
+    from oracle import retrieval_oracle as RO
+    from tricolo_b200.evaluation import compute_metrics, construct_embeddings_matrix, metrics_from_ranks, retrieve
+
+    tuples = RO.make_val_shaped(round_bf16=True)
+    ed = {"caption_embedding_tuples": tuples}
+    compute_metrics("Text2ShapeChairTable", ed, write_nearest=False)
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        m = compute_metrics("Text2ShapeChairTable", ed, write_nearest=False)
+        torch.cuda.synchronize(dev)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    text, gallery, labels, fit_labels, *_ = construct_embeddings_matrix("x", ed)
+    td, gd, ld = torch.from_numpy(text).to(dev), torch.from_numpy(np.ascontiguousarray(gallery)).to(dev), torch.from_numpy(labels).to(dev)
+    dt = statistics.median(timed(lambda: retrieve(td, gd, ld, 5), 20, 5))
+    q = len(tuples)
+    return {"workload": "c3: Text2Shape chair_table val shape, 7424 queries x 1486 shapes (BASELINE configs[2])",
+            "compute_metrics_ms": statistics.median(ts), "queries_per_s": q / (statistics.median(ts) * 1e-3),
+            "api": "tricolo_b200.evaluation.compute_metrics(dataset, embeddings_dict): tuple list in, metric dict out (wall clock)",
+            "tensor_in_device_ms": dt, "tensor_in_queries_per_s": q / (dt * 1e-3),
+            "metrics": {"RR@1": float(m["recall_rate"][0]), "RR@5": float(m["recall_rate"][4]), "NDCG@5": float(m["ndcg"][4]),
+                        "MRR": float(m["mrr"])}}
+
+
+def retrieval_cpu_baseline(n_q, n_g):
+    """The reference's CPU path beside it, through the oracle's restatement (or the unmodified reference
+    where it is importable): compute_metrics at C3 with the split, and one 3000-query block (the reference's own block
+    size, eval_retrieval.py:110) against a bounded gallery slice for C5, extrapolated and labelled so."""
+    import numpy as np
+
+    from oracle import reference_shim as RS
+    from oracle import retrieval_oracle as RO
+
+    cores = os.cpu_count() or 1
+    ref = RS.load()
+    tuples = RO.make_val_shaped(round_bf16=True)
+    out = {"cores": cores, "kind": "reference" if ref is not None else "port"}
+    t0 = time.perf_counter()
+    if ref is not None:
+        cwd = os.getcwd()
+        os.chdir("/tmp")
+        try:
+            ref.ER.compute_metrics("Text2ShapeChairTable", {"caption_embedding_tuples": tuples})
+        finally:
+            os.chdir(cwd)
+        t_total = time.perf_counter() - t0
+        out["c3"] = {"compute_metrics_s": t_total, "queries_per_s": len(tuples) / t_total}
+    else:
+        text, gal, labels, fit_labels, _, _ = RO.build_matrices(tuples)
+        t1 = time.perf_counter()
+        sim = RO.similarities(text, gal)
+        val, idx, rank = RO.topk_and_rank(sim, labels, 5)
+        t2 = time.perf_counter()
+        RO.metrics_from_topk(idx, rank, labels, 5, fit_labels)
+        t3 = time.perf_counter()
+        out["c3"] = {"compute_metrics_s": t3 - t0, "queries_per_s": len(tuples) / (t3 - t0),
+                     "split_s": {"construct": t1 - t0, "nearest_neighbors (dot + stable argsort)": t2 - t1, "metrics": t3 - t2},
+                     "note": "oracle port: vectorised NumPy restatement (the reference's own Python loops over full sorted rows "
+                             "are 3-5 s at this shape: BASELINE.md)"}
+    # C5: one 3000-query block of dot + full argsort + full sort (eval_retrieval.py:74-76) against a gallery slice
+    g_s = min(n_g, 50_000)
+    rng = np.random.default_rng(0)
+    q = rng.standard_normal((3000, DIM))
+    g = rng.standard_normal((g_s, DIM)).astype(np.float32)
+    t0 = time.perf_counter()
+    s = np.dot(q, g.T)
+    np.argsort(s, axis=1)
+    np.sort(s, axis=1)
+    tb = time.perf_counter() - t0
+    blocks = (n_q + 2999) // 3000
+    full = tb * (n_g / g_s) * blocks
+    out["c5"] = {"block_s": tb, "block": f"3000 queries x {g_s} shapes: np.dot (fp64) + full argsort + full sort (eval_retrieval.py:74-76)",
+                 "extrapolated_s": full, "extrapolated_queries_per_s": n_q / full,
+                 "note": f"EXTRAPOLATED: x{n_g / g_s:.0f} to the full gallery (linear; the sort's log factor ignored) x{blocks} blocks; "
+                         "the reference cannot run this size as written (1.6 TB of sort_indices)"}
     return out
 
 
 def cpu_baseline(batch):
-    """The oracle's CPU-PyTorch port of the reference loss on the host cores: bounded sample (~10-30 s)."""
+    """The reference loss on the host cores (the unmodified reference where importable, else the oracle's PyTorch port):
+    bounded sample (~10-30 s)."""
     import torch
-
-    from oracle import ntxent_oracle as NO
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    step, kind = reference_loss_step()
     sample_batch = min(batch, 2048)
     feats = make_features(sample_batch, sample_batch, 0)
-
-    def step():
-        fd = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
-        out = NO.torch_trimodal(fd, TAU, ALPHA)
-        out["train_loss/total_loss"].backward()
-
-    step()
+    step(feats)
     t0 = time.perf_counter()
     n = 0
     while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
-        step()
+        step(feats)
         n += 1
     dt = (time.perf_counter() - t0) / n
     full = dt * (batch / sample_batch) ** 2
-    return {"value": batch / full, "unit": "pairs/s", "cores": cores, "kind": "port",
+    return {"value": batch / full, "unit": "pairs/s", "cores": cores, "kind": kind,
             "sample": f"{n} fwd+bwd steps of the trimodal loss at B={sample_batch} (fp32, torch CPU, {cores} threads), "
                       f"scaled x{(batch // sample_batch) ** 2} to B={batch} (cost is quadratic in B)",
             "ms_per_sample_step": dt * 1e3}
@@ -604,13 +893,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     elif args.gpus > 1:
         raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    ok = True
     try:
-        run_ours(args, rank, world, local_rank)
+        ok = run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
 
             dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: parity check failed (see the \"parity\" object of the JSON line)")
 
 
 if __name__ == "__main__":

@@ -24,35 +24,9 @@ from oracle import retrieval_oracle as RO  # noqa: E402  (data generators only)
 
 
 def install_shim():
-    def stub(name, **attrs):
-        m = types.ModuleType(name)
-        m.__dict__.update(attrs)
-        sys.modules[name] = m
-        return m
+    from oracle.reference_shim import install_shim as _install  # the one shim used by tests, goldens and the baseline arm
 
-    class LightningModule(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self._device = torch.device("cpu")
-
-        @property
-        def device(self):
-            return self._device
-
-        def save_hyperparameters(self, *a, **k):
-            pass
-
-    ltp = stub("lightning.pytorch", LightningModule=LightningModule)
-    stub("lightning", pytorch=ltp)
-
-    class _Writer:
-        def write(self, obj):
-            pass
-
-    stub("jsonlines", open=lambda *a, **k: _Writer())
-    stub("hydra", utils=stub("hydra.utils"))
-    stub("clip")
-    sys.path.insert(0, REF)
+    _install(REF)
 
 
 def loss_cases():

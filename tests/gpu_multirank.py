@@ -24,7 +24,7 @@ def main():
     ok = True
     keys = ["text_features", "image_features", "voxel_features"]
 
-    def run_loss(loc, transport, bwd, sync="flags"):
+    def run_loss(loc, transport, bwd, sync="barrier"):
         os.environ["TRICOLO_B200_SYMM"] = transport
         os.environ["TRICOLO_B200_SHARDED_BWD"] = bwd
         os.environ["TRICOLO_B200_SHARD_SYNC"] = sync
@@ -48,11 +48,12 @@ def main():
         loc = [f[rank * bl:(rank + 1) * bl].cuda().requires_grad_(True) for f in full]
         ref_l, ref_g = NO.trimodal_forward_backward(dict(zip(keys, [f.numpy() for f in full])), TAU, ALPHA)
         results = {}
-        # symm/sharedg: NVLink peer memory, flag protocol (no barrier kernels), sharded shared-G backward with the
-        # in-kernel reduce-scatter - the default for 128-row-aligned shards; .../barrier: the same with cross-device
-        # barrier kernels instead of flags; symm/pc: directional backward; nccl: NCCL collectives
-        for name, transport, bwd, sync in (("symm/sharedg", "1", "sharedg", "flags"), ("symm/sharedg/barrier", "1", "sharedg", "barrier"),
-                                           ("symm/pc", "1", "pc", "flags"), ("nccl/pc", "0", "pc", "flags")):
+        # symm/sharedg: NVLink peer memory, sharded shared-G backward with the in-kernel reduce-scatter; symm/pc:
+        # directional backward; .../flags: the barrier-free flag protocol instead of barrier kernels (fused all-gather
+        # push warps, flag-signalled reduce-scatter); nccl: NCCL collectives
+        for name, transport, bwd, sync in (("symm/sharedg", "1", "sharedg", "barrier"), ("symm/sharedg/flags", "1", "sharedg", "flags"),
+                                           ("symm/pc", "1", "pc", "barrier"), ("symm/pc/flags", "1", "pc", "flags"),
+                                           ("nccl/pc", "0", "pc", "barrier")):
             losses, grads = run_loss(loc, transport, bwd, sync)
             lerr = max(abs(losses[k] - v) / abs(v) for k, v in ref_l.items())
             errs = [np.linalg.norm(grads[m].double().cpu().numpy() - ref_g[k][rank * bl:(rank + 1) * bl]) /
@@ -69,7 +70,7 @@ def main():
     # two forwards before the two backwards: the second forward must not overwrite the operands the first backward needs
     os.environ["TRICOLO_B200_SYMM"] = "1"
     os.environ["TRICOLO_B200_SHARDED_BWD"] = "sharedg"
-    os.environ["TRICOLO_B200_SHARD_SYNC"] = "flags"
+    os.environ["TRICOLO_B200_SHARD_SYNC"] = "barrier"
     first = results["symm/sharedg"][1]
     loc2 = [(x.detach() * 0.5 + 0.1).requires_grad_(True) for x in loc]
     for x in loc:

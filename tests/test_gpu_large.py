@@ -1,0 +1,116 @@
+"""GPU parity at the two large BASELINE configurations, against golden outputs of the UNMODIFIED reference
+(tests/golden/make_golden_large.py, run in the build container where /root/reference exists):
+
+  C4  global batch 8192, dim 512 (bench.py's own inputs): 3 pair losses + every 64th gradient row of
+      TriCoLoNet._calculate_losses (tricolo_net.py:56-65) in fp32 on the CPU - both single-GPU backward forms.
+  C5  one 3000-query block (the reference's own block size, eval_retrieval.py:110) against the full 200 000-shape
+      gallery: indices where the fp64 margin exceeds 1e-5, ranks inside the interval an fp32-accumulated similarity
+      can reach (exact where that interval is a single value), metrics; for the fused kernel, the two-kernel form
+      and an 8-shard replay; the three forms bit-identical to each other.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_oracle as RO
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+TAU, ALPHA = 0.1, 0.25
+KEYS = ("text_features", "image_features", "voxel_features")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(HERE, "golden", "large_outputs.json")))
+
+
+@pytest.mark.parametrize("mode", ["sharedg", "pc"])
+def test_c4_loss_and_grads_vs_reference_golden(gold, mode, monkeypatch):
+    from bench import make_features
+    from tricolo_b200.loss import trimodal_ntxent
+
+    monkeypatch.setenv("TRICOLO_B200_BWD", mode)
+    g = gold["c4"]
+    feats = make_features(g["batch"], g["batch"], 0, seed=g["seed"])
+    dev = [feats[k].cuda().requires_grad_(True) for k in KEYS]
+    losses = trimodal_ntxent(dev, TAU, ALPHA)
+    losses.sum().backward()
+    names = ["train_loss/text_image_loss", "train_loss/text_voxel_loss", "train_loss/image_voxel_loss"]
+    for got, n in zip(losses.detach().cpu().tolist(), names):
+        assert abs(got - g["losses"][n]) <= 1e-3 * abs(g["losses"][n]), (n, got, g["losses"][n])
+    gg = np.load(os.path.join(HERE, "golden", "c4_grads.npz"))
+    for m, k in enumerate(KEYS):
+        ref = gg[k].astype(np.float64)
+        got = dev[m].grad[:: g["row_stride"]].double().cpu().numpy()
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err <= 1e-3, (mode, k, err)
+        assert abs(float(dev[m].grad.double().norm()) - g["grad_norm"][k]) <= 1e-3 * g["grad_norm"][k]
+
+
+def test_c5_block_vs_reference_golden(gold):
+    from tricolo_b200 import ops
+    from tricolo_b200.evaluation import metrics_from_ranks, retrieve
+
+    g = gold["c5_block"]
+    z = np.load(os.path.join(HERE, "golden", "c5_block.npz"))
+    text, gal, labels = RO.make_large_retrieval(seed=g["seed"], n_shapes=g["gallery"], n_queries=g["queries"], dim=g["dim"])
+    t, ga, lab = torch.from_numpy(text).cuda().bfloat16(), torch.from_numpy(gal).cuda().bfloat16(), torch.from_numpy(labels).cuda()
+    fused = retrieve(t, ga, lab, 5, fused=True)
+    two = retrieve(t, ga, lab, 5, fused=False, block_queries=1024)
+    # 8 gallery shards replayed on one GPU (tricolo_b200/distributed.py: sharded_retrieve), fused kernel per shard
+    bounds = np.linspace(0, g["gallery"], 9).astype(int)
+    shards = [ga[lo:hi].contiguous() for lo, hi in zip(bounds[:-1], bounds[1:])]
+    gt = sum(ops.gt_sim_mma(t, s, lab, int(lo)) for s, lo in zip(shards, bounds[:-1]))
+    cv, ci, nb = [], [], 0
+    for s, lo in zip(shards, bounds[:-1]):
+        v, i, b = ops.sim_topk_fused(t, s, 5, lab, gt, int(lo))
+        cv.append(v); ci.append(i); nb = nb + b
+    mv, mi = ops.topk_merge(torch.stack(cv), torch.stack(ci))
+    sharded = (mv, mi, nb + 1)
+    for other in (two, sharded):  # the three forms are the same numbers, bit for bit
+        assert all(torch.equal(a, b) for a, b in zip(fused, other))
+    idx = fused[1].cpu().numpy().astype(np.int64)
+    rank = fused[2].cpu().numpy().astype(np.int64)
+    safe = z["margin"] > 1e-5  # rows whose top-6 fp64 similarities are further apart than any fp32 rounding
+    assert safe.sum() == g["rows_top5_safe"] and safe.mean() > 0.95
+    assert np.array_equal(idx[safe], z["indices"][safe].astype(np.int64))
+    # rank of the ground truth: inside the interval an fp32-accumulated similarity can reach (|error| <= rank_delta),
+    # i.e. EXACTLY the reference's rank wherever no other similarity lies within that distance of the positive's
+    assert np.all(rank >= z["rank_lo"]) and np.all(rank <= z["rank_hi"])
+    exact = z["rank_lo"] == z["rank_hi"]
+    assert exact.sum() == g["rows_rank_exact"] and np.array_equal(rank[exact], z["rank"][exact].astype(np.int64))
+    assert np.abs(fused[0].double().cpu().numpy()[safe] - z["top5_val"][safe]).max() <= 2e-6
+    # metrics: RR@k / NDCG@5 only see ranks <= 5, which sit in the sparse tail of the similarity distribution
+    got = metrics_from_ranks(idx, rank, labels, 5, np.arange(g["gallery"]))
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.abs(got[k] - np.asarray(g["metrics"][k])).max() <= 1e-3 * max(1e-9, np.abs(np.asarray(g["metrics"][k])).max()) + 1e-12, k
+    assert abs(got["mrr"] - g["metrics"]["mrr"]) <= 1e-3 * g["metrics"]["mrr"]
+
+
+def test_indep_backward_mode_in_a_fresh_process():
+    """TRICOLO_B200_BWD=indep (one CTA per dim half, 12 B^2 D executed; the only kernel for dim <= 256) is read once per
+    process, so the dim-512 use of it is checked in a subprocess: loss and gradients against the oracle."""
+    code = r'''
+import numpy as np, torch
+from oracle import ntxent_oracle as NO
+from tricolo_b200.loss import trimodal_ntxent
+g = torch.Generator().manual_seed(5)
+base = torch.randn(600, 512, generator=g)
+f = [(base + 0.5 * torch.randn(600, 512, generator=g)).bfloat16().float() for _ in range(3)]
+dev = [x.cuda().requires_grad_(True) for x in f]
+trimodal_ntxent(dev, 0.1, 0.25).sum().backward()
+_, ref = NO.trimodal_forward_backward(dict(zip(("text_features", "image_features", "voxel_features"), [x.numpy() for x in f])), 0.1, 0.25)
+errs = [float(np.linalg.norm(d.grad.double().cpu().numpy() - r) / np.linalg.norm(r)) for d, r in zip(dev, ref.values())]
+assert max(errs) <= 1e-3, errs
+print("INDEP OK", errs)
+'''
+    env = dict(os.environ, TRICOLO_B200_BWD="indep", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "INDEP OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

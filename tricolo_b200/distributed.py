@@ -135,8 +135,10 @@ def _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev):
 
 
 def _flags_enabled() -> bool:
-    """TRICOLO_B200_SHARD_SYNC=barrier keeps the first version's cross-device barrier kernels (same results)."""
-    return os.environ.get("TRICOLO_B200_SHARD_SYNC", "flags") != "barrier"
+    """TRICOLO_B200_SHARD_SYNC=flags selects the barrier-free protocol (device-side flags, arrival-gated tile sweep,
+    optional fused all-gather).  Same results; measured SLOWER than the barrier form on 8 B200 (0.29 vs 0.22 ms per
+    step at B=8192: every flag costs a system-scope fence behind a burst of NVLink stores), so it is opt-in."""
+    return os.environ.get("TRICOLO_B200_SHARD_SYNC", "barrier") == "flags"
 
 
 def _fused_push_enabled() -> bool:
@@ -145,8 +147,15 @@ def _fused_push_enabled() -> bool:
     return os.environ.get("TRICOLO_B200_PUSH", "fwd") != "k1"
 
 
-def _sharded_g_enabled() -> bool:
-    return os.environ.get("TRICOLO_B200_SHARDED_BWD", "sharedg") != "pc"
+def _sharded_g_enabled(b_loc: int = 1 << 30) -> bool:
+    """Backward form of a sharded step: TRICOLO_B200_SHARDED_BWD=sharedg|pc forces one.  Default: the sharded shared-G
+    form (6 b B D, in-kernel reduce-scatter) from 2048 rows per rank on, the directional kernel (8 b B D, no exchange)
+    below - measured at B=8192: N=2 0.439 vs 0.470 ms per step, N=8 0.246 vs 0.217 (at 1024 rows per rank the 29 MB of
+    fp32 partials per rank and the per-kernel fixed costs outweigh the saved recompute)."""
+    e = os.environ.get("TRICOLO_B200_SHARDED_BWD", "")
+    if e in ("sharedg", "pc"):
+        return e == "sharedg"
+    return b_loc >= 2048
 
 
 def _world(group=None):
@@ -177,7 +186,7 @@ class _GlobalNTXent(torch.autograd.Function):
             # no barrier kernels: K1 stores every row into all ranks' buffers as soon as the destination is ready and
             # flags each 128-row chunk; the tile kernel consumes column tiles in arrival order; statistics are pushed
             # into per-source slots and the finalise kernel waits for the W flags
-            use_sg = _sharded_g_enabled() and ops.ShardedBwdPlan.supported(b_loc, dim, world)
+            use_sg = _sharded_g_enabled(b_loc) and ops.ShardedBwdPlan.supported(b_loc, dim, world)
             fused = _fused_push_enabled()
             inv_all, xs = ops.l2norm_fwd_push(feats, ws.dsts_all, ws.z_row_stride, rank, world, ws.sync_addrs, op_format,
                                               remote=not fused)
@@ -267,7 +276,7 @@ class _GlobalNTXent(torch.autograd.Function):
         grad_losses = grad_losses.contiguous()
         ws = getattr(ctx, "symm_ws", None)
         need = [bool(ctx.needs_input_grad[6 + m]) for m in range(n)]
-        use_sg = getattr(ctx, "use_sg", _sharded_g_enabled() and ops.ShardedBwdPlan.supported(b_loc, dim, ws.world if ws else 1))
+        use_sg = getattr(ctx, "use_sg", _sharded_g_enabled(b_loc) and ops.ShardedBwdPlan.supported(b_loc, dim, ws.world if ws else 1))
         if ws is not None and any(need) and use_sg:
             # row block of G once per pair; column-side partials land in their owners' receive buffers over NVLink
             plan, work, addrs, hr = ws.sharded_bwd(pairs, need)
