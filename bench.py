@@ -594,7 +594,7 @@ def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrie
     import numpy as np
     import torch
 
-    from tricolo_b200.evaluation import metrics_from_ranks
+    from tricolo_b200.evaluation import retrieve_metrics
 
     n_q, n_g = args.retrieval_queries, args.retrieval_gallery
     g_loc = n_g // world
@@ -606,10 +606,8 @@ def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrie
             return sharded_retrieve(text[:nq], gal, labels[:nq], base, 5, block_queries=block, fused=fused)
         return retrieve(text[:nq], gal, labels[:nq], 5, block_queries=block, fused=fused)
 
-    def to_metrics(res, nq):  # "to final metrics on host" (SURVEY 8d): D2H of indices and ranks + the fp64 finalise
-        _, idx, rk = res
-        return metrics_from_ranks(idx.cpu().numpy().astype(np.int64), rk.cpu().numpy().astype(np.int64),
-                                  labels[:nq].cpu().numpy(), 5, np.arange(n_g))
+    def to_metrics(res, nq):  # "to final metrics on host" (SURVEY 8d): K5 reduction on the device, 6 numbers D2H,
+        return retrieve_metrics(None, None, None, 5, rank=res[2])  # closed-form finalise on the host
 
     steps = 5
     run(True, n_q)  # warm-up outside the kernel profile (its launches must not enter the per-launch flop count)
@@ -668,7 +666,7 @@ def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrie
                   "h2d_bytes_per_step": int(text_h.numel() * 4 + gal_h.numel() * 4 + lab_h.numel() * 8),
                   "d2h_bytes_per_step": int(nq_e * (5 * 4 + 4)),
                   "api": "tricolo_b200.evaluation.retrieve / distributed.sharded_retrieve on pinned fp32 host arrays + "
-                         "metrics_from_ranks on the host (wall clock, host finalise included)"}
+                         "retrieve_metrics (K5 reduction on the device, metric dict on the host; wall clock)"}
     # two-kernel form on a slice (bounded: block x G_loc x 4 bytes of fp32 similarities per block)
     block = 8192
     nq2 = min(n_q, 16 * block)

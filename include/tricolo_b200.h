@@ -339,6 +339,20 @@ int tcl_topk_merge(const float* cand_val, const int32_t* cand_idx, int n_shards,
                    int k, float* topk_val, int32_t* topk_idx, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * K5 - metric reduction.                       replaces eval_retrieval.py:169-201 for the tensor-in entry
+ * With exactly one relevant gallery item per query (the gallery is de-duplicated by model id, :49-56) every metric is
+ * a function of the 1-based rank r_q of the ground truth:
+ *   recall_rate[j] = recall[j] = mean(r <= j+1), precision[j] = mean(r <= j+1)/(j+1),
+ *   ndcg[j] = mean([r <= j+1] / log2(r+1)), mrr = mean(1/r).
+ * out (device, k+1 doubles): out[j] = #{q : r_q == j+1} for j < k, out[k] = sum_q 1/r_q (fp64, fixed order).
+ * workspace: tcl_rank_metrics_workspace_bytes(), 256-byte aligned, zero-initialised once (the kernel leaves its
+ * counter at zero).  k <= 16.
+ * ------------------------------------------------------------------------- */
+size_t tcl_rank_metrics_workspace_bytes(void);
+int tcl_rank_metrics(const int32_t* rank, int64_t n_q, int k, double* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------
  * K2'+K4 fused — retrieval without materialising S (dim % 64 == 0, dim <= 512, k <= 16).
  * Same results as tcl_sim_gemm + tcl_topk_rank (same order, same rank definition), bit for bit:
  * the per-query ground-truth similarity gt_sim[q] must be the number the tensor core produces for
@@ -380,7 +394,8 @@ enum {
   TCL_K_GATHER_SUM = 13,
   TCL_K_PEER_SUM = 14,
   TCL_K_NTXENT_G = 15, /* shared-G backward, kernel A (logit recompute -> G); its GEMM kernel is TCL_K_NTXENT_BWD */
-  TCL_K_COUNT = 16
+  TCL_K_RANK_METRICS = 16,
+  TCL_K_COUNT = 17
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);

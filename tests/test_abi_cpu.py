@@ -92,6 +92,22 @@ def test_host_metrics_finalise_matches_oracle():
     assert got["mrr"] == ref["mrr"]
 
 
+def test_rank_count_closed_form_matches_reference_order_finalise():
+    """metrics_from_rank_counts (what the K5 device reduction feeds) against metrics_from_ranks on the same ranks."""
+    from oracle import retrieval_oracle as RO
+    from tricolo_b200.evaluation import metrics_from_rank_counts, metrics_from_ranks
+
+    tuples = RO.make_val_shaped(seed=3, n_shapes=300, n_queries=1000, dim=128, round_bf16=True)
+    ref = RO.compute_metrics(tuples)
+    rank, labels = ref["_rank"], RO.build_matrices(tuples)[2]
+    counts = [(rank == j + 1).sum() for j in range(5)]
+    got = metrics_from_rank_counts(counts, float((1.0 / rank).sum()), len(rank))
+    want = metrics_from_ranks(ref["_indices"], rank, labels, 5, np.arange(300))
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.abs(got[k] - want[k]).max() <= 1e-14
+    assert abs(got["mrr"] - want["mrr"]) <= 1e-14
+
+
 def test_distance_flip_quirk():
     from tricolo_b200.evaluation.eval_retrieval import _flip_distances_like_reference
 

@@ -392,6 +392,28 @@ def test_fused_retrieval_matches_unfused_bit_exact(tb, q, g, d, k, ties):
         assert np.array_equal(b[1].cpu().numpy()[:, : min(k, g)], ri) and np.array_equal(b[2].cpu().numpy(), rr)
 
 
+def test_rank_metrics_reduction(tb):
+    """K5 (tcl_rank_metrics) + the closed-form finalise equal the reference-order host finalise on the same ranks."""
+    ops = tb.ops
+    tuples = RO.make_val_shaped(seed=3, n_shapes=1486, n_queries=7424, dim=512, round_bf16=True)
+    text, gal, labels, fit_labels, _, _ = RO.build_matrices(tuples)
+    t, g, lab = torch.from_numpy(text).float().cuda(), torch.from_numpy(gal).cuda(), torch.from_numpy(labels).cuda()
+    val, idx, rank = tb.eval.retrieve(t, g, lab, 5)
+    ref = tb.eval.metrics_from_ranks(idx.cpu().numpy().astype(np.int64), rank.cpu().numpy().astype(np.int64), labels, 5, fit_labels)
+    got = tb.eval.retrieve_metrics(t, g, lab, 5)
+    for k in ("precision", "recall", "recall_rate", "ndcg"):
+        assert np.abs(got[k] - ref[k]).max() <= 1e-12, k
+    assert abs(got["mrr"] - ref["mrr"]) <= 1e-12
+    red = ops.rank_metrics(rank, 5).cpu().numpy()  # counts are exact integers; two launches give identical sums
+    r = rank.cpu().numpy()
+    assert [int(x) for x in red[:5]] == [int((r == j + 1).sum()) for j in range(5)]
+    assert np.array_equal(red, ops.rank_metrics(rank, 5).cpu().numpy())
+    big = torch.randint(1, 200000, (1_000_003,), device="cuda", dtype=torch.int32)
+    rb = ops.rank_metrics(big, 16).cpu().numpy()
+    assert abs(rb[16] - float((1.0 / big.double()).sum())) <= 1e-9 * rb[16]
+    assert [int(x) for x in rb[:16]] == [int((big == j + 1).sum()) for j in range(16)]
+
+
 def test_fused_sharded_matches_unsharded(tb):
     ops = tb.ops
     gen = torch.Generator(device="cuda").manual_seed(5)

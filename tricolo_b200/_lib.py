@@ -18,7 +18,7 @@ TCL_OP_F16, TCL_OP_BF16 = 0, 1
 TCL_DT_F32, TCL_DT_F16, TCL_DT_BF16, TCL_DT_F64 = 0, 1, 2, 3
 KERNEL_IDS = {
     "l2norm_fwd": 0, "cast16": 1, "transpose16": 2, "ntxent_fwd": 3, "fwd_reduce": 4, "fwd_finalize": 5,
-    "ntxent_bwd": 6, "l2norm_bwd": 7, "sim_gemm": 8, "topk_rank": 9, "gather_gt": 10, "topk_merge": 11, "sim_topk_fused": 12, "gather_sum": 13, "peer_sum": 14, "ntxent_g": 15,
+    "ntxent_bwd": 6, "l2norm_bwd": 7, "sim_gemm": 8, "topk_rank": 9, "gather_gt": 10, "topk_merge": 11, "sim_topk_fused": 12, "gather_sum": 13, "peer_sum": 14, "ntxent_g": 15, "rank_metrics": 16,
 }
 
 _DTYPE_CODE = {
@@ -108,6 +108,8 @@ SIGNATURES = {
     "tcl_topk_rank": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_gather_gt_sim": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "tcl_topk_merge": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "tcl_rank_metrics_workspace_bytes": (_sz, []),
+    "tcl_rank_metrics": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "tcl_gt_sim_mma": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "tcl_sim_topk_fused_workspace_bytes": (_sz, [_i64, _i64, _i]),
     "tcl_sim_topk_fused": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

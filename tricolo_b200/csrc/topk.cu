@@ -178,9 +178,90 @@ __global__ void topk_merge_kernel(const float* __restrict__ cv, const int32_t* _
   }
 }
 
+// K5: metric reduction from the ranks of the ground truth (with one relevant gallery item per query all
+// of RR@k / NDCG@k / precision / recall / MRR are functions of the rank): count[j] = #{rank == j+1}, j < k, and
+// sum 1/rank in fp64.  Two levels in one launch, both in a fixed order (per-block partials, then the block that
+// finishes last adds them in block order): deterministic.
+static constexpr int RM_MAX_K = 16;
+__global__ void __launch_bounds__(256) rank_metrics_kernel(const int32_t* __restrict__ rank, int64_t n_q, int k,
+                                                           double* __restrict__ partial, unsigned int* __restrict__ counter,
+                                                           double* __restrict__ out) {
+  __shared__ double sh[8][RM_MAX_K + 1];
+  __shared__ bool last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int cnt[RM_MAX_K];
+#pragma unroll
+  for (int j = 0; j < RM_MAX_K; ++j) cnt[j] = 0;
+  double rr = 0.0;
+  // contiguous chunk per thread so that the fp64 sum order does not depend on the launch geometry's interleaving
+  const int64_t per_block = (n_q + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = per_block * blockIdx.x, b1 = b0 + per_block < n_q ? b0 + per_block : n_q;
+  for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+    const int r = rank[i];
+    rr += 1.0 / static_cast<double>(r);
+#pragma unroll
+    for (int j = 0; j < RM_MAX_K; ++j) cnt[j] += (j < k && r == j + 1) ? 1u : 0u;
+  }
+  double v[RM_MAX_K + 1];
+#pragma unroll
+  for (int j = 0; j < RM_MAX_K; ++j) v[j] = static_cast<double>(cnt[j]);
+  v[RM_MAX_K] = rr;
+#pragma unroll
+  for (int j = 0; j <= RM_MAX_K; ++j) {
+    double x = v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sh[warp][j] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x <= RM_MAX_K) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += sh[w][threadIdx.x];
+    partial[static_cast<int64_t>(blockIdx.x) * (RM_MAX_K + 1) + threadIdx.x] = x;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    last = atomicAdd(counter, 1u) + 1u == gridDim.x;
+    if (last) *counter = 0u;
+  }
+  __syncthreads();
+  if (last && threadIdx.x <= RM_MAX_K) {
+    __threadfence();
+    double x = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) x += __ldcg(partial + static_cast<int64_t>(b) * (RM_MAX_K + 1) + threadIdx.x);
+    if (threadIdx.x < k) out[threadIdx.x] = x;
+    if (threadIdx.x == RM_MAX_K) out[k] = x;
+  }
+}
+
 }  // namespace tcl
 
 using namespace tcl;
+
+static constexpr int kRankMetricsBlocks = 592;  // 4 per SM
+
+extern "C" size_t tcl_rank_metrics_workspace_bytes(void) {
+  return sizeof(double) * kRankMetricsBlocks * (RM_MAX_K + 1) + 256;
+}
+
+extern "C" int tcl_rank_metrics(const int32_t* rank, int64_t n_q, int k, double* out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  TCL_REQUIRE(rank && out && workspace, TCL_ERR_BAD_ARG, "rank_metrics: null pointer");
+  TCL_REQUIRE(k >= 1 && k <= RM_MAX_K && n_q >= 1, TCL_ERR_BAD_ARG, "rank_metrics: k %d, n_q %lld", k, (long long)n_q);
+  TCL_REQUIRE(workspace_bytes >= tcl_rank_metrics_workspace_bytes() && aligned_to(workspace, 256), TCL_ERR_WORKSPACE,
+              "rank_metrics: workspace (zero-initialised once by the caller, 256-byte aligned)");
+  if (int e = require_sm100()) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t blocks = (n_q + 2047) / 2048;
+  if (blocks > kRankMetricsBlocks) blocks = kRankMetricsBlocks;
+  unsigned int* counter = static_cast<unsigned int*>(workspace);
+  double* partial = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+  ProfScope prof(TCL_K_RANK_METRICS, st);
+  rank_metrics_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(rank, n_q, k, partial, counter, out);
+  TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
 
 extern "C" int tcl_topk_rank(const float* s, int64_t ld_s, int64_t n_q, int64_t n_g, int k,
                              const int64_t* labels, int64_t idx_base, const float* gt_sim_in,

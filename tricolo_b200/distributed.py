@@ -134,6 +134,26 @@ def _symm_workspace(group, world, rank, b_loc, n, dim, dt, p, dev):
     return ws
 
 
+def _hold(ws, ctx) -> None:
+    """A forward that needs gradients holds the workspace (its gathered operands) until its backward has run - or until
+    the autograd node is dropped without one (loss discarded, exception): the finalizer releases it then, so that a
+    lost backward does not leave every later step on the NCCL path."""
+    ws.busy = True
+    ctx.symm_ws = ws
+    token = object()
+    ws.holder = token
+    try:
+        weakref.finalize(ctx, _release, weakref.ref(ws), token)
+    except TypeError:  # the autograd node cannot be weakly referenced on this torch build: released by backward only
+        pass
+
+
+def _release(ws_ref, token) -> None:
+    ws = ws_ref()
+    if ws is not None and getattr(ws, "holder", None) is token:
+        ws.busy = False
+
+
 def _flags_enabled() -> bool:
     """TRICOLO_B200_SHARD_SYNC=flags selects the barrier-free protocol (device-side flags, arrival-gated tile sweep,
     optional fused all-gather).  Same results; measured SLOWER than the barrier form on 8 B200 (0.29 vs 0.22 ms per
@@ -205,8 +225,7 @@ class _GlobalNTXent(torch.autograd.Function):
             lse2_row_all, lse2_col, loss = ops.ntxent_finalize_sharded(p, b_loc, rank, world, inv_tau, alpha, ws.stats_addrs,
                                                                        ws.sync_addrs[rank], dev)
             if needs_grad:
-                ws.busy = True
-                ctx.symm_ws = ws
+                _hold(ws, ctx)
                 ctx.flags = True
             ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
             ctx.save_for_backward(lse2_row_all, lse2_col, ws.z, *xs, *invs)
@@ -230,8 +249,7 @@ class _GlobalNTXent(torch.autograd.Function):
             lse2_row_all, lse2_col, loss = ops.ntxent_finalize_sharded(p, b_loc, rank, world, inv_tau, alpha, ws.stats_addrs,
                                                                        0, dev)
             if needs_grad:
-                ws.busy = True
-                ctx.symm_ws = ws
+                _hold(ws, ctx)
             ctx.cfg = (inv_tau, float(alpha), op_format, tuple(pairs), row_offset, b_glob, float(grad_world_scale), n)
             ctx.save_for_backward(lse2_row_all, lse2_col, ws.z, *xs, *invs)
             return loss

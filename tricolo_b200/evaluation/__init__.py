@@ -7,5 +7,7 @@ from .eval_retrieval import (  # noqa: F401
     print_nearest_info,
     retrieve,
     metrics_from_ranks,
+    metrics_from_rank_counts,
+    retrieve_metrics,
 )
 from .accumulator import RetrievalAccumulator, save_predictions  # noqa: F401,E402

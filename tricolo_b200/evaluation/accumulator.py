@@ -97,9 +97,10 @@ class RetrievalAccumulator:
         if write_nearest:
             n_q = len(labels)
             distances = ER._flip_distances_like_reference(val.cpu().numpy().astype(np.float64), 3000 if n_q > 8000 else None)
-            ids = self._categories if dataset == "Primitives" else self._model_ids
+            # 'groundtruth' is always the raw model id (get_nearest_info reads caption_tuples[idx][2], eval_retrieval.py:
+            # 232-240); the Primitives swap (:45-46) applies to the labels only
             nearest = [[label_to_model_id[int(c)] for c in row] for row in indices]
-            ER.print_nearest_info(self._categories, list(ids), nearest, distances)
+            ER.print_nearest_info(self._categories, list(self._model_ids), nearest, distances)
         if print_results:
             ER._print_results(pr_at_k)
         return pr_at_k

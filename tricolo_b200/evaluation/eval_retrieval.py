@@ -242,6 +242,8 @@ def retrieve(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k:
     dt = ops.L.op_torch_dtype(operand_format)
     g16 = gallery if gallery.dtype == dt else ops.cast_16bit(gallery, operand_format)
     n_q, n_g, dim = text.shape[0], gallery.shape[0], text.shape[1]
+    if n_g < k:  # the reference's slicing would silently return fewer columns; unfilled slots would carry index -1
+        raise ValueError(f"retrieve: the gallery has {n_g} shapes, fewer than k = {k}")
     dev = text.device
     if fused is None:
         fused = _fusable(dim, k)
@@ -269,6 +271,27 @@ def retrieve(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k:
         val[s:e], idx[s:e] = v, i
         rank[s:e] = nb + 1
     return val, idx, rank
+
+
+def metrics_from_rank_counts(counts, sum_rr: float, n_queries: int) -> dict:
+    """The metric dict from #{rank == j+1} (j < k) and sum 1/rank: the closed form of eval_retrieval.py:161-206 when
+    every query has exactly one relevant gallery item (equal to metrics_from_ranks to ~1e-15)."""
+    counts = np.asarray(counts, dtype=np.float64)
+    k = counts.shape[0]
+    hit = np.cumsum(counts)  # #{rank <= j+1}
+    rr = hit / n_queries
+    return {"precision": rr / np.arange(1, k + 1), "recall": rr.copy(), "recall_rate": rr,
+            "ndcg": np.cumsum(counts / np.log2(np.arange(1, k + 1) + 1)) / n_queries, "mrr": float(sum_rr) / n_queries}
+
+
+def retrieve_metrics(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k: int = 5, rank=None, **kw) -> dict:
+    """Tensor-in entry all the way to the metric dict: retrieve() (or ranks already computed, e.g. by
+    distributed.sharded_retrieve) + the K5 reduction on the device; only k+1 numbers cross PCIe.  Valid when labels
+    index a de-duplicated gallery (one relevant item per query), which is what construct_embeddings_matrix builds."""
+    if rank is None:
+        _, _, rank = retrieve(text, gallery, labels, k, **kw)
+    red = ops.rank_metrics(rank.contiguous(), k).cpu().numpy()
+    return metrics_from_rank_counts(red[:k], red[k], rank.numel())
 
 
 def compute_metrics(dataset, embeddings_dict, print_results=False, write_nearest=True):

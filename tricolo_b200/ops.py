@@ -26,6 +26,16 @@ def _rows_2d(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _dense16(t: torch.Tensor) -> torch.Tensor:
+    """The retrieval kernels build their TMA maps with row stride == dim: a strided 16-bit view (e.g. a column slice of
+    an interleaved buffer) is copied to a dense matrix instead of being silently misread."""
+    if t.dim() != 2:
+        raise ValueError(f"expected a [rows, dim] matrix, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) != t.shape[1] or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t
+
+
 def _z_stride(zs) -> int:
     """Common row stride (elements) of a set of 16-bit operand matrices (contiguous or strided views)."""
     st = zs[0].stride(0)
@@ -392,6 +402,7 @@ def sim_gemm(q16: torch.Tensor, g16: torch.Tensor, out: Optional[torch.Tensor] =
     dev = L.require_cuda(q16, g16)
     if q16.dtype != g16.dtype or q16.dtype not in (torch.float16, torch.bfloat16):
         raise TypeError("sim_gemm: operands must both be float16 or both bfloat16")
+    q16, g16 = _dense16(q16), _dense16(g16)
     n_q, dim = q16.shape
     n_g = g16.shape[0]
     ld = (n_g + 31) // 32 * 32
@@ -408,8 +419,9 @@ def topk_rank(s: torch.Tensor, n_g: int, k: int, labels: torch.Tensor, idx_base:
     """K4. Returns (topk_val [Q,k] f32, topk_idx [Q,k] i32, gt_sim [Q] f32, n_before [Q] i32)."""
     dev = L.require_cuda(s, labels)
     n_q = s.shape[0]
-    if labels.dtype != torch.int64:
-        labels = labels.to(torch.int64)
+    labels = labels.to(torch.int64).contiguous()
+    if s.stride(1) != 1:
+        raise ValueError("topk_rank: similarity rows must have unit column stride")
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     gt = torch.empty((n_q,), dtype=torch.float32, device=dev) if gt_sim_in is None else gt_sim_in
@@ -442,10 +454,28 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
     return val, idx
 
 
+_RM_WS = {}
+
+
+def rank_metrics(rank: torch.Tensor, k: int) -> torch.Tensor:
+    """K5: device tensor of k+1 doubles - #{rank == j+1} for j < k, then sum 1/rank (fp64, fixed order)."""
+    dev = L.require_cuda(rank)
+    if rank.dtype != torch.int32 or not rank.is_contiguous():
+        raise TypeError("rank_metrics: contiguous int32 ranks expected")
+    ws = _RM_WS.get(dev)
+    if ws is None:
+        ws = _RM_WS[dev] = torch.zeros((int(LIB.tcl_rank_metrics_workspace_bytes()),), dtype=torch.uint8, device=dev)
+    out = torch.empty((k + 1,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(LIB.tcl_rank_metrics(L.ptr(rank), rank.numel(), k, L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev)))
+    return out
+
+
 def gt_sim_mma(q16: torch.Tensor, g16: torch.Tensor, labels: torch.Tensor, idx_base: int = 0) -> torch.Tensor:
     """Ground-truth similarity q . g[label - idx_base] produced by the same MMA sequence as the GEMM
     (0 where the label is outside this gallery shard)."""
     dev = L.require_cuda(q16, g16, labels)
+    q16, g16, labels = _dense16(q16), _dense16(g16), labels.to(torch.int64).contiguous()
     n_q, dim = q16.shape
     op = F16 if q16.dtype == torch.float16 else BF16
     out = torch.empty((n_q,), dtype=torch.float32, device=dev)
@@ -462,6 +492,7 @@ def sim_topk_fused(q16: torch.Tensor, g16: torch.Tensor, k: int, labels: torch.T
     dev = L.require_cuda(q16, g16, labels, gt_sim)
     if q16.dtype != g16.dtype or q16.dtype not in (torch.float16, torch.bfloat16):
         raise TypeError("sim_topk_fused: operands must both be float16 or both bfloat16")
+    q16, g16, labels, gt_sim = _dense16(q16), _dense16(g16), labels.to(torch.int64).contiguous(), gt_sim.contiguous()
     n_q, dim = q16.shape
     n_g = g16.shape[0]
     op = F16 if q16.dtype == torch.float16 else BF16
