@@ -101,6 +101,7 @@ struct NormBwdParams {
   int64_t job_tile_base[3];
   int unit_tiles[3];
   int n_clusters;
+  int unit_shift;  // log2 of the rows of one unit: 7 (one 128-row block; 0 means 7) or 8 (CTA-pair gradient GEMM)
 };
 // normalise backward of the sharded shared-G form (ntxent_bwd_g.cu): a tensor's gradient is the sum of its row-side
 // partials (local slots, one per tile range that touched the row's unit) and its column-side partials (receive

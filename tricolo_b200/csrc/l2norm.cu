@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(NormBwdParams pr, int64
   const int64_t split_stride = (pr.split_rows ? pr.split_rows : rows) * static_cast<int64_t>(dim);
   if (pr.n_clusters > 0) {
     // persistent gradient kernel: one partial per tile range that touches this row's 128-row unit
-    const int64_t u0 = pr.job_tile_base[blockIdx.y] + (row >> 7) * pr.unit_tiles[blockIdx.y];
+    const int64_t u0 = pr.job_tile_base[blockIdx.y] + (row >> (pr.unit_shift ? pr.unit_shift : 7)) * pr.unit_tiles[blockIdx.y];
     n_split = pc_range_of(pr.total_tiles, u0 + pr.unit_tiles[blockIdx.y] - 1, pr.n_clusters) -
               pc_range_of(pr.total_tiles, u0, pr.n_clusters) + 1;
   }

@@ -382,6 +382,7 @@ struct GBSegDev {
 struct GBJobDev {
   GBSegDev seg[2];
   int n_seg;
+  int n_rowblocks;   // 128-row blocks of the output (the CTA-pair kernel pads an odd count)
   int k_tiles;       // 128-wide K tiles per segment
   int dst_first;     // first tensor map of this job in GBParams::tm_dst
   int owner_rows;    // > 0: output rows are owned in blocks of owner_rows by successive ranks (tm_dst[dst_first + owner])
@@ -673,6 +674,273 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
   }
 }
 
+// =================================================================================================================
+// kernel B, CTA-pair form (cta_group::2): two adjacent 128-row blocks of a job as ONE M = 256 MMA over two SMs
+// =================================================================================================================
+// The one-SM kernel above ingests 160 KB of operands per 16.8 MFLOP tile (A 32 KB + B 128 KB): 105 flop per byte, and
+// the L2 -> SM fabric delivers ~12 TB/s over the whole chip, i.e. 1.29 PFLOP/s - exactly what it measures.  As a CTA
+// pair the two row blocks share the B operand: tcgen05.mma.cta_group::2 (M = 256, N = 256) takes each CTA's own 128 A
+// rows from that CTA's shared memory and HALF of the N columns of B from each: CTA r loads dims [256 c + 128 r, +128)
+// of the other operand, 64 KB instead of 128 KB per tile - 175 flop per byte, above the tensor roof.
+//   * only the leader (cluster rank 0) issues MMAs; its `full` barriers count the TMA bytes of BOTH CTAs (the peer's
+//     loads name the leader's barrier: cp.async.bulk.tensor ... cta_group::2); tcgen05.commit multicasts to both CTAs'
+//     `empty` / `acc_full` barriers; the read-out warps of both CTAs arrive on the leader's `acc_empty`;
+//   * a unit = (job, pair of row blocks), T tiles; the flat tile sequence is cut into one range per CLUSTER; each CTA
+//     drains its own 128 rows of the accumulator as above.
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // same shared-memory offset in the even (leader) CTA of the pair
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_result_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0,
+                                                int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct GB2Walk {  // as GBWalk with one range per cluster; pc.ib = first row block of the pair
+  int64_t cursor, end;
+  int c, n;
+  __device__ explicit GB2Walk(const GBParams& P) {
+    n = static_cast<int>(gridDim.x >> 1);
+    c = static_cast<int>(blockIdx.x >> 1);
+    const int64_t total = P.job_tile_base[GB_MAX_JOBS];
+    cursor = pc_range_lo(total, c, n);
+    end = pc_range_lo(total, c + 1, n);
+  }
+  __device__ bool next(const GBParams& P, GBPiece& pc) {
+    if (cursor >= end) return false;
+    int j = 0;
+    while (j + 1 < GB_MAX_JOBS && cursor >= P.job_tile_base[j + 1]) ++j;
+    const int T = P.unit_tiles[j];
+    const int64_t local = cursor - P.job_tile_base[j];
+    pc.job = j;
+    pc.ib = 2 * static_cast<int>(local / T);
+    pc.dh = 0;
+    pc.ta = static_cast<int>(local % T);
+    const int64_t left = end - cursor;
+    pc.tb = left < T - pc.ta ? pc.ta + static_cast<int>(left) : T;
+    pc.slot = c - pc_range_of(P.job_tile_base[GB_MAX_JOBS], cursor - pc.ta, n);
+    cursor += pc.tb - pc.ta;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __grid_constant__ GBParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + GBSmem::bar_off;
+  auto g_full = [&](int s) { return bars + 8u * s; };                                 // leader's
+  auto g_empty = [&](int s) { return bars + 8u * (GB_GSLOTS + s); };                  // per CTA (multicast commit)
+  auto c_full = [&](int s) { return bars + 8u * (2 * GB_GSLOTS + s); };               // leader's
+  auto c_empty = [&](int s) { return bars + 8u * (2 * GB_GSLOTS + GB_CSTAGES + s); };  // per CTA
+  const uint32_t acc_full_bar = bars + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES);         // per CTA (multicast commit)
+  const uint32_t acc_empty_bar = acc_full_bar + 8u;                                   // leader's: read-out warps of both CTAs
+  const uint32_t tmem_slot = acc_full_bar + 32u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      base_ptr + GBSmem::bar_off + 8u * (2 * GB_GSLOTS + 2 * GB_CSTAGES) + 32u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int n_chunk = (P.dim + 255) / 256;
+  const uint32_t g_smem = base + GBSmem::g_off;
+  const uint32_t ring = base + GBSmem::ring_off;
+
+  if (warp == 0 && elect_one()) {
+    for (int j = 0; j < GB_MAX_JOBS; ++j) {
+      if (P.unit_tiles[j] == 0) continue;
+      for (int s = 0; s < P.job[j].n_seg; ++s) {
+        tma_prefetch_desc(&P.job[j].seg[s].tm_g);
+        tma_prefetch_desc(&P.job[j].seg[s].tm_other);
+      }
+    }
+    for (int s = 0; s < GB_GSLOTS; ++s) {
+      mbar_init(g_full(s), 1);
+      mbar_init(g_empty(s), 1);
+    }
+    for (int s = 0; s < GB_CSTAGES; ++s) {
+      mbar_init(c_full(s), 1);
+      mbar_init(c_empty(s), 1);
+    }
+    mbar_init(acc_full_bar, 1);
+    mbar_init(acc_empty_bar, 2 * GB_DRAIN_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any TMA byte or commit may reach them
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  GB2Walk walk(P);
+  GBPiece pc;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA warp (both CTAs): own G tile, own half of B
+    if (elect_one()) {
+      uint32_t it = 0, tg = 0;
+      while (walk.next(P, pc)) {
+        const GBJobDev& J = P.job[pc.job];
+        const int i0 = (pc.ib + static_cast<int>(crank)) * BW_BM;  // this CTA's row block
+        for (int t = pc.ta; t < pc.tb; ++t, ++tg) {
+          const GBSegDev& sg = J.seg[t / J.k_tiles];
+          const int k0 = (t % J.k_tiles) * BW_BN;
+          const int gsl = tg % GB_GSLOTS;
+          mbar_wait(g_empty(gsl), ((tg / GB_GSLOTS) & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(g_full(gsl), 2 * GB_SLOT);  // both CTAs' G tiles
+          if (!sg.col_side) tma_load_3d_2sm(g_smem + gsl * GB_SLOT, &sg.tm_g, g_full(gsl) & kPeerBitMask, 0, i0, k0 >> 6);
+          else tma_load_3d_2sm(g_smem + gsl * GB_SLOT, &sg.tm_g, g_full(gsl) & kPeerBitMask, 0, k0, i0 >> 6);
+          for (int c = 0; c < n_chunk; ++c, ++it) {
+            const int s = it % GB_CSTAGES;
+            mbar_wait(c_empty(s), ((it / GB_CSTAGES) & 1) ^ 1);
+            if (leader) mbar_arrive_expect_tx(c_full(s), 2 * GB_SLOT);
+            // [2 groups of 64 dims][128 k rows][128 B]: dims [256 c + 128 rank, +128) of the tile's 128 other rows
+            tma_load_3d_2sm(ring + s * GB_SLOT, &sg.tm_other, c_full(s) & kPeerBitMask, 0, k0, (c * 256 + static_cast<int>(crank) * 128) >> 6);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- gradient MMAs (leader only)
+    if (leader && elect_one()) {
+      uint32_t it = 0, tg = 0, piece = 0;
+      while (walk.next(P, pc)) {
+        const GBJobDev& J = P.job[pc.job];
+        mbar_wait_cluster(acc_empty_bar, (piece & 1) ^ 1);  // both CTAs' read-outs of the previous piece are done
+        tc_fence_after();
+        for (int t = pc.ta; t < pc.tb; ++t, ++tg) {
+          const bool col_side = J.seg[t / J.k_tiles].col_side != 0;
+          const uint32_t idesc = col_side ? P.idesc_col : P.idesc_row;
+          const int gsl = tg % GB_GSLOTS;
+          mbar_wait(g_full(gsl), (tg / GB_GSLOTS) & 1);
+          tc_fence_after();
+          for (int c = 0; c < n_chunk; ++c, ++it) {
+            const int s = it % GB_CSTAGES;
+            mbar_wait(c_full(s), (it / GB_CSTAGES) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kb2 = 0; kb2 < 2; ++kb2) {
+              const uint32_t a_addr = g_smem + gsl * GB_SLOT + kb2 * (col_side ? 8192 : BW_KB_BYTES);
+              const uint64_t ad = col_side ? umma_desc_mn_sw128(a_addr, BW_KB_BYTES) : umma_desc_k_sw128(a_addr);
+              const uint32_t a_step = col_side ? 128u : 2u;
+              const uint64_t bd = umma_desc_mn_sw128(ring + s * GB_SLOT + kb2 * 8192, BW_KB_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BW_BK / 16; ++kk)
+                tc_mma_f16_2sm(tmem + c * 256, ad + a_step * kk, bd + 128 * kk, idesc, ((t - pc.ta) | kb2 | kk) != 0);
+            }
+            tc_commit_2sm(c_empty(s), 0x3);
+          }
+          tc_commit_2sm(g_empty(gsl), 0x3);
+        }
+        tc_commit_2sm(acc_full_bar, 0x3);
+        ++piece;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- accumulator read-out (8 warps per CTA)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t stg = base + GBSmem::drain_off + static_cast<uint32_t>(warp - 2) * GB_DRAIN_BYTES;
+    uint8_t* stg_ptr = base_ptr + GBSmem::drain_off + (warp - 2) * GB_DRAIN_BYTES;
+    const uint32_t acc_empty_leader = map_to_peer(acc_empty_bar, 0u);
+    uint32_t piece = 0;
+    while (walk.next(P, pc)) {
+      const GBJobDev& J = P.job[pc.job];
+      mbar_wait(acc_full_bar, piece & 1);
+      tc_fence_after();
+      const int ib = pc.ib + static_cast<int>(crank);
+      const bool live = ib < J.n_rowblocks;  // an odd block count leaves the last pair's second CTA without rows
+      int owner = 0, rin = ib * BW_BM;
+      if (J.owner_rows > 0) {
+        owner = rin / J.owner_rows;
+        rin -= owner * J.owner_rows;
+      }
+      const CUtensorMap* tm = &P.tm_dst[J.dst_first + (live ? owner : 0)];
+      const int row0 = J.src_row_base + pc.slot * J.slot_rows + rin + q * 32;
+#pragma unroll 1
+      for (int cc = 0; cc < 8 && live; ++cc) {
+        const int col = half * 256 + cc * 32;
+        if (col >= P.dim) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, col), v);
+        tc_wait_ld();
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        uint8_t* rowp = stg_ptr + lane * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+          *reinterpret_cast<uint4*>(rowp + ((c16 ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * c16], v[4 * c16 + 1], v[4 * c16 + 2], v[4 * c16 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm, stg, col, row0);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(acc_empty_bar);
+        else mbar_arrive_remote(acc_empty_leader);
+      }
+      ++piece;
+    }
+    if (lane == 0) {
+      bulk_wait_all();
+      fence_proxy_async_generic();
+      __threadfence_system();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves while the other may still signal its barriers / read its shared memory
+  if (warp == 1) tmem_dealloc_2sm(tmem, 512);
+  if (P.world > 0 && threadIdx.x == 0) {
+    uint32_t* sy = P.sync[P.rank];
+    const uint32_t e = ld_relaxed_u32(sy + ShardSync::kBwdEpoch) + 1u;
+    __threadfence_system();
+    if (atomicAdd(sy + ShardSync::kGemmDone, 1u) + 1u == gridDim.x) {
+      sy[ShardSync::kGemmDone] = 0u;
+      __threadfence_system();
+      for (int p = 0; p < P.world; ++p) st_release_sys_u32(P.sync[p] + ShardSync::kGrads + P.rank, e);
+      *reinterpret_cast<volatile uint32_t*>(sy + ShardSync::kBwdEpoch) = e;
+    }
+  }
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------------
@@ -720,6 +988,33 @@ static int launch_ggemm(const GBParams& B, int n_ctas, cudaStream_t st) {
   ntxent_ggemm_kernel<<<static_cast<unsigned>(n_ctas), GB_THREADS, smem, st>>>(B);
   prof_end(TCL_K_NTXENT_BWD, st);
   TCL_CHECK_CUDA(cudaGetLastError());
+  return TCL_OK;
+}
+
+// TRICOLO_B200_GGEMM=1sm keeps the one-SM gradient GEMM kernel; default: the CTA-pair (cta_group::2) kernel
+static bool ggemm_2sm_enabled() {
+  const char* e = getenv("TRICOLO_B200_GGEMM");
+  return !(e && !strcmp(e, "1sm"));
+}
+
+static int launch_ggemm2(const GBParams& B, int n_clusters, cudaStream_t st) {
+  const int smem = static_cast<int>(GBSmem::total);
+  if (int e = ensure_dyn_smem(ntxent_ggemm2_kernel, smem)) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * static_cast<unsigned>(n_clusters), 1, 1);
+  cfg.blockDim = dim3(GB_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_begin(TCL_K_NTXENT_BWD, st);
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_ggemm2_kernel, B));
+  prof_end(TCL_K_NTXENT_BWD, st);
   return TCL_OK;
 }
 
@@ -785,6 +1080,8 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   memset(&B, 0, sizeof(B));
   NormBwdParams N;
   memset(&N, 0, sizeof(N));
+  const bool two_sm = ggemm_2sm_enabled();  // CTA-pair kernel: a unit is a PAIR of 128-row blocks
+  const int n_units = two_sm ? (n_iblocks + 1) / 2 : n_iblocks;
   int n_jobs = 0;
   for (int m = 0; m < a.n_tensors; ++m) {
     if (!a.need_grad[m]) continue;
@@ -797,18 +1094,21 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
       const int o = S.col_side ? a.pair_row[p] : a.pair_col[p];
       uint16_t* gp = g_mat + static_cast<size_t>(pair_slot[p]) * batch * ld_g;
       if (int e = make_tmap_3d_16bit(&S.tm_g, gp, batch, ld_g / 64, ld_g, BW_BM, 2)) return e;
-      if (int e = make_tmap_3d_16bit(&S.tm_other, a.z[o], batch, dim / 64, dim, 64, 4)) return e;
+      // one-SM kernel: stage = 64 k rows x 256 dims; CTA pair: stage = 128 k rows x this CTA's 128 dims
+      if (int e = make_tmap_3d_16bit(&S.tm_other, a.z[o], batch, dim / 64, dim, ggemm_2sm_enabled() ? 128 : 64,
+                                     ggemm_2sm_enabled() ? 2 : 4)) return e;
     }
     if (J.n_seg == 0) continue;
     float* gpart = gbase + static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self_pad * dim;
     if (int e = make_tmap_2d_f32(&B.tm_dst[n_jobs], gpart, static_cast<uint64_t>(kBwdMaxSplit) * n_self_pad, dim, 32, 32)) return e;
     J.k_tiles = n_jtiles;
+    J.n_rowblocks = n_iblocks;
     J.dst_first = n_jobs;
     J.owner_rows = 0;
     J.slot_rows = n_self_pad;
     J.src_row_base = 0;
     B.unit_tiles[n_jobs] = J.n_seg * n_jtiles;
-    B.job_tile_base[n_jobs + 1] = B.job_tile_base[n_jobs] + static_cast<int64_t>(n_iblocks) * B.unit_tiles[n_jobs];
+    B.job_tile_base[n_jobs + 1] = B.job_tile_base[n_jobs] + static_cast<int64_t>(n_units) * B.unit_tiles[n_jobs];
     N.job[n_jobs].x = a.x[m];
     N.job[n_jobs].inv_norm = a.inv_norm + static_cast<size_t>(m) * batch;
     N.job[n_jobs].gpart = gpart;
@@ -819,18 +1119,19 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   for (int j = n_jobs; j < GB_MAX_JOBS; ++j) B.job_tile_base[j + 1] = B.job_tile_base[n_jobs];
   B.dim = static_cast<int>(dim);
   B.n_dsplit = 1;  // one GPU: long units, G streams from HBM - reading it once per 256-column half would double that
-  B.idesc_row = umma_idesc_f16(BW_BM, 256, a.op_format) | (1u << 16);
+  B.idesc_row = umma_idesc_f16(two_sm ? 256 : BW_BM, 256, a.op_format) | (1u << 16);
   B.idesc_col = B.idesc_row | (1u << 15);
   const int64_t total_b = B.job_tile_base[GB_MAX_JOBS];
   int t_max = 1;
   for (int j = 0; j < n_jobs; ++j) t_max = B.unit_tiles[j] > t_max ? B.unit_tiles[j] : t_max;
-  int64_t ctas_b = n_sm;
+  int64_t ctas_b = two_sm ? n_sm / 2 : n_sm;  // tile ranges: one per CTA, or one per CTA pair
   if (ctas_b > total_b) ctas_b = total_b;
   const int64_t cap = (kBwdMaxSplit - 1) * total_b / t_max;
   if (ctas_b > cap) ctas_b = cap;
   if (ctas_b < 1) ctas_b = 1;
-  if (int e = launch_ggemm(B, static_cast<int>(ctas_b), st)) return e;
+  if (int e = two_sm ? launch_ggemm2(B, static_cast<int>(ctas_b), st) : launch_ggemm(B, static_cast<int>(ctas_b), st)) return e;
   N.n_clusters = static_cast<int>(ctas_b);
+  N.unit_shift = two_sm ? 8 : 7;
   N.split_rows = n_self_pad;
   N.total_tiles = total_b;
   for (int j = 0; j < TCL_MAX_TENSORS; ++j) {

@@ -169,13 +169,13 @@ def _fused_push_enabled() -> bool:
 
 def _sharded_g_enabled(b_loc: int = 1 << 30) -> bool:
     """Backward form of a sharded step: TRICOLO_B200_SHARDED_BWD=sharedg|pc forces one.  Default: the sharded shared-G
-    form (6 b B D, in-kernel reduce-scatter) from 2048 rows per rank on, the directional kernel (8 b B D, no exchange)
-    below - measured at B=8192: N=2 0.439 vs 0.470 ms per step, N=8 0.246 vs 0.217 (at 1024 rows per rank the 29 MB of
-    fp32 partials per rank and the per-kernel fixed costs outweigh the saved recompute)."""
+    form (6 b B D, in-kernel reduce-scatter) from 4096 rows per rank on, the directional kernel (8 b B D, no exchange)
+    below - measured at B=8192: N=2 0.439 vs 0.470 ms per step, N=4 0.305 vs 0.28, N=8 0.246 vs 0.217 (with few rows per rank the
+    29 MB of fp32 partials per rank and the per-kernel fixed costs outweigh the saved recompute)."""
     e = os.environ.get("TRICOLO_B200_SHARDED_BWD", "")
     if e in ("sharedg", "pc"):
         return e == "sharedg"
-    return b_loc >= 2048
+    return b_loc >= 4096
 
 
 def _world(group=None):
