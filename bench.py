@@ -667,9 +667,11 @@ def bench_retrieval(args, rank, world, dev, peaks, timed, max_over_ranks, retrie
                   "d2h_bytes_per_step": int(nq_e * (5 * 4 + 4)),
                   "api": "tricolo_b200.evaluation.retrieve / distributed.sharded_retrieve on pinned fp32 host arrays + "
                          "retrieve_metrics (K5 reduction on the device, metric dict on the host; wall clock)"}
-    # two-kernel form on a slice (bounded: block x G_loc x 4 bytes of fp32 similarities per block)
-    block = 8192
-    nq2 = min(n_q, 16 * block)
+    # two-kernel form on a slice (bounded: block x G_loc x 4 bytes of fp32 similarities per block, ~4 GB)
+    from tricolo_b200.evaluation.eval_retrieval import two_kernel_block_queries
+
+    block = two_kernel_block_queries(g_loc)
+    nq2 = min(n_q, max(4 * block, 131072))
     run(False, nq2, block)
     _lib.profile_enable(True)
     t2 = timed(lambda: run(False, nq2, block), steps, 0)

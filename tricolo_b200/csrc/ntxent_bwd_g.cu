@@ -811,6 +811,10 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
     // ---------------------------------------------------------------- TMA warp (both CTAs): own G tile, own half of B
     if (elect_one()) {
       uint32_t it = 0, tg = 0;
+      GT_DECL
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long gt_w0 = clock64();
+#endif
       while (walk.next(P, pc)) {
         const GBJobDev& J = P.job[pc.job];
         const int i0 = (pc.ib + static_cast<int>(crank)) * BW_BM;  // this CTA's row block
@@ -818,37 +822,54 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
           const GBSegDev& sg = J.seg[t / J.k_tiles];
           const int k0 = (t % J.k_tiles) * BW_BN;
           const int gsl = tg % GB_GSLOTS;
+          GT_BEGIN();
           mbar_wait(g_empty(gsl), ((tg / GB_GSLOTS) & 1) ^ 1);
+          GT_END(0);
           if (leader) mbar_arrive_expect_tx(g_full(gsl), 2 * GB_SLOT);  // both CTAs' G tiles
           if (!sg.col_side) tma_load_3d_2sm(g_smem + gsl * GB_SLOT, &sg.tm_g, g_full(gsl) & kPeerBitMask, 0, i0, k0 >> 6);
           else tma_load_3d_2sm(g_smem + gsl * GB_SLOT, &sg.tm_g, g_full(gsl) & kPeerBitMask, 0, k0, i0 >> 6);
           for (int c = 0; c < n_chunk; ++c, ++it) {
             const int s = it % GB_CSTAGES;
+            GT_BEGIN();
             mbar_wait(c_empty(s), ((it / GB_CSTAGES) & 1) ^ 1);
+            GT_END(1);
             if (leader) mbar_arrive_expect_tx(c_full(s), 2 * GB_SLOT);
             // [2 groups of 64 dims][128 k rows][128 B]: dims [256 c + 128 rank, +128) of the tile's 128 other rows
             tma_load_3d_2sm(ring + s * GB_SLOT, &sg.tm_other, c_full(s) & kPeerBitMask, 0, k0, (c * 256 + static_cast<int>(crank) * 128) >> 6);
           }
         }
       }
+#ifdef TCL_PAIR_TRACE
+      GT_ADD(2, clock64() - gt_w0);
+#endif
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- gradient MMAs (leader only)
     if (leader && elect_one()) {
       uint32_t it = 0, tg = 0, piece = 0;
+      GT_DECL
+#ifdef TCL_PAIR_TRACE
+      const unsigned long long gt_w0 = clock64();
+#endif
       while (walk.next(P, pc)) {
         const GBJobDev& J = P.job[pc.job];
+        GT_BEGIN();
         mbar_wait_cluster(acc_empty_bar, (piece & 1) ^ 1);  // both CTAs' read-outs of the previous piece are done
+        GT_END(3);
         tc_fence_after();
         for (int t = pc.ta; t < pc.tb; ++t, ++tg) {
           const bool col_side = J.seg[t / J.k_tiles].col_side != 0;
           const uint32_t idesc = col_side ? P.idesc_col : P.idesc_row;
           const int gsl = tg % GB_GSLOTS;
+          GT_BEGIN();
           mbar_wait(g_full(gsl), (tg / GB_GSLOTS) & 1);
+          GT_END(4);
           tc_fence_after();
           for (int c = 0; c < n_chunk; ++c, ++it) {
             const int s = it % GB_CSTAGES;
+            GT_BEGIN();
             mbar_wait(c_full(s), (it / GB_CSTAGES) & 1);
+            GT_END(5);
             tc_fence_after();
 #pragma unroll
             for (int kb2 = 0; kb2 < 2; ++kb2) {
@@ -867,6 +888,11 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
         tc_commit_2sm(acc_full_bar, 0x3);
         ++piece;
       }
+#ifdef TCL_PAIR_TRACE
+      GT_ADD(6, clock64() - gt_w0);
+      GT_ADD(10, tg);
+      GT_ADD(11, piece);
+#endif
     }
   } else {
     // ---------------------------------------------------------------- accumulator read-out (8 warps per CTA)

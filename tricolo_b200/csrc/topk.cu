@@ -77,31 +77,51 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(
   const int n_vec = n_g >> 2;  // full float4 groups
   const float4* row4 = reinterpret_cast<const float4*>(row);
   int g4 = lane;
-  // 4 independent 16-byte loads in flight per lane
-  for (; g4 + 96 < n_vec; g4 += 128) {
-    float4 a = __ldg(row4 + g4);
-    float4 b = __ldg(row4 + g4 + 32);
-    float4 c = __ldg(row4 + g4 + 64);
-    float4 d = __ldg(row4 + g4 + 96);
-    const float vals[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w,
-                            c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+  // software-pipelined loads (the next 4 x 16 bytes per lane are requested before the current 16 values are consumed)
+  // and a warp-wide entry threshold: the largest k-th value of any lane's list.  That lane alone holds k earlier candidates
+  // that are >= thr, all with smaller column numbers than anything still to come (columns grow from iteration to
+  // iteration), so a value <= thr can no longer enter the row's top-k.  Without it every lane keeps inserting into its
+  // own list (the k-th best of 1/32 of the row is a weak bar): hundreds of divergent insertion passes per row, ~50 us
+  // of a warp's time, whatever the row length.
+  float thr = -FLT_MAX;
+  auto consume = [&](const float4& a, const float4& b, const float4& c, const float4& d, int base4) {
+    const float vals[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const int col = (g4 + (u >> 2) * 32) * 4 + (u & 3);
+      const int col = (base4 + (u >> 2) * 32) * 4 + (u & 3);
       const float x = vals[u];
       cnt += (x > s_gt) || (x == s_gt && col < gt_cut);
-      top.push(x, col);
+      if (x > thr) top.push(x, col);
+    }
+  };
+  // warp-uniform trip count (the threshold update shuffles over the full warp): whole 512-column chunks only
+  const int n_full = n_vec >> 7;  // chunks of 128 float4 in which every lane has all four loads
+  if (n_full > 0) {
+    float4 a = __ldcs(row4 + g4), b = __ldcs(row4 + g4 + 32), c = __ldcs(row4 + g4 + 64), d = __ldcs(row4 + g4 + 96);
+    for (int ch = 0; ch < n_full; ++ch, g4 += 128) {
+      float4 na = a, nb = b, nc = c, nd = d;
+      if (ch + 1 < n_full) {
+        na = __ldcs(row4 + g4 + 128); nb = __ldcs(row4 + g4 + 160); nc = __ldcs(row4 + g4 + 192); nd = __ldcs(row4 + g4 + 224);
+      }
+      if ((ch & 3) == 0) {  // refresh the threshold every 2048 columns
+        float t = top.v[K - 1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+        thr = t;
+      }
+      consume(a, b, c, d, g4);
+      a = na; b = nb; c = nc; d = nd;
     }
   }
   for (; g4 < n_vec; g4 += 32) {
-    float4 a = __ldg(row4 + g4);
+    float4 a = __ldcs(row4 + g4);
     const float vals[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int col = g4 * 4 + u;
       const float x = vals[u];
       cnt += (x > s_gt) || (x == s_gt && col < gt_cut);
-      top.push(x, col);
+      if (x > thr) top.push(x, col);
     }
   }
   {  // scalar tail (n_g % 4 columns); still ascending per lane: only lane 31 .. no: use lane order

@@ -370,7 +370,9 @@ def sharded_retrieve(text: torch.Tensor, gallery_shard: torch.Tensor, labels: to
     if fused is None:
         fused = dim % 64 == 0 and 64 <= dim <= 512 and k <= 16
     if block_queries is None:
-        block_queries = 148 * 128 * 8 if fused else 8192
+        from .evaluation.eval_retrieval import two_kernel_block_queries
+
+        block_queries = 148 * 128 * 8 if fused else two_kernel_block_queries(n_g)
     labels = labels.to(torch.int64)
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)

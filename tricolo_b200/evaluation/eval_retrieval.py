@@ -27,7 +27,16 @@ import torch
 from .. import ops
 
 OPERAND_FORMAT = ops.BF16  # raw, un-normalised embeddings: bf16 keeps fp32's range (BASELINE north_star)
-BLOCK_QUERIES = 65536      # queries per GEMM/top-k chunk of the fast entry
+BLOCK_QUERIES = 65536      # upper bound of the queries per GEMM/top-k chunk of the two-kernel form
+
+
+def two_kernel_block_queries(n_gallery: int) -> int:
+    """Queries per chunk of the two-kernel form: the fp32 similarity block is kept around 4 GB, so that a top-k launch
+    is several waves of rows even for a small gallery shard (at 25 000 shapes per rank a block of 8192 queries is ONE
+    wave of one-row warps: every warp streams, then every warp sorts, and HBM idles in between - 58 % of peak; with
+    32768+ rows per launch the phases of different waves overlap)."""
+    ld = (n_gallery + 31) // 32 * 32
+    return max(8192, min(BLOCK_QUERIES, (4 << 30) // (4 * ld) // 1024 * 1024))
 
 
 def construct_embeddings_matrix(dataset, embeddings_dict, model_id_to_label=None, label_to_model_id=None):
@@ -157,6 +166,9 @@ def metrics_from_ranks(indices: np.ndarray, rank: np.ndarray, labels: np.ndarray
     """Host fp64 finalise with the reference's NumPy op order (eval_retrieval.py:161-206)."""
     q = indices.shape[0]
     fit_labels = labels if fit_labels is None else np.asarray(fit_labels)
+    if (np.asarray(indices) < 0).any():  # retrieve() marks the slots a gallery smaller than k cannot fill with -1
+        raise ValueError("metrics: fewer gallery items than n_neighbors (the reference fails on this input too, "
+                         "eval_retrieval.py:175)")
     rel_score = np.equal(fit_labels[indices], labels[:, None]).astype(np.float32)
     num_correct = np.cumsum(rel_score, axis=1, dtype=np.float32)
     num_relevant = np.bincount(fit_labels)[labels]
@@ -242,15 +254,13 @@ def retrieve(text: torch.Tensor, gallery: torch.Tensor, labels: torch.Tensor, k:
     dt = ops.L.op_torch_dtype(operand_format)
     g16 = gallery if gallery.dtype == dt else ops.cast_16bit(gallery, operand_format)
     n_q, n_g, dim = text.shape[0], gallery.shape[0], text.shape[1]
-    if n_g < k:  # the reference's slicing would silently return fewer columns; unfilled slots would carry index -1
-        raise ValueError(f"retrieve: the gallery has {n_g} shapes, fewer than k = {k}")
     dev = text.device
     if fused is None:
         fused = _fusable(dim, k)
     elif fused and not _fusable(dim, k):
         raise ValueError(f"fused retrieval needs dim % 64 == 0, dim <= 512, k <= 16 (got dim={dim}, k={k})")
     if block_queries is None:
-        block_queries = FUSED_BLOCK_QUERIES if fused else BLOCK_QUERIES
+        block_queries = FUSED_BLOCK_QUERIES if fused else two_kernel_block_queries(n_g)
     val = torch.empty((n_q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     rank = torch.empty((n_q,), dtype=torch.int32, device=dev)
