@@ -1,7 +1,8 @@
 """Short drivers for ncu captures.
    ncu ... python profiles/prof_step.py loss [B]        three fwd+bwd steps of the trimodal loss
    ncu ... python profiles/prof_step.py retrieval       two-kernel form: GEMM -> HBM -> top-k (3 blocks of 8192 x 200k)
-   ncu ... python profiles/prof_step.py fused           fused kernel, 18944 queries x 200k (one CTA per SM)"""
+   ncu ... python profiles/prof_step.py fused           fused kernel, 18944 queries x 200k (one CTA per SM)
+   ncu ... python profiles/prof_step.py shard           two-kernel form at one rank's shard of 8: 41984 queries x 25k"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,6 +18,12 @@ if what == "loss":
     for _ in range(3):
         for f in feats: f.grad = None
         trimodal_ntxent(feats, TAU, ALPHA).sum().backward()
+elif what == "shard":
+    g = torch.Generator(device=dev).manual_seed(0)
+    gal = torch.randn(25000, 512, generator=g, device=dev).bfloat16()
+    text = torch.randn(41984, 512, generator=g, device=dev).bfloat16()
+    lab = torch.randint(0, 25000, (41984,), generator=g, device=dev)
+    retrieve(text, gal, lab, 5, fused=False)
 else:
     g = torch.Generator(device=dev).manual_seed(0)
     gal = torch.randn(200000, 512, generator=g, device=dev).bfloat16()

@@ -38,12 +38,26 @@ def launches(path, out):
     out.write("\n")
 
 
+TRAFFIC = {}
+
+
+def _bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
 def full(path, out):
     txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     out.write(f"## ncu --set full: {path.split('/')[-1]}\n\n")
     for r in rows[2:]:
+        try:  # DRAM bytes per launch (first capture of each kernel) for bench.py's roofline.traffic
+            name = r[hdr.index("Kernel Name")].split("(")[0].split("<")[0].replace("void ", "").strip()
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            TRAFFIC.setdefault(name, int(_bytes(r[ir], units[ir]) + _bytes(r[iw], units[iw])))
+        except (ValueError, IndexError):
+            pass
         out.write(f"### `{r[hdr.index('Kernel Name')][:90]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
         for m in METRICS:
             if m in hdr:
@@ -59,4 +73,9 @@ if __name__ == "__main__":
             launches(sys.argv[2], out)
         for rep in sys.argv[3:]:
             full(rep, out)
+    if TRAFFIC:
+        import json
+        TRAFFIC["_source"] = (f"ncu --set full --clock-control none, profiles/{tag}_summary.md (B200, bench shapes); bytes per launch = "
+                              "dram__bytes_read.sum + dram__bytes_write.sum")
+        json.dump(TRAFFIC, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
     print("wrote", f"profiles/{tag}_summary.md")
