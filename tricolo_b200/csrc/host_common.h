@@ -124,6 +124,7 @@ struct NormShParams {
   const float* scales;      // [world] scale of every source rank (receive-buffer header)
   const uint32_t* sync;     // own sync pad: wait for every source's kGrads flag (NULL: the caller ran a barrier)
   int n_ranges, n_dsplit, world, rank, n_slots_col;
+  int unit_shift;  // log2 rows of a unit: 7, or 8 with the CTA-pair gradient GEMM
 };
 int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim, int64_t x_stride,
                               float eps, cudaStream_t st);

@@ -541,13 +541,13 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
   for (int dh = 0; dh < pr.n_dsplit; ++dh) {
     if (jb.row_job >= 0) {
       const int T_ = pr.unit_tiles[jb.row_job];
-      const int64_t u0 = pr.job_tile_base[jb.row_job] + ((row >> 7) * pr.n_dsplit + dh) * T_;
+      const int64_t u0 = pr.job_tile_base[jb.row_job] + ((row >> pr.unit_shift) * pr.n_dsplit + dh) * T_;
       np_row[dh] = pc_range_of(pr.total_tiles, u0 + T_ - 1, pr.n_ranges) - pc_range_of(pr.total_tiles, u0, pr.n_ranges) + 1;
     }
     if (jb.col_job >= 0) {
       const int T_ = pr.unit_tiles[jb.col_job];
       const int64_t grow = static_cast<int64_t>(pr.rank) * rows + row;
-      const int64_t u0 = pr.job_tile_base[jb.col_job] + ((grow >> 7) * pr.n_dsplit + dh) * T_;
+      const int64_t u0 = pr.job_tile_base[jb.col_job] + ((grow >> pr.unit_shift) * pr.n_dsplit + dh) * T_;
       np_col[dh] = pc_range_of(pr.total_tiles, u0 + T_ - 1, pr.n_ranges) - pc_range_of(pr.total_tiles, u0, pr.n_ranges) + 1;
     }
   }

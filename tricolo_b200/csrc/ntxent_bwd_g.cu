@@ -1176,6 +1176,7 @@ struct ShardPlan {
   int n_row_jobs, n_col_jobs;
   int row_tensor[TCL_MAX_TENSORS], col_tensor[TCL_MAX_TENSORS];  // tensor index of each job
   int n_dsplit, n_ctas, n_slots_col;
+  int two_sm;  // CTA-pair gradient GEMM: a unit is a PAIR of 128-row blocks, n_ctas counts clusters (tile ranges)
   int n_iblocks, n_jtiles, n_self_pad;
   int64_t ld_g;
   int64_t job_tile_base[GB_MAX_JOBS + 1];
@@ -1222,6 +1223,8 @@ static int make_shard_plan(ShardPlan* out, int n_tensors, int n_pairs, const int
   const size_t g_bytes = static_cast<size_t>(S.n_gpairs) * b_loc * S.ld_g * 2;
   S.n_dsplit = g_bytes <= (64ull << 20) ? 2 : 1;
   if (const char* e = getenv("TRICOLO_B200_GSPLIT")) S.n_dsplit = atoi(e) == 2 ? 2 : 1;
+  S.two_sm = ggemm_2sm_enabled() && S.n_dsplit == 1 && b_loc % (2 * BW_BM) == 0;
+  const int ush = S.two_sm ? 2 : 1;  // row blocks per unit
   // jobs: column-side first - their drains cross NVLink and should be in flight while the row-side tiles still compute
   for (int pass = 0; pass < 2; ++pass) {
     for (int m = 0; m < n_tensors; ++m) {
@@ -1234,7 +1237,7 @@ static int make_shard_plan(ShardPlan* out, int n_tensors, int n_pairs, const int
       S.job_is_col[j] = pass == 0;
       S.job_tensor[j] = m;
       const int k_tiles = pass == 0 ? S.n_iblocks : S.n_jtiles;
-      const int n_units = (pass == 0 ? S.n_jtiles : S.n_iblocks) * S.n_dsplit;
+      const int n_units = (pass == 0 ? S.n_jtiles : S.n_iblocks) * S.n_dsplit / ush;
       S.unit_tiles[j] = n_seg * k_tiles;
       S.job_tile_base[j + 1] = S.job_tile_base[j] + static_cast<int64_t>(n_units) * S.unit_tiles[j];
       if (pass == 0) S.col_tensor[S.n_col_jobs++] = m; else S.row_tensor[S.n_row_jobs++] = m;
@@ -1243,7 +1246,7 @@ static int make_shard_plan(ShardPlan* out, int n_tensors, int n_pairs, const int
   for (int j = S.n_jobs; j < GB_MAX_JOBS; ++j) S.job_tile_base[j + 1] = S.job_tile_base[S.n_jobs];
   const int64_t total = S.job_tile_base[GB_MAX_JOBS];
   // tile ranges: one per SM of a B200 (every rank must derive the same number: it fixes the partial slots a unit uses)
-  int64_t n = kNumSMsB200;
+  int64_t n = S.two_sm ? kNumSMsB200 / 2 : kNumSMsB200;
   if (const char* e = getenv("TRICOLO_B200_GCTAS")) { const int v = atoi(e); if (v >= 1 && v < n) n = v; }
   if (n > total) n = total;
   int t_max = 1;
@@ -1255,7 +1258,7 @@ static int make_shard_plan(ShardPlan* out, int n_tensors, int n_pairs, const int
   S.n_slots_col = 1;
   for (int j = 0; j < S.n_jobs; ++j) {
     if (!S.job_is_col[j]) continue;
-    const int k = max_pieces(total, S.job_tile_base[j], S.unit_tiles[j], S.n_jtiles * S.n_dsplit, S.n_ctas);
+    const int k = max_pieces(total, S.job_tile_base[j], S.unit_tiles[j], S.n_jtiles * S.n_dsplit / ush, S.n_ctas);
     S.n_slots_col = k > S.n_slots_col ? k : S.n_slots_col;
   }
   TCL_REQUIRE(S.n_slots_col <= kBwdMaxSplit, TCL_ERR_BAD_SHAPE, "bwd_sharded: %d pieces per column unit", S.n_slots_col);
@@ -1317,7 +1320,8 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
   if (S.n_jobs == 0) return TCL_OK;
   int n_sm = 0;
   if (int e = device_sm_count(&n_sm)) return e;
-  TCL_REQUIRE(n_sm >= S.n_ctas, TCL_ERR_BAD_ARCH, "bwd_sharded_gemm: %d SMs, the plan assumes %d", n_sm, S.n_ctas);
+  TCL_REQUIRE(n_sm >= S.n_ctas * (S.two_sm ? 2 : 1), TCL_ERR_BAD_ARCH, "bwd_sharded_gemm: %d SMs, the plan assumes %d", n_sm,
+              S.n_ctas * (S.two_sm ? 2 : 1));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   uint16_t* g_mat = reinterpret_cast<uint16_t*>(ws + S.ws_g);
@@ -1373,13 +1377,15 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
       sg.col_side = col;
       uint16_t* gp = g_mat + S.pair_slot[p] * g_pair;
       if (int e = make_tmap_3d_16bit(&sg.tm_g, gp, b_loc, S.ld_g / 64, S.ld_g, BW_BM, 2)) return e;
+      const uint32_t brows = S.two_sm ? 128 : 64, bchunks = S.two_sm ? 2 : 4;  // stage shape: see launch_bwd_sharedg
       if (col) {  // B operand: the pair's row tensor, this rank's rows (K = local rows)
-        if (int e = make_tmap_3d_16bit(&sg.tm_other, z_loc(pair_row[p]), b_loc, dim / 64, z_row_stride, 64, 4)) return e;
+        if (int e = make_tmap_3d_16bit(&sg.tm_other, z_loc(pair_row[p]), b_loc, dim / 64, z_row_stride, brows, bchunks)) return e;
       } else {    // B operand: the pair's column tensor, all rows (K = global columns of G)
-        if (int e = make_tmap_3d_16bit(&sg.tm_other, z_all[pair_col[p]], b_glob, dim / 64, z_row_stride, 64, 4)) return e;
+        if (int e = make_tmap_3d_16bit(&sg.tm_other, z_all[pair_col[p]], b_glob, dim / 64, z_row_stride, brows, bchunks)) return e;
       }
     }
     J.k_tiles = col ? S.n_iblocks : S.n_jtiles;
+    J.n_rowblocks = col ? S.n_jtiles : S.n_iblocks;
     J.dst_first = n_dst;
     if (col) {
       for (int r = 0; r < world; ++r) {
@@ -1403,7 +1409,7 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
   for (int j = 0; j <= GB_MAX_JOBS; ++j) B.job_tile_base[j] = S.job_tile_base[j];
   B.dim = static_cast<int>(dim);
   B.n_dsplit = S.n_dsplit;
-  B.idesc_row = umma_idesc_f16(BW_BM, 256, op_format) | (1u << 16);
+  B.idesc_row = umma_idesc_f16(S.two_sm ? 256 : BW_BM, 256, op_format) | (1u << 16);
   B.idesc_col = B.idesc_row | (1u << 15);
   if (sync_ptrs != nullptr) {
     for (int r = 0; r < world; ++r) {
@@ -1413,7 +1419,7 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
     B.rank = rank;
     B.world = world;
   }
-  return launch_ggemm(B, S.n_ctas, st);
+  return S.two_sm ? launch_ggemm2(B, S.n_ctas, st) : launch_ggemm(B, S.n_ctas, st);
 }
 
 extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x, int x_dtype, int64_t b_loc,
@@ -1464,6 +1470,7 @@ extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x
   }
   N.total_tiles = S.job_tile_base[GB_MAX_JOBS];
   N.n_ranges = S.n_ctas;
+  N.unit_shift = S.two_sm ? 8 : 7;
   N.n_dsplit = S.n_dsplit;
   N.world = world;
   N.rank = rank;
