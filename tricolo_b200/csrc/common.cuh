@@ -48,6 +48,16 @@ __device__ __forceinline__ float lg2_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still draining.  griddep_launch() (early, in every kernel) lets the successor
+// begin; griddep_wait() blocks until the predecessor grid has completed and its memory operations are visible - it
+// stands between the prologue (barrier init, TMEM allocation, descriptor prefetch: no global data) and the first global
+// access.  Both are no-ops for a normally launched kernel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // system-scope flags in (peer-mapped) global memory: the sharded loss signals "rows landed", "statistics landed",
 // "gradient partials landed" to the other ranks with a release store into THEIR flag word over NVLink and waits on
 // its own words with acquire loads.  Flags carry a step counter (epoch), compared with wrap-safe arithmetic, so they

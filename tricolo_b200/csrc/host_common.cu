@@ -1,6 +1,7 @@
 #include "host_common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -38,6 +39,11 @@ int require_sm100() {
   if (cached[dev] == 2)
     return set_error(TCL_ERR_BAD_ARCH, "tricolo_b200 is sm_100a only (device %d)", dev);
   return TCL_OK;
+}
+
+bool pdl_enabled() {
+  const char* e = getenv("TRICOLO_B200_PDL");
+  return !(e && e[0] == '0');
 }
 
 int ensure_dyn_smem_impl(const void* func, int bytes) {

@@ -40,6 +40,36 @@ inline int ensure_dyn_smem(F* kernel, int bytes) {
   return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
+// Launch configuration with the optional attributes this library uses: a thread-block cluster along x and programmatic
+// dependent launch (TRICOLO_B200_PDL=0 switches the latter off).
+bool pdl_enabled();
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x = 1, bool pdl = true) {
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    int n = 0;
+    if (cluster_x > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = cluster_x;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl && pdl_enabled()) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+  }
+};
+
 // Encode a 2D row-major [rows, cols] 16-bit tensor for TMA tiled loads with a
 // {box_cols, box_rows} box and the 128-byte swizzle.  Out-of-bounds elements
 // are zero-filled (ragged edge tiles rely on this).

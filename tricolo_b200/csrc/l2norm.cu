@@ -174,6 +174,8 @@ __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float (&o)[8]) {
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) l2norm_fwd_push_kernel(const __grid_constant__ PushPack pk, int64_t rows, int dim,
                                                               int64_t x_stride, int64_t z_stride, float eps) {
+  griddep_launch();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // blocks in (row block, tensor) order, tensor fastest: the blocks of one 128-row chunk are scheduled together
   const int tensor = static_cast<int>(blockIdx.x % pk.n_tensors);
@@ -407,6 +409,8 @@ __global__ void __launch_bounds__(256) transpose16_kernel(PtrPack3 pk, int64_t r
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(NormBwdParams pr, int64_t rows, int dim,
                                                          int64_t x_stride, int n_split, float eps) {
+  griddep_launch();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (row >= rows) return;
@@ -504,11 +508,12 @@ int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t 
   TCL_REQUIRE(dim <= 512 && dim % 4 == 0, TCL_ERR_BAD_SHAPE, "normalise backward: dim %d > 512", dim);
   dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_jobs);
   ProfScope prof(TCL_K_L2NORM_BWD, st);
+  LaunchCfg L(grid, dim3(256), 0, st);
   switch (x_dtype) {
-    case TCL_DT_F32: l2norm_bwd_kernel<float><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
-    case TCL_DT_F64: l2norm_bwd_kernel<double><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
-    case TCL_DT_F16: l2norm_bwd_kernel<__half><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
-    case TCL_DT_BF16: l2norm_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, n_split, eps); break;
+    case TCL_DT_F32: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_kernel<float>, pr, rows, dim, x_stride, n_split, eps)); break;
+    case TCL_DT_F64: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_kernel<double>, pr, rows, dim, x_stride, n_split, eps)); break;
+    case TCL_DT_F16: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_kernel<__half>, pr, rows, dim, x_stride, n_split, eps)); break;
+    case TCL_DT_BF16: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_kernel<__nv_bfloat16>, pr, rows, dim, x_stride, n_split, eps)); break;
     default: return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
@@ -523,6 +528,8 @@ int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t 
 template <typename T>
 __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_constant__ NormShParams pr, int64_t rows,
                                                                  int dim, int64_t x_stride, float eps) {
+  griddep_launch();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (pr.sync != nullptr) {  // every source rank's gradient GEMM has completed and its partials have landed here
@@ -611,11 +618,12 @@ int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, i
   TCL_REQUIRE(dim <= 512 && dim % 4 == 0, TCL_ERR_BAD_SHAPE, "normalise backward: dim %d > 512", dim);
   dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_jobs);
   ProfScope prof(TCL_K_L2NORM_BWD, st);
+  LaunchCfg L(grid, dim3(256), 0, st);
   switch (x_dtype) {
-    case TCL_DT_F32: l2norm_bwd_sharded_kernel<float><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
-    case TCL_DT_F64: l2norm_bwd_sharded_kernel<double><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
-    case TCL_DT_F16: l2norm_bwd_sharded_kernel<__half><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
-    case TCL_DT_BF16: l2norm_bwd_sharded_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pr, rows, dim, x_stride, eps); break;
+    case TCL_DT_F32: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<float>, pr, rows, dim, x_stride, eps)); break;
+    case TCL_DT_F64: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<double>, pr, rows, dim, x_stride, eps)); break;
+    case TCL_DT_F16: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<__half>, pr, rows, dim, x_stride, eps)); break;
+    case TCL_DT_BF16: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<__nv_bfloat16>, pr, rows, dim, x_stride, eps)); break;
     default: return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
   }
   TCL_CHECK_CUDA(cudaGetLastError());
@@ -706,10 +714,11 @@ static int launch_push_t(const PushPack& pk, int n_tensors, int64_t rows, int di
                          int op_format, float eps, cudaStream_t st) {
   dim3 grid(static_cast<unsigned>((rows + 7) / 8) * n_tensors);
   ProfScope prof(TCL_K_L2NORM_FWD, st);
+  LaunchCfg L(grid, dim3(256), 0, st);
   if (op_format == TCL_OP_F16)
-    l2norm_fwd_push_kernel<TIn, __half><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_fwd_push_kernel<TIn, __half>, pk, rows, dim, stride, z_stride, eps));
   else
-    l2norm_fwd_push_kernel<TIn, __nv_bfloat16><<<grid, 256, 0, st>>>(pk, rows, dim, stride, z_stride, eps);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_fwd_push_kernel<TIn, __nv_bfloat16>, pk, rows, dim, stride, z_stride, eps));
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }

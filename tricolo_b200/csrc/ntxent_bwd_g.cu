@@ -121,11 +121,13 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_launch();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tmem_x = tmem + GA_XCOL;
+  griddep_wait();
   const int64_t total = static_cast<int64_t>(P.n_pairs) * P.n_iblocks * P.n_jtiles;
   GWalk walk(total, P.n_jtiles);
   int unit, ta, tb;
@@ -496,10 +498,12 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_launch();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  griddep_wait();
   GBWalk walk(P);
   GBPiece pc;
 
@@ -799,11 +803,13 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
     tmem_alloc_2sm(tmem_slot, 512);
     tmem_relinquish_2sm();
   }
+  griddep_launch();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers exist before any TMA byte or commit may reach them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  griddep_wait();
   GB2Walk walk(P);
   GBPiece pc;
 
@@ -1002,7 +1008,8 @@ template <int kOp>
 static int launch_g_kernel(const GAParams& A, int n_ctas, cudaStream_t st) {
   const int smem = static_cast<int>(GASmem::total);
   if (int e = ensure_dyn_smem(ntxent_g_kernel<kOp>, smem)) return e;
-  ntxent_g_kernel<kOp><<<n_ctas, GA_THREADS, smem, st>>>(A);
+  LaunchCfg L(dim3(n_ctas), dim3(GA_THREADS), smem, st);
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, ntxent_g_kernel<kOp>, A));
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
@@ -1011,7 +1018,8 @@ static int launch_ggemm(const GBParams& B, int n_ctas, cudaStream_t st) {
   const int smem = static_cast<int>(GBSmem::total);
   if (int e = ensure_dyn_smem(ntxent_ggemm_kernel, smem)) return e;
   prof_begin(TCL_K_NTXENT_BWD, st);
-  ntxent_ggemm_kernel<<<static_cast<unsigned>(n_ctas), GB_THREADS, smem, st>>>(B);
+  LaunchCfg L(dim3(static_cast<unsigned>(n_ctas)), dim3(GB_THREADS), smem, st);
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, ntxent_ggemm_kernel, B));
   prof_end(TCL_K_NTXENT_BWD, st);
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
@@ -1026,20 +1034,9 @@ static bool ggemm_2sm_enabled() {
 static int launch_ggemm2(const GBParams& B, int n_clusters, cudaStream_t st) {
   const int smem = static_cast<int>(GBSmem::total);
   if (int e = ensure_dyn_smem(ntxent_ggemm2_kernel, smem)) return e;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * static_cast<unsigned>(n_clusters), 1, 1);
-  cfg.blockDim = dim3(GB_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  LaunchCfg L(dim3(2 * static_cast<unsigned>(n_clusters), 1, 1), dim3(GB_THREADS), smem, st, 2);
   prof_begin(TCL_K_NTXENT_BWD, st);
-  TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_ggemm2_kernel, B));
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, ntxent_ggemm2_kernel, B));
   prof_end(TCL_K_NTXENT_BWD, st);
   return TCL_OK;
 }

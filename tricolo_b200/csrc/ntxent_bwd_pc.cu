@@ -189,11 +189,13 @@ __global__ void __launch_bounds__(PC_THREADS, 1) ntxent_bwd_pc_kernel(const __gr
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_launch();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  griddep_wait();
 
   PcWalk walk(P);
   PcPiece pc;
@@ -660,19 +662,8 @@ static int launch_bwd_pc_t(const BwdParams& P, int n_jobs, int* n_clusters_out, 
   if (n < 1) n = 1;
   *n_clusters_out = static_cast<int>(n);
   const int smem = static_cast<int>(PcSmem::total());
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * static_cast<unsigned>(n), 1, 1);
-  cfg.blockDim = dim3(PC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_bwd_pc_kernel<kOp>, P));
+  LaunchCfg L(dim3(2 * static_cast<unsigned>(n), 1, 1), dim3(PC_THREADS), smem, st, 2);
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, ntxent_bwd_pc_kernel<kOp>, P));
   return TCL_OK;
 }
 

@@ -309,10 +309,12 @@ __global__ void __launch_bounds__(FW_THREADS + FW_PUSH_WARPS * 32, 1) ntxent_fwd
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  griddep_launch();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  griddep_wait();  // the normalised operands of the preceding kernel are complete
 
   if (warp == 0) {
     if (elect_one()) {
@@ -486,11 +488,13 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ntxent_fwd_pair_kernel(const __
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_launch();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tmem_x = tmem + F2_XCOL;
+  griddep_wait();
 
   // Prologue: the row block travels global -> ring slots (TMA, 16 KB K-blocks) -> registers -> TMEM.  (Per-thread row
   // loads straight from global took ~12k cycles per CTA: 32 distinct lines per load instruction.)  The ring proper
@@ -665,6 +669,8 @@ namespace tcl {
 __global__ void fwd_reduce_kernel(const float* __restrict__ row_part, const float* __restrict__ col_part,
                                   float* __restrict__ row_sum, float* __restrict__ col_sum, int n_pairs,
                                   int n_rows, int n_cols, int n_jsplit, int n_iblocks) {
+  griddep_launch();
+  griddep_wait();
   const int pair = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_rows) {
@@ -687,6 +693,8 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
     float* __restrict__ col_sum, const float* __restrict__ diag2, float* __restrict__ lse2_row,
     float* __restrict__ lse2_col, float* __restrict__ loss_parts, float* __restrict__ loss,
     const float* __restrict__ row_part, const float* __restrict__ col_part, int n_row_slots, int n_iblocks) {
+  griddep_launch();
+  griddep_wait();
   const int pair = blockIdx.y;
   const int crank = static_cast<int>(cluster_ctarank());
   float* rs = row_sum + static_cast<int64_t>(pair) * n_rows;
@@ -776,6 +784,8 @@ struct StatsPushParams {
   int local_only;  // 1: slot `rank` of the OWN buffer only, no flag: the ranks pull after a barrier (tcl_ntxent_finalize_sharded)
 };
 __global__ void __launch_bounds__(256) fwd_reduce_push_kernel(const __grid_constant__ StatsPushParams P) {
+  griddep_launch();
+  griddep_wait();
   const int pair = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t* sy = P.sync[P.rank];
@@ -818,6 +828,8 @@ __global__ void __launch_bounds__(1024) fwd_finalize_sharded_kernel(
     int b_loc, int b_glob, int n_pairs, int world, float c1, float alpha, const __grid_constant__ StatsSrc src,
     const uint32_t* __restrict__ sync, float* __restrict__ lse2_row, float* __restrict__ lse2_col,
     float* __restrict__ loss) {
+  griddep_launch();
+  griddep_wait();
   const int pair = blockIdx.y;
   const int crank = static_cast<int>(cluster_ctarank());
   if (sync != nullptr) {
@@ -996,20 +1008,9 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
   if (use_pair) {
     const int smem = (int)Fwd2Smem::total;
     if (int e = ensure_dyn_smem(ntxent_fwd_pair_kernel, smem)) return e;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * ((P.n_iblocks + 1) / 2), P.n_jsplit, n_pairs);
-    cfg.blockDim = dim3(F2_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    LaunchCfg L(dim3(2 * ((P.n_iblocks + 1) / 2), P.n_jsplit, n_pairs), dim3(F2_THREADS), smem, st, 2);
     ProfScope prof(TCL_K_NTXENT_FWD, st);
-    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntxent_fwd_pair_kernel, P));
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, ntxent_fwd_pair_kernel, P));
   } else {
     const int smem = (int)FwdSmem::total(P.num_kb);
     if (int e = ensure_dyn_smem(ntxent_fwd_kernel, smem)) return e;
@@ -1022,7 +1023,8 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
       P.n_push_ctas = static_cast<int>(total < n_sm ? total : n_sm);
     }
     ProfScope prof(TCL_K_NTXENT_FWD, st);
-    ntxent_fwd_kernel<<<grid, FW_THREADS + (P.n_push > 0 ? FW_PUSH_WARPS * 32 : 0), smem, st>>>(P);
+    LaunchCfg L(grid, dim3(FW_THREADS + (P.n_push > 0 ? FW_PUSH_WARPS * 32 : 0)), smem, st);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, ntxent_fwd_kernel, P));
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   if (parts != nullptr) {  // the caller reduces the partials itself (fused into the finalise kernel)
@@ -1035,8 +1037,9 @@ static int ntxent_fwd_impl(int n_pairs, const void* const* zrow, const void* con
   const int nmax = (int)(n_rows > n_cols ? n_rows : n_cols);
   {
     ProfScope prof(TCL_K_FWD_REDUCE, st);
-    fwd_reduce_kernel<<<dim3((nmax + 255) / 256, n_pairs), 256, 0, st>>>(
-        P.row_part, P.col_part, row_sumexp, col_sumexp, n_pairs, P.n_rows, P.n_cols, 2 * P.n_jsplit, P.n_iblocks);
+    LaunchCfg L(dim3((nmax + 255) / 256, n_pairs), dim3(256), 0, st);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, fwd_reduce_kernel, (const float*)P.row_part, (const float*)P.col_part, row_sumexp,
+                                      col_sumexp, n_pairs, P.n_rows, P.n_cols, 2 * P.n_jsplit, P.n_iblocks));
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
@@ -1064,20 +1067,10 @@ static int ntxent_finalize_impl(int n_pairs, int64_t n_rows, int64_t n_cols, int
     const int nmax = (int)(n_rows > n_cols ? n_rows : n_cols);
     int threads = 32;
     while (threads < 1024 && threads * FIN_CTAS < nmax) threads <<= 1;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(FIN_CTAS, n_pairs, 1);
-    cfg.blockDim = dim3(threads);
-    cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = FIN_CTAS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    LaunchCfg L(dim3(FIN_CTAS, n_pairs, 1), dim3(threads), 0, static_cast<cudaStream_t>(stream), FIN_CTAS);
     const float* rp = parts ? parts->row_part : nullptr;
     const float* cp = parts ? parts->col_part : nullptr;
-    TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_finalize_kernel, (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha,
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, fwd_finalize_kernel, (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha,
                                       row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss, rp, cp,
                                       parts ? parts->n_row_slots : 0, parts ? parts->n_iblocks : 0));
   }
@@ -1166,7 +1159,8 @@ extern "C" int tcl_ntxent_fwd_sharded(int n_pairs, const void* const* zrow, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     ProfScope prof(TCL_K_FWD_REDUCE, st);
-    fwd_reduce_push_kernel<<<dim3(static_cast<unsigned>((b_glob + 255) / 256), n_pairs), 256, 0, st>>>(S);
+    LaunchCfg L(dim3(static_cast<unsigned>((b_glob + 255) / 256), n_pairs), dim3(256), 0, st);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, fwd_reduce_push_kernel, S));
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
@@ -1191,18 +1185,8 @@ extern "C" int tcl_ntxent_finalize_sharded(int n_pairs, int64_t b_loc, int64_t b
   ProfScope prof(TCL_K_FWD_FINALIZE, st);
   int threads = 32;
   while (threads < 1024 && threads * FIN_CTAS < b_glob) threads <<= 1;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(FIN_CTAS, n_pairs, 1);
-  cfg.blockDim = dim3(threads);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = FIN_CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TCL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_finalize_sharded_kernel, (int)b_loc, (int)b_glob, n_pairs, world,
+  LaunchCfg L(dim3(FIN_CTAS, n_pairs, 1), dim3(threads), 0, st, FIN_CTAS);
+  TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, fwd_finalize_sharded_kernel, (int)b_loc, (int)b_glob, n_pairs, world,
                                     inv_tau * 1.4426950408889634f, alpha, src, static_cast<const uint32_t*>(sync_own), lse2_row,
                                     lse2_col, loss));
   return TCL_OK;
