@@ -355,6 +355,44 @@ def run_ours(args, rank, world, local_rank):
                 "whole_step": {"algorithmic_flops": step_flops, "achieved": step_tf, "frac": step_tf / peaks["tf_burst"],
                                "frac_of_sustained_peak": step_tf / peaks["tf_sustained"]}}
 
+    # ---------------- NVLink traffic of the fused compute+transfer kernels (N > 1): algorithmic bytes per rank and step
+    nvlink = None
+    if world > 1:
+        gather_in = 3 * (batch - b_loc) * DIM * 2
+        nvlink = {"gather": {"kernel": "l2norm_fwd_push_kernel (K1 storing into every rank's gathered buffer)",
+                             "bytes_in_per_rank": gather_in, "bytes_out_per_rank": gather_in,
+                             "gbs_per_direction": gather_in / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9 if "l2norm_fwd" in kern else None},
+                  "statistics": {"kernel": "fwd_finalize_sharded_kernel (pulls every rank's slot)",
+                                 "bytes_in_per_rank": (world - 1) * 3 * (batch + 2 * b_loc) * 4}}
+        if bwd_mode == "sharedg":
+            rs16 = os.environ.get("TRICOLO_B200_RS16", "1") != "0"
+            rs_out = 2 * batch * DIM * (2 if rs16 else 4) * (world - 1) // world  # image and voxel are column-side tensors
+            nvlink["reduce_scatter"] = {"kernel": "ntxent_ggemm(2)_kernel drain (TMA stores into the owners' receive buffers)",
+                                        "partials": "fp16" if rs16 else "fp32", "bytes_out_per_rank": rs_out,
+                                        "gbs_if_spread_over_the_kernel": rs_out / (kern["ntxent_bwd"]["ms_per_launch"] * 1e-3) / 1e9}
+        else:
+            nvlink["reduce_scatter"] = {"bytes_out_per_rank": 0, "note": "directional backward: complete local gradients, no exchange"}
+
+    # ---------------- the north star's stated operand format on record: the same step with bf16 tensor-core operands
+    bf16_line = None
+    if op == ops.F16 and world == 1:
+        try:
+            def step_bf16(fs):
+                for f in fs:
+                    f.grad = None
+                losses = trimodal_ntxent(fs, TAU, ALPHA, op_format=ops.BF16)
+                losses.sum().backward()
+                return losses
+            tb = timed(lambda: step_bf16(feats), 10, 3)
+            pb = loss_parity(args, rank, world, dev, batch, b_loc, row0, feats, step_bf16, dist)
+            bf16_line = {"eager_ms_per_step": statistics.median(tb), "loss_rel_err": pb.get("loss_rel_err"),
+                         "grad_rel_err": pb.get("grad_rel_err"),
+                         "note": "TCL_OP_BF16 operands: same kernels and rate, 8-bit significand; gradients miss rtol 1e-3 "
+                                 "(DESIGN section 2), which is why fp16 operands are the default"}
+            step(feats)  # restore the default-format gradients
+        except Exception as ex:
+            bf16_line = {"error": repr(ex)[:200]}
+
     # ---------------- e2e: host buffers in, loss + gradients back to the host, every step
     e2e = bench_e2e(args, world, dev, op, host, b_loc, batch, loss_fn, timed, max_over_ranks, barrier)
 
@@ -392,7 +430,8 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if op == ops.F16 else "bf16", "data": "synthetic",
             "config": cfg, "roofline": roofline, "kernels": kern, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "parity": parity, "cpu_baseline": cpu, "small_batch": small, "retrieval": retrieval,
+            "parity": parity, "nvlink": nvlink, "bf16_operands": bf16_line, "cpu_baseline": cpu, "small_batch": small,
+            "retrieval": retrieval,
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)

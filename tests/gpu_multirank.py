@@ -34,8 +34,9 @@ def main():
         out["train_loss/total_loss"].backward()
         return {k: float(v.detach()) for k, v in out.items()}, [x.grad.clone() for x in loc]
 
-    def close(a, b):  # different kernels / summation orders: norm-wise 1e-4, element-wise against the largest entry
-        return (float((a - b).norm()) <= 1e-4 * float(b.norm()) and
+    def close(a, b):  # different kernels / summation orders / fp16 partials over NVLink: norm-wise 6e-4 (every form is
+        # checked against the fp64 oracle at 1e-3 above), element-wise against the largest entry
+        return (float((a - b).norm()) <= 6e-4 * float(b.norm()) and
                 torch.allclose(a, b, rtol=1e-3, atol=1e-3 * float(b.abs().max())))
 
     # ---- global-negative trimodal loss vs the single-process fp64 oracle.  Rows per rank: 256 (one or two 128-row

@@ -508,14 +508,15 @@ def _emulated_forward(tb, f, pairs, world, op=0):
     return z_all, torch.stack(invs), xs, lse2_row_all, fin[0][1].contiguous(), loss
 
 
-@pytest.mark.parametrize("b_glob,world,gsplit,need", [
-    (1024, 8, None, (1, 1, 1)),      # one 128-row block per rank
-    (4096, 2, None, (1, 1, 1)),      # accumulator halves (G of all pairs fits L2)
-    (4096, 2, "1", (1, 1, 1)),       # full-width accumulators, cut units
-    (3072, 4, None, (1, 0, 1)),      # image needs no gradient: its jobs disappear, G of (text,image) is still needed
-    (8192, 8, None, (1, 1, 1)),      # BASELINE configs[3] at N=8
+@pytest.mark.parametrize("b_glob,world,gsplit,need,rs16", [
+    (1024, 8, None, (1, 1, 1), "0"),      # one 128-row block per rank
+    (4096, 2, None, (1, 1, 1), "0"),      # accumulator halves (G of all pairs fits L2)
+    (4096, 2, "1", (1, 1, 1), "0"),       # full-width accumulators, cut units, CTA-pair gradient GEMM
+    (4096, 2, "1", (1, 1, 1), "1"),       # the same with fp16 column-side partials (the default)
+    (3072, 4, None, (1, 0, 1), "1"),      # image needs no gradient: its jobs disappear, G of (text,image) is still needed
+    (8192, 8, None, (1, 1, 1), "1"),      # BASELINE configs[3] at N=8
 ])
-def test_sharded_sharedg_backward_rank_emulation(tb, monkeypatch, b_glob, world, gsplit, need):
+def test_sharded_sharedg_backward_rank_emulation(tb, monkeypatch, b_glob, world, gsplit, need, rs16):
     """tcl_ntxent_bwd_sharded_gemm / _finish replayed rank by rank on ONE GPU (every rank's receive buffer is a local
     allocation; on a multi-GPU box they are peer-mapped: tests/gpu_multirank.py): the row block of G formed once per
     pair, row-side gradients local, column-side partials stored into the owner's slots, must reproduce the unsharded
@@ -523,6 +524,10 @@ def test_sharded_sharedg_backward_rank_emulation(tb, monkeypatch, b_glob, world,
     ops = tb.ops
     if gsplit is not None:
         monkeypatch.setenv("TRICOLO_B200_GSPLIT", gsplit)
+    monkeypatch.setenv("TRICOLO_B200_RS16", rs16)
+    # fp32 partials: only the summation order differs from the unsharded kernels; fp16 partials (what crosses NVLink by
+    # default) add one 11-bit rounding per source rank - still inside the 1e-3 budget against the oracle (test below)
+    tol = 1e-4 if rs16 == "0" else 6e-4
     g = torch.Generator().manual_seed(33)
     base = torch.randn(b_glob, 512, generator=g)
     f = [(base + 0.5 * torch.randn(b_glob, 512, generator=g)).bfloat16().float().cuda() for _ in range(3)]
@@ -549,7 +554,7 @@ def test_sharded_sharedg_backward_rank_emulation(tb, monkeypatch, b_glob, world,
                 continue
             ref = dev[m].grad[sl]
             rel = float((dxs[m] - ref).norm()) / float(ref.norm())
-            assert rel <= 1e-4, (r, m, rel)
+            assert rel <= tol, (r, m, rel)
             # element-wise: the LSEs of the replayed forward differ from the fused forward's in the last fp32 bit, which
             # flips the 16-bit rounding of single entries of G (one ulp of a diagonal entry = 4e-4 of the largest
             # gradient element); both results are equally close to the fp64 oracle (profiles/shard_g_debug.py)
@@ -558,7 +563,7 @@ def test_sharded_sharedg_backward_rank_emulation(tb, monkeypatch, b_glob, world,
 
 @pytest.mark.parametrize("b_glob,world,fused", [(1024, 8, True), (4096, 2, True), (1024, 8, False), (2048, 4, False),
                                                 (2048, 4, None), (1400, 2, None)])
-def test_flag_protocol_rank_emulation(tb, b_glob, world, fused):
+def test_flag_protocol_rank_emulation(tb, monkeypatch, b_glob, world, fused):
     """The barrier-free sharded step (tcl_l2norm_fwd_push -> tcl_ntxent_fwd_sharded -> tcl_ntxent_finalize_sharded ->
     tcl_ntxent_bwd_sharded_gemm/_finish with sync pads) replayed rank by rank on ONE GPU, two steps in a row (the flags
     carry the step number and are never reset).  fused: the all-gather of the column modalities (image, voxel) is done
@@ -571,6 +576,7 @@ def test_flag_protocol_rank_emulation(tb, b_glob, world, fused):
     n, dim = 3, 512
     if fused is None:
         return _barrier_form_rank_emulation(tb, b_glob, world)
+    monkeypatch.setenv("TRICOLO_B200_RS16", "0")  # fp32 partials: compared tightly with the unsharded gradients below
     zbufs = [torch.zeros((b_glob, n * dim), dtype=torch.float16, device="cuda") for _ in range(world)]
     syncs = [torch.zeros((ops.shard_sync_bytes() // 4,), dtype=torch.int32, device="cuda") for _ in range(world)]
     stats = [torch.full((ops.shard_stats_bytes(3, b_loc, world) // 4,), float("nan"), device="cuda") for _ in range(world)]

@@ -142,7 +142,7 @@ struct NormShJob {
   const float* inv_norm;
   void* dx;
   const float* row_part;  // [kBwdMaxSplit][b_loc][dim] or unused (row_job < 0)
-  const float* col_part;  // [world][n_slots_col][b_loc][dim] or unused (col_job < 0)
+  const void* col_part;   // [world][n_slots_col][b_loc][dim] fp32 or fp16 (NormShParams::col16), or unused (col_job < 0)
   int row_job, col_job;   // indices into the tile table
 };
 struct NormShParams {
@@ -155,6 +155,7 @@ struct NormShParams {
   const uint32_t* sync;     // own sync pad: wait for every source's kGrads flag (NULL: the caller ran a barrier)
   int n_ranges, n_dsplit, world, rank, n_slots_col;
   int unit_shift;  // log2 rows of a unit: 7, or 8 with the CTA-pair gradient GEMM
+  int col16;       // the column-side partials are fp16
 };
 int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, int64_t rows, int dim, int64_t x_stride,
                               float eps, cudaStream_t st);

@@ -581,11 +581,26 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
       }
       for (int k = 0; k < np_col[dh]; ++k) {
         float4 v[TCL_MAX_PEERS];
+        if (pr.col16) {  // fp16 partials (what crosses NVLink by default)
+          uint2 h[TCL_MAX_PEERS];
 #pragma unroll
-        for (int r = 0; r < TCL_MAX_PEERS; ++r)
-          v[r] = r < pr.world
-                     ? __ldcv(reinterpret_cast<const float4*>(jb.col_part + (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < TCL_MAX_PEERS; ++r)
+            h[r] = r < pr.world ? __ldcv(reinterpret_cast<const uint2*>(static_cast<const __half*>(jb.col_part) +
+                                                                       (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
+                                : make_uint2(0u, 0u);
+#pragma unroll
+          for (int r = 0; r < TCL_MAX_PEERS; ++r) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h[r].x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h[r].y));
+            v[r] = make_float4(a.x, a.y, b.x, b.y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < TCL_MAX_PEERS; ++r)
+            v[r] = r < pr.world
+                       ? __ldcv(reinterpret_cast<const float4*>(static_cast<const float*>(jb.col_part) + (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int r = 0; r < TCL_MAX_PEERS; ++r) {
           if (r < pr.world) { acc[0] += sc[r] * v[r].x; acc[1] += sc[r] * v[r].y; acc[2] += sc[r] * v[r].z; acc[3] += sc[r] * v[r].w; }

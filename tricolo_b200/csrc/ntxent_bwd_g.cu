@@ -390,6 +390,7 @@ struct GBJobDev {
   int owner_rows;    // > 0: output rows are owned in blocks of owner_rows by successive ranks (tm_dst[dst_first + owner])
   int slot_rows;     // rows of one partial slot in the destination
   int src_row_base;  // first destination row of this rank's slots (remote: rank * n_slots * slot_rows)
+  int dst16;         // the destination holds fp16 (partials that cross NVLink): tm_dst boxes are {64 cols, 32 rows}
 };
 struct GBParams {
   GBJobDev job[GB_MAX_JOBS];
@@ -626,6 +627,37 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
       }
       const CUtensorMap* tm = &P.tm_dst[J.dst_first + owner];
       const int row0 = J.src_row_base + pc.slot * J.slot_rows + rin + q * 32;
+      if (J.dst16) {
+        // partials that cross NVLink travel as fp16 (half the bytes; |acc| <= ~kGScale fits, 11 significant bits):
+        // 64 columns = one 128-byte row of the staging tile per step
+#pragma unroll 1
+        for (int cc = 0; cc < hw / 64; ++cc) {
+          const int ucol = half * hw + cc * 64;
+          if (ucol >= ucols) break;
+          uint32_t v[32], w[32];
+          tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, buf * 256 + ucol), v);
+          tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, buf * 256 + ucol + 32), w);
+          tc_wait_ld();
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
+          uint8_t* rowp = stg_ptr + lane * 128;
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            const uint32_t* src = c16 < 4 ? v + 8 * c16 : w + 8 * (c16 - 4);
+            *reinterpret_cast<uint4*>(rowp + ((c16 ^ (lane & 7)) << 4)) =
+                make_uint4(pack2<TCL_OP_F16>(__uint_as_float(src[0]), __uint_as_float(src[1])),
+                           pack2<TCL_OP_F16>(__uint_as_float(src[2]), __uint_as_float(src[3])),
+                           pack2<TCL_OP_F16>(__uint_as_float(src[4]), __uint_as_float(src[5])),
+                           pack2<TCL_OP_F16>(__uint_as_float(src[6]), __uint_as_float(src[7])));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tm, stg, pc.dh * 256 + ucol, row0);
+            bulk_commit_group();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int cc = 0; cc < hw / 32; ++cc) {
         const int ucol = half * hw + cc * 32;
@@ -646,6 +678,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
           tma_store_2d(tm, stg, pc.dh * 256 + ucol, row0);
           bulk_commit_group();
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -921,6 +954,35 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
       }
       const CUtensorMap* tm = &P.tm_dst[J.dst_first + (live ? owner : 0)];
       const int row0 = J.src_row_base + pc.slot * J.slot_rows + rin + q * 32;
+      if (J.dst16) {  // fp16 partials for the rows that cross NVLink (see the one-SM kernel)
+#pragma unroll 1
+        for (int cc = 0; cc < 4 && live; ++cc) {
+          const int col = half * 256 + cc * 64;
+          if (col >= P.dim) break;
+          uint32_t v[32], w[32];
+          tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, col), v);
+          tmem_ld_32x32b_x32(tmem_addr(tmem, q * 32, col + 32), w);
+          tc_wait_ld();
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
+          uint8_t* rowp = stg_ptr + lane * 128;
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            const uint32_t* src = c16 < 4 ? v + 8 * c16 : w + 8 * (c16 - 4);
+            *reinterpret_cast<uint4*>(rowp + ((c16 ^ (lane & 7)) << 4)) =
+                make_uint4(pack2<TCL_OP_F16>(__uint_as_float(src[0]), __uint_as_float(src[1])),
+                           pack2<TCL_OP_F16>(__uint_as_float(src[2]), __uint_as_float(src[3])),
+                           pack2<TCL_OP_F16>(__uint_as_float(src[4]), __uint_as_float(src[5])),
+                           pack2<TCL_OP_F16>(__uint_as_float(src[6]), __uint_as_float(src[7])));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tm, stg, col, row0);
+            bulk_commit_group();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int cc = 0; cc < 8 && live; ++cc) {
         const int col = half * 256 + cc * 32;
@@ -941,6 +1003,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
           tma_store_2d(tm, stg, col, row0);
           bulk_commit_group();
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -1183,6 +1246,7 @@ struct ShardPlan {
   int n_jobs;
   size_t ws_scale, ws_part, ws_g, ws_total;  // local workspace offsets / size
   size_t recv_hdr, recv_job_bytes, recv_total;
+  int rs16;  // column-side partials travel and are stored as fp16 (TRICOLO_B200_RS16=0: fp32)
   int pair_slot[TCL_MAX_PAIRS], n_gpairs;
 };
 
@@ -1265,7 +1329,11 @@ static int make_shard_plan(ShardPlan* out, int n_tensors, int n_pairs, const int
   S.ws_g = S.ws_part + up(static_cast<size_t>(S.n_row_jobs) * kBwdMaxSplit * S.n_self_pad * dim * 4);
   S.ws_total = S.ws_g + up(g_bytes) + 1024;
   S.recv_hdr = 1024;  // [world] floats: every source rank's scale
-  S.recv_job_bytes = static_cast<size_t>(world) * S.n_slots_col * b_loc * dim * 4;
+  {
+    const char* e = getenv("TRICOLO_B200_RS16");
+    S.rs16 = !(e && e[0] == '0');
+  }
+  S.recv_job_bytes = static_cast<size_t>(world) * S.n_slots_col * b_loc * dim * (S.rs16 ? 2 : 4);
   S.recv_total = S.recv_hdr + static_cast<size_t>(S.n_col_jobs) * S.recv_job_bytes;
   return TCL_OK;
 }
@@ -1387,8 +1455,13 @@ extern "C" int tcl_ntxent_bwd_sharded_gemm(int n_tensors, const void* const* z_a
     if (col) {
       for (int r = 0; r < world; ++r) {
         char* dst = static_cast<char*>(recv_ptrs[r]) + S.recv_hdr + static_cast<size_t>(i_col) * S.recv_job_bytes;
-        if (int e = make_tmap_2d_f32(&B.tm_dst[n_dst++], dst, static_cast<uint64_t>(world) * S.n_slots_col * b_loc, dim, 32, 32)) return e;
+        if (S.rs16) {
+          if (int e = make_tmap_2d_16bit(&B.tm_dst[n_dst++], dst, static_cast<uint64_t>(world) * S.n_slots_col * b_loc, dim, dim, 32, 64)) return e;
+        } else {
+          if (int e = make_tmap_2d_f32(&B.tm_dst[n_dst++], dst, static_cast<uint64_t>(world) * S.n_slots_col * b_loc, dim, 32, 32)) return e;
+        }
       }
+      J.dst16 = S.rs16;
       J.owner_rows = static_cast<int>(b_loc);
       J.slot_rows = static_cast<int>(b_loc);
       J.src_row_base = rank * S.n_slots_col * static_cast<int>(b_loc);
@@ -1452,7 +1525,7 @@ extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x
       }
       if (S.job_tensor[j] == m && S.job_is_col[j]) {
         J.col_job = j;
-        J.col_part = reinterpret_cast<const float*>(rv + S.recv_hdr + static_cast<size_t>(i_col) * S.recv_job_bytes);
+        J.col_part = rv + S.recv_hdr + static_cast<size_t>(i_col) * S.recv_job_bytes;
       }
       i_row += !S.job_is_col[j];
       i_col += S.job_is_col[j] != 0;
@@ -1473,6 +1546,7 @@ extern "C" int tcl_ntxent_bwd_sharded_finish(int n_tensors, const void* const* x
   N.rank = rank;
   N.n_slots_col = S.n_slots_col;
   N.row_slot_stride = static_cast<int64_t>(S.n_self_pad) * dim;
+  N.col16 = S.rs16;
   N.scales = reinterpret_cast<const float*>(rv);
   N.sync = static_cast<const uint32_t*>(sync_own);
   return launch_l2norm_bwd_sharded(N, n_out, x_dtype, b_loc, static_cast<int>(dim), x_row_stride, eps,
