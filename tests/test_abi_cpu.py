@@ -57,6 +57,38 @@ def test_argument_validation_without_gpu():
     assert L.tcl_ntxent_bwd_workspace_bytes(3, 8192, 512) >= 3 * 8192 * 512 * 4
 
 
+def test_sharded_backward_plan_and_validation_without_gpu():
+    """The plan of the sharded shared-G backward (buffer sizes, slot counts) is a pure host function of the sizes, and
+    the sharded entry points validate their arguments before any CUDA call."""
+    from tricolo_b200 import _lib, ops
+
+    L = _lib.LIB
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    p8 = ops.ShardedBwdPlan(3, pairs, (1, 1, 1), 1024, 8, 512)
+    p2 = ops.ShardedBwdPlan(3, pairs, (1, 1, 1), 4096, 2, 512)
+    # receive buffer: 1 KB header + 2 column-side tensors x world x slots x b_loc x dim x 2 bytes (fp16 partials)
+    assert (p8.recv_bytes - 1024) % (2 * 8 * 1024 * 512 * 2) == 0 and p8.recv_bytes > 1024
+    assert p2.workspace_bytes > 3 * 4096 * 8192 * 2  # holds the rank's row block of G for every pair
+    # text never needs a gradient: only its column-side partner tensors get jobs; still a valid plan
+    p = ops.ShardedBwdPlan(3, pairs, (0, 1, 1), 1024, 8, 512)
+    assert p.recv_bytes == p8.recv_bytes
+    assert not ops.ShardedBwdPlan.supported(1000, 512, 8) and not ops.ShardedBwdPlan.supported(1024, 256, 8)
+    with pytest.raises(ValueError):
+        ops.ShardedBwdPlan(3, pairs, (1, 1, 1), 1000, 8, 512)  # rows per rank not a multiple of 128
+    assert L.tcl_shard_sync_bytes() == 4096
+    assert L.tcl_shard_stats_bytes(3, 1024, 8) == 8 * 3 * (8192 + 2048) * 4
+    assert L.tcl_shard_stats_bytes(4, 1024, 8) == 0 and L.tcl_rank_metrics_workspace_bytes() > 0
+    buf = ctypes.create_string_buffer(8192)
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    arr = (ctypes.c_void_p * 8)(*([ptr.value] * 8))
+    rc = L.tcl_l2norm_fwd_push(3, arr, 0, 1024, 512, 512, 9, 8, arr, 1536, 0, arr, 1e-12, arr, 1, None)  # rank 9 of 8
+    assert rc == 4 and b"rank" in L.tcl_last_error_string()
+    rc = L.tcl_ntxent_finalize_sharded(3, 1024, 8000, 0, 8, 10.0, 0.25, arr, None, ptr, ptr, ptr, None)  # b_glob != W * b_loc
+    assert rc == 4
+    rc = L.tcl_rank_metrics(ptr, 100, 17, ptr, ptr, 1 << 20, None)  # k > 16
+    assert rc == 4
+
+
 def test_no_cpu_fallback():
     import torch
 
