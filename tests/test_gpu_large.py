@@ -31,12 +31,14 @@ def gold():
     return json.load(open(os.path.join(HERE, "golden", "large_outputs.json")))
 
 
-@pytest.mark.parametrize("mode", ["sharedg", "pc"])
+@pytest.mark.parametrize("mode", ["sharedg", "pc", "sharedg+fold"])
 def test_c4_loss_and_grads_vs_reference_golden(gold, mode, monkeypatch):
     from bench import make_features
     from tricolo_b200.loss import trimodal_ntxent
 
-    monkeypatch.setenv("TRICOLO_B200_BWD", mode)
+    monkeypatch.setenv("TRICOLO_B200_BWD", mode.split("+")[0])
+    # opt-in form: normalise backward by the gradient kernel's read-out warps (csrc/norm_fold.cuh), read per call
+    monkeypatch.setenv("TRICOLO_B200_FOLD", "1" if mode.endswith("+fold") else "0")
     g = gold["c4"]
     feats = make_features(g["batch"], g["batch"], 0, seed=g["seed"])
     dev = [feats[k].cuda().requires_grad_(True) for k in KEYS]

@@ -332,7 +332,9 @@ using namespace tcl;
 extern "C" size_t tcl_ntxent_bwd_workspace_bytes(int n_jobs, int64_t n_self, int64_t dim) {
   if (n_jobs < 1 || n_self < 1 || dim < 1) return 0;
   const int64_t n_self_pad = (n_self + BW_BM - 1) / BW_BM * BW_BM;  // the persistent kernel stores whole 128-row units
-  return static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self_pad * dim * sizeof(float) + 256;
+  // [64 floats of scales][n_jobs x kBwdMaxSplit partial slots][block counters of the folded normalise backward]
+  return static_cast<size_t>(n_jobs) * kBwdMaxSplit * n_self_pad * dim * sizeof(float) + 256 +
+         sizeof(uint32_t) * 8 * static_cast<size_t>(n_self_pad / BW_BM) + 256;
 }
 
 extern "C" int tcl_ntxent_bwd_needs_transpose(int64_t dim) {

@@ -96,6 +96,7 @@ struct BwdSharedGArgs {
 };
 size_t bwd_sharedg_workspace_bytes(int n_pairs, int64_t batch);
 bool bwd_sharedg_enabled(int n_pairs, int64_t batch, int64_t dim);
+bool fold_enabled();  // normalise backward inside the gradient kernels' read-out (norm_fold.cuh)
 int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st);
 
 }  // namespace tcl

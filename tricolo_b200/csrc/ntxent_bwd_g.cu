@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "ntxent_bwd.h"
+#include "norm_fold.cuh"
 #include "../../include/tricolo_b200.h"
 
 namespace tcl {
@@ -55,6 +56,8 @@ struct GAParams {
   // rank's entry of every rank's receive-buffer header
   float* scale_out[TCL_MAX_PEERS];
   int n_scale_out;
+  uint32_t* zero_words;  // block counters of the folded normalise backward (norm_fold.cuh), cleared here for kernel B
+  int n_zero_words;
   int n_pairs, n_rows, n_cols, row_offset, num_kb, n_jtiles, n_iblocks;
   float c1, alpha, out_scale;
   uint32_t idesc;
@@ -215,6 +218,8 @@ __global__ void __launch_bounds__(GA_THREADS, 1) ntxent_g_kernel(const __grid_co
     }
     const float inv_gmax = gmax > 0.f ? kGScale / gmax : 0.f;  // G in [-kGScale, kGScale]: see ntxent_bwd.h
     if (blockIdx.x == 0 && ew == 0 && lane < P.n_scale_out) *P.scale_out[lane] = gmax * P.out_scale * (1.f / kGScale);
+    if (blockIdx.x == 0 && ew == 1)
+      for (int i = lane; i < P.n_zero_words; i += 32) P.zero_words[i] = 0u;
 
     while (walk.next(unit, ta, tb)) {
       const int pi = unit / P.n_iblocks;
@@ -403,10 +408,11 @@ struct GBParams {
   // kGrads[rank] = epoch to every rank and publishes the backward epoch (host_common.h: ShardSync); world = 0: off
   uint32_t* sync[TCL_MAX_PEERS];
   int rank, world;
+  FoldParams fold;  // normalise backward by the read-out warps that complete a row block (norm_fold.cuh); jobs indexed alike
 };
 
 struct GBPiece {
-  int job, ib, dh, ta, tb, slot;
+  int job, ib, dh, ta, tb, slot, n_pieces;  // n_pieces: pieces the whole unit is cut into
 };
 
 // wait-time accounting of the first and the last CTA (`make trace`): [0..31] CTA 0, [32..63] the last CTA
@@ -445,7 +451,12 @@ struct GBWalk {
     pc.ta = static_cast<int>(local % T);
     const int64_t left = end - cursor;
     pc.tb = left < T - pc.ta ? pc.ta + static_cast<int>(left) : T;
-    pc.slot = c - pc_range_of(P.job_tile_base[GB_MAX_JOBS], cursor - pc.ta, n);
+    {
+      const int64_t total = P.job_tile_base[GB_MAX_JOBS], first = cursor - pc.ta;
+      const int r0 = pc_range_of(total, first, n);
+      pc.slot = c - r0;
+      pc.n_pieces = pc_range_of(total, first + T - 1, n) - r0 + 1;
+    }
     cursor += pc.tb - pc.ta;
     return true;
   }
@@ -683,6 +694,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      if (P.fold.enabled && J.owner_rows == 0)
+        fold_piece_done(P.fold, pc.job, pc.ib, pc.n_pieces, warp - 2, lane,
+                        reinterpret_cast<volatile uint32_t*>(base_ptr + GBSmem::bar_off + 240), 1);
       GT_END(8);
       ++piece;
     }
@@ -784,7 +798,12 @@ struct GB2Walk {  // as GBWalk with one range per cluster; pc.ib = first row blo
     pc.ta = static_cast<int>(local % T);
     const int64_t left = end - cursor;
     pc.tb = left < T - pc.ta ? pc.ta + static_cast<int>(left) : T;
-    pc.slot = c - pc_range_of(P.job_tile_base[GB_MAX_JOBS], cursor - pc.ta, n);
+    {
+      const int64_t total = P.job_tile_base[GB_MAX_JOBS], first = cursor - pc.ta;
+      const int r0 = pc_range_of(total, first, n);
+      pc.slot = c - r0;
+      pc.n_pieces = pc_range_of(total, first + T - 1, n) - r0 + 1;
+    }
     cursor += pc.tb - pc.ta;
     return true;
   }
@@ -1011,6 +1030,9 @@ __global__ void __launch_bounds__(GB_THREADS, 1) ntxent_ggemm2_kernel(const __gr
         if (leader) mbar_arrive(acc_empty_bar);
         else mbar_arrive_remote(acc_empty_leader);
       }
+      if (P.fold.enabled && J.owner_rows == 0 && live)
+        fold_piece_done(P.fold, pc.job, ib, pc.n_pieces, warp - 2, lane,
+                        reinterpret_cast<volatile uint32_t*>(base_ptr + GBSmem::bar_off + 240), 1);
       ++piece;
     }
     if (lane == 0) {
@@ -1104,6 +1126,14 @@ static int launch_ggemm2(const GBParams& B, int n_clusters, cudaStream_t st) {
   return TCL_OK;
 }
 
+// TRICOLO_B200_FOLD=1 folds the normalise backward into kernel B's read-out (norm_fold.cuh).  Off by default: measured
+// at B = 8192 on one GPU the read-out warps are on the critical path (one 512-column accumulator), kernel B grows by
+// 58 us while the separate kernel it replaces takes 42 us.  Read per call, not cached.
+bool fold_enabled() {
+  const char* e = getenv("TRICOLO_B200_FOLD");
+  return e && e[0] == '1';
+}
+
 static int device_sm_count(int* n_sm) {
   int dev = 0;
   TCL_CHECK_CUDA(cudaGetDevice(&dev));
@@ -1145,6 +1175,13 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   if (A.n_pairs == 0) return TCL_OK;
   A.scale_out[0] = scale;
   A.n_scale_out = 1;
+  // normalise backward folded into kernel B's read-out (norm_fold.cuh): block counters behind the partial slots
+  const bool fold = fold_enabled() && dim % 4 == 0;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(gbase + static_cast<size_t>(a.n_tensors) * kBwdMaxSplit * n_self_pad * dim);
+  if (fold) {
+    A.zero_words = cnt;
+    A.n_zero_words = FOLD_MAX_JOBS * n_iblocks;
+  }
   A.n_rows = A.n_cols = static_cast<int>(batch);
   A.row_offset = 0;
   A.num_kb = static_cast<int>(dim / 64);
@@ -1215,7 +1252,26 @@ int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st) {
   const int64_t cap = (kBwdMaxSplit - 1) * total_b / t_max;
   if (ctas_b > cap) ctas_b = cap;
   if (ctas_b < 1) ctas_b = 1;
+  if (fold) {
+    B.fold.enabled = 1;
+    B.fold.counters = cnt;
+    B.fold.x_stride = a.x_row_stride;
+    B.fold.slot_stride = static_cast<int64_t>(n_self_pad) * dim;
+    B.fold.rows = static_cast<int>(batch);
+    B.fold.dim = static_cast<int>(dim);
+    B.fold.x_dtype = a.x_dtype;
+    B.fold.n_rowblocks = n_iblocks;
+    B.fold.eps = a.eps;
+    for (int j = 0; j < n_jobs; ++j) {
+      B.fold.job[j].x = N.job[j].x;
+      B.fold.job[j].dx = N.job[j].dx;
+      B.fold.job[j].inv_norm = N.job[j].inv_norm;
+      B.fold.job[j].gpart = N.job[j].gpart;
+      B.fold.job[j].scale = N.job[j].scale;
+    }
+  }
   if (int e = two_sm ? launch_ggemm2(B, static_cast<int>(ctas_b), st) : launch_ggemm(B, static_cast<int>(ctas_b), st)) return e;
+  if (fold) return TCL_OK;  // the read-out warps have written dx
   N.n_clusters = static_cast<int>(ctas_b);
   N.unit_shift = two_sm ? 8 : 7;
   N.split_rows = n_self_pad;
