@@ -567,6 +567,7 @@ def bench_small_batches(dev, op, timed, trimodal_ntxent):
     import torch
 
     from oracle import ntxent_oracle as NO
+    from tricolo_b200.loss import trimodal_ntxent_total
 
     out = {}
     for name, b, keys in (("c1: Bi(V) B=128 fwd+bwd", 128, ("text_features", "voxel_features")),
@@ -574,10 +575,10 @@ def bench_small_batches(dev, op, timed, trimodal_ntxent):
         g = torch.Generator().manual_seed(1234)
         sf = [torch.randn(b, DIM, generator=g).to(dev).requires_grad_(True) for _ in keys]
 
-        def ours():
+        def ours():  # the training step of the reference: loss_dict["train_loss/total_loss"].backward()
             for f in sf:
                 f.grad = None
-            trimodal_ntxent(sf, TAU, ALPHA, op_format=op).sum().backward()
+            trimodal_ntxent_total(sf, TAU, ALPHA, op_format=op)[1].backward()
 
         def ref():
             fd = {k: f.detach().clone().requires_grad_(True) for k, f in zip(keys, sf)}
@@ -598,7 +599,7 @@ def bench_small_batches(dev, op, timed, trimodal_ntxent):
             for f in sf:
                 f.grad = None
             with torch.cuda.graph(graph):
-                trimodal_ntxent(sf, TAU, ALPHA, op_format=op).sum().backward()
+                trimodal_ntxent_total(sf, TAU, ALPHA, op_format=op)[1].backward()
             gt = statistics.median(timed(graph.replay, 50, 10))
             rec.update({"graph_ms_per_step": gt, "graph_pairs_per_s": b / (gt * 1e-3), "graph_speedup_vs_torch_eager_on_gpu": rt / gt})
         except Exception as e:  # report, never hide

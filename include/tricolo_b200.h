@@ -302,6 +302,24 @@ int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x_host_ptrs, int x_dty
                         int op_format, float inv_tau, float alpha, float eps, const void* state,
                         const float* grad_losses, const uint8_t* need_grad_host, void* const* dx_host_ptrs,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* The same two calls with the SUM of the pair losses (loss_dict["<prefix>/total_loss"], tricolo_net.py:64) as an
+ * output of the forward and its upstream gradient as an input of the backward, so that the training step
+ * `total_loss.backward()` needs no framework kernels between the two library calls:
+ *   loss          [n_pairs + 1] floats: the pair losses, then their fp32 sum in pair order
+ *   grad_losses   [n_pairs] device floats or NULL, grad_total one device float or NULL (not both NULL):
+ *                 the upstream gradient of pair p is grad_losses[p] + *grad_total
+ * At batch sizes where every 32 x 64 logit tile gets its own SM (n_pairs * ceil(B/32) * ceil(B/64) <= SM count,
+ * dim % 64 == 0, dim <= 512) all four entry points run ONE cooperative kernel each (csrc/ntxent_small.cu);
+ * TRICOLO_B200_SMALL=0 keeps the multi-kernel form. */
+int tcl_ntxent_loss_fwd_total(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t batch, int64_t dim,
+                              int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                              int op_format, float inv_tau, float alpha, float eps, void* state, size_t state_bytes,
+                              void* workspace, size_t workspace_bytes, float* loss, void* stream);
+int tcl_ntxent_loss_bwd_total(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t batch, int64_t dim,
+                              int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                              int op_format, float inv_tau, float alpha, float eps, const void* state,
+                              const float* grad_losses, const float* grad_total, const uint8_t* need_grad_host,
+                              void* const* dx_host_ptrs, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
  * K2' — similarity GEMM for retrieval.           replaces eval_retrieval.py:74 (np.dot)
@@ -395,7 +413,9 @@ enum {
   TCL_K_PEER_SUM = 14,
   TCL_K_NTXENT_G = 15, /* shared-G backward, kernel A (logit recompute -> G); its GEMM kernel is TCL_K_NTXENT_BWD */
   TCL_K_RANK_METRICS = 16,
-  TCL_K_COUNT = 17
+  TCL_K_NTXENT_SMALL_FWD = 17, /* small-batch whole-loss forward, one cooperative launch (csrc/ntxent_small.cu) */
+  TCL_K_NTXENT_SMALL_BWD = 18, /* small-batch whole-loss backward, one cooperative launch */
+  TCL_K_COUNT = 19
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);
@@ -416,6 +436,9 @@ int tcl_debug_pc_trace(unsigned long long* out32, int reset);
 int tcl_debug_gb_trace(unsigned long long* out64, int reset);
 /* tcl_debug_fwd_trace: the same for the first cluster of the CTA-pair forward kernel (ntxent_fwd.cu). */
 int tcl_debug_fwd_trace(unsigned long long* out32, int reset);
+/* tcl_debug_small_trace: %globaltimer stamps (ns) of CTA 0 at the phase boundaries of the small-batch kernels
+ * (csrc/ntxent_small.cu): [0..5] forward, [16..22] backward; zeros unless built with `make trace`. */
+int tcl_debug_small_trace(unsigned long long* out32);
 /* tcl_debug_max_clusters: cudaOccupancyMaxActiveClusters for the producer/consumer kernel's footprint. */
 int tcl_debug_max_clusters(int cluster_size, int* out);
 

@@ -752,6 +752,7 @@ def test_backward_forms_agree(tb, b, n_mod, monkeypatch):
     """The shared-G backward (G of a pair formed once, two GEMM kernels) and the producer/consumer backward (logits
     recomputed per direction) are two implementations of the same gradient: both within rtol 1e-3 of the oracle and
     within fp32 summation noise of each other, including ragged batches, two modalities and unequal upstream scales."""
+    monkeypatch.setenv("TRICOLO_B200_SMALL", "0")  # b = 333 would take the single-launch form (test_small_batch_*)
     g = torch.Generator().manual_seed(77 + b)
     base = torch.randn(b, 512, generator=g)
     feats = [(base + 0.5 * torch.randn(b, 512, generator=g)).bfloat16().float() for _ in range(n_mod)]
@@ -788,6 +789,7 @@ def test_backward_forms_agree(tb, b, n_mod, monkeypatch):
 def test_other_dims_all_kernels(tb, dim, b, monkeypatch):
     """dim != 512: odd numbers of 64-wide K-blocks (ring slots with one block, partly empty accumulator chunks), the
     dim <= 256 kernels, both forward kernels (b >= 2048 -> CTA pair) and both backward forms, against the oracle."""
+    monkeypatch.setenv("TRICOLO_B200_SMALL", "0")  # b = 300 would take the single-launch form (test_small_batch_*)
     g = torch.Generator().manual_seed(1000 + dim + b)
     base = torch.randn(b, dim, generator=g)
     feats = [(base + 0.5 * torch.randn(b, dim, generator=g)).bfloat16().float() for _ in range(3)]
@@ -804,3 +806,118 @@ def test_other_dims_all_kernels(tb, dim, b, monkeypatch):
         for x, k in zip(dev, keys):
             err = np.linalg.norm(x.grad.double().cpu().numpy() - ref_g[k]) / np.linalg.norm(ref_g[k])
             assert err <= RTOL, (mode, k, err)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# small-batch single-launch form (csrc/ntxent_small.cu): taken automatically when every 64 x 64 tile gets its own SM
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,dim,n_mod", [(128, 512, 2), (256, 512, 3), (57, 512, 3), (200, 320, 3), (200, 64, 3),
+                                         (230, 192, 3), (448, 448, 2), (2, 512, 2), (64, 128, 3)])
+def test_small_batch_form_vs_oracle_and_pipeline(tb, b, dim, n_mod, monkeypatch):
+    """C1 / C2 (config/config.yaml:62-66: batch 128 bimodal, 256 trimodal) and ragged / other-dim shapes: the
+    single-launch form against the fp64 oracle (rtol 1e-3), and against the multi-kernel pipeline on the same inputs
+    (same 16-bit operands, different summation orders: fp32 noise), with unequal upstream scales."""
+    from tricolo_b200 import _lib as LB
+
+    g = torch.Generator().manual_seed(4000 + b + dim)
+    base = torch.randn(b, dim, generator=g)
+    feats = [(base + 0.5 * torch.randn(b, dim, generator=g)).bfloat16().float() for _ in range(n_mod)]
+    keys = ["text_features", "image_features", "voxel_features"][:n_mod]
+    pairs = [(i, j) for i in range(n_mod) for j in range(i + 1, n_mod)]
+    w = torch.tensor([1.0, -0.5, 3.0][:len(pairs)])
+    out = {}
+    for form in ("1", "0"):
+        monkeypatch.setenv("TRICOLO_B200_SMALL", form)
+        LB.profile_enable(True)
+        dev = [f.cuda().requires_grad_(True) for f in feats]
+        losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA)
+        (losses * w.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        out[form] = (losses.detach().cpu().numpy(), [d.grad.double().cpu().numpy() for d in dev])
+        ran = LB.profile_read()  # the form that ran is the form that was asked for
+        LB.profile_enable(False)
+        for name, want in (("ntxent_small_fwd", form == "1"), ("ntxent_small_bwd", form == "1"), ("ntxent_fwd", form == "0")):
+            assert (name in ran) == want, (form, name, sorted(ran))
+    tot = [np.zeros((b, dim)) for _ in range(n_mod)]
+    for p, (i, j) in enumerate(pairs):
+        ref_l, gp = NO.trimodal_forward_backward({keys[i]: feats[i].numpy(), keys[j]: feats[j].numpy()}, TAU, ALPHA)
+        (ref,) = [v for k, v in ref_l.items() if not k.endswith("total_loss")]
+        for form in ("1", "0"):
+            assert float(out[form][0][p]) == pytest.approx(ref, rel=RTOL, abs=1e-6), (form, p)
+        tot[i] += float(w[p]) * gp[keys[i]]
+        tot[j] += float(w[p]) * gp[keys[j]]
+    for m in range(n_mod):
+        den = max(np.linalg.norm(tot[m]), 1e-12)
+        for form in ("1", "0"):
+            assert np.linalg.norm(out[form][1][m] - tot[m]) / den <= RTOL, (form, m)
+        assert np.linalg.norm(out["1"][1][m] - out["0"][1][m]) / den <= RTOL
+
+
+def test_small_batch_form_mixed_with_pipeline_and_replay(tb, monkeypatch):
+    """The two forms share the state layout: a single-launch forward followed by a pipeline backward (and the reverse)
+    gives the same gradients; the single-launch form is deterministic (bit-identical on replay, also from a CUDA
+    graph) and honours requires_grad subsets."""
+    g = torch.Generator().manual_seed(99)
+    feats = [torch.randn(256, 512, generator=g).bfloat16().float() for _ in range(3)]
+
+    def run(fwd_form, bwd_form, need=(True, True, True)):
+        dev = [f.cuda().requires_grad_(n) for f, n in zip(feats, need)]
+        monkeypatch.setenv("TRICOLO_B200_SMALL", fwd_form)
+        losses = tb.loss.trimodal_ntxent(dev, TAU, ALPHA)
+        monkeypatch.setenv("TRICOLO_B200_SMALL", bwd_form)
+        losses.sum().backward()
+        return losses.detach().clone(), [None if d.grad is None else d.grad.clone() for d in dev]
+
+    l11, g11 = run("1", "1")
+    l11b, g11b = run("1", "1")
+    assert torch.equal(l11, l11b) and all(torch.equal(a, b) for a, b in zip(g11, g11b))
+    for ff, bf in (("1", "0"), ("0", "1"), ("0", "0")):
+        l, gr = run(ff, bf)
+        assert torch.allclose(l, l11, rtol=1e-5)
+        for a, b in zip(gr, g11):
+            assert float((a - b).norm()) <= 5e-4 * float(b.norm()), (ff, bf)
+    # the sum output and its upstream gradient (calculate_losses -> total_loss.backward(), the training step): the
+    # same numbers as summing the pair losses with framework ops, in both forms, also when both outputs are used
+    for form in ("1", "0"):
+        monkeypatch.setenv("TRICOLO_B200_SMALL", form)
+        ref_l, ref_g = run(form, form)
+        dev = [f.cuda().requires_grad_(True) for f in feats]
+        d = tb.loss.calculate_losses(dict(zip(["text_features", "image_features", "voxel_features"], dev)), "train_loss",
+                                     tb.loss.NTXentLoss(TAU, ALPHA))
+        assert list(d) == ["train_loss/text_image_loss", "train_loss/text_voxel_loss", "train_loss/image_voxel_loss",
+                           "train_loss/total_loss"]
+        tot = d["train_loss/total_loss"]
+        assert tot.dim() == 0 and float(tot) == pytest.approx(float(ref_l.sum()), rel=1e-6)
+        tot.backward()
+        assert all(torch.equal(x.grad, r) for x, r in zip(dev, ref_g)), form
+        dev = [f.cuda().requires_grad_(True) for f in feats]
+        ls, tot = tb.loss.trimodal_ntxent_total(dev, TAU, ALPHA)
+        (2.0 * tot + (ls * torch.tensor([1.0, -3.0, 0.5], device="cuda")).sum()).backward()
+        dev2 = [f.cuda().requires_grad_(True) for f in feats]
+        (tb.loss.trimodal_ntxent(dev2, TAU, ALPHA) * torch.tensor([3.0, -1.0, 2.5], device="cuda")).sum().backward()
+        for x, y in zip(dev, dev2):
+            assert float((x.grad - y.grad).norm()) <= 1e-6 * float(y.grad.norm()), form
+    _, gsub = run("1", "1", need=(True, False, True))
+    assert gsub[1] is None
+    for m in (0, 2):  # the other tensors' gradients do not depend on who else wants one
+        assert torch.equal(gsub[m], g11[m])
+    # CUDA graph capture of the two cooperative launches
+    monkeypatch.setenv("TRICOLO_B200_SMALL", "1")
+    static = [f.cuda().requires_grad_(True) for f in feats]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            tb.loss.trimodal_ntxent(static, TAU, ALPHA).sum().backward()
+    torch.cuda.current_stream().wait_stream(s)
+    for t in static:
+        t.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        lg = tb.loss.trimodal_ntxent(static, TAU, ALPHA)
+        lg.sum().backward()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(lg.detach(), l11)
+    assert all(torch.equal(t.grad, b) for t, b in zip(static, g11))

@@ -96,6 +96,20 @@ struct BwdSharedGArgs {
 };
 size_t bwd_sharedg_workspace_bytes(int n_pairs, int64_t batch);
 bool bwd_sharedg_enabled(int n_pairs, int64_t batch, int64_t dim);
+// ntxent_small.cu: whole loss in one cooperative launch per direction when every 64 x 64 tile gets its own SM
+bool small_enabled(int n_tensors, int n_pairs, int64_t batch, int64_t dim, int op_format);
+size_t small_fwd_workspace_bytes(int n_pairs, int64_t batch);
+size_t small_bwd_workspace_bytes(int n_tensors, int64_t batch, int64_t dim);
+int launch_small_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim, int64_t x_row_stride,
+                     int n_pairs, const int32_t* pair_row, const int32_t* pair_col, int op_format, float inv_tau,
+                     float alpha, float eps, void* const* z, float* const* inv, float* diag2, float* lse_row,
+                     float* lse_col, float* loss_parts, float* loss, bool want_total, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st);
+int launch_small_bwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim, int64_t x_row_stride,
+                     int n_pairs, const int32_t* pair_row, const int32_t* pair_col, int op_format, float inv_tau,
+                     float alpha, float eps, const void* const* z, const float* inv_base, const float* lse_row,
+                     const float* lse_col, const float* grad_losses, const float* grad_total, const uint8_t* need_grad,
+                     void* const* dx, void* workspace, size_t workspace_bytes, cudaStream_t st);
 bool fold_enabled();  // normalise backward inside the gradient kernels' read-out (norm_fold.cuh)
 int launch_bwd_sharedg(const BwdSharedGArgs& a, cudaStream_t st);
 

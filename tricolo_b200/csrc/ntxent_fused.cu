@@ -30,6 +30,20 @@ static LossState loss_state_layout(int n_tensors, int n_pairs, int64_t batch, in
   return L;
 }
 
+// loss[n] = loss[0] + ... + loss[n - 1] in fp32, pair order: sum(loss_dict.values()), tricolo_net.py:64
+__global__ void sum_losses_kernel(float* loss, int n) {
+  griddep_wait();
+  float t = 0.f;
+  for (int p = 0; p < n; ++p) t += loss[p];
+  loss[n] = t;
+}
+// out[p] = d/d loss[p] + d/d (sum of the losses); either input may be null
+__global__ void combine_grads_kernel(const float* grad_losses, const float* grad_total, int n, float* out) {
+  griddep_wait();
+  const int p = threadIdx.x;
+  if (p < n) out[p] = (grad_losses ? grad_losses[p] : 0.f) + (grad_total ? *grad_total : 0.f);
+}
+
 }  // namespace tcl
 
 using namespace tcl;
@@ -46,14 +60,21 @@ extern "C" size_t tcl_ntxent_loss_workspace_bytes(int n_tensors, int n_pairs, in
   size_t bwd = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256) +
                align_up(tcl_ntxent_bwd_workspace_bytes(n_tensors, batch, dim), 1024);
   if (bwd_sharedg_enabled(n_pairs, batch, dim)) bwd += bwd_sharedg_workspace_bytes(n_pairs, batch);  // G per pair
-  return (fwd > bwd ? fwd : bwd) + 256;
+  size_t need = fwd > bwd ? fwd : bwd;
+  // small-batch single-launch form (ntxent_small.cu); sized independently of the device so that the answer is the
+  // same with and without a GPU
+  if (batch <= 4096 && dim <= 512) {
+    const size_t sf = small_fwd_workspace_bytes(n_pairs, batch), sb = small_bwd_workspace_bytes(n_tensors, batch, dim);
+    if (batch <= 1024) need = need > sb ? need : sb;
+    need = need > sf ? need : sf;
+  }
+  return need + 256 + 256;  // the last 256 bytes: combined upstream gradients of tcl_ntxent_loss_bwd_total
 }
 
-extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
-                                   int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
-                                   const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
-                                   void* state, size_t state_bytes, void* workspace, size_t workspace_bytes,
-                                   float* loss, void* stream) {
+static int loss_fwd_impl(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                         int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                         int op_format, float inv_tau, float alpha, float eps, void* state, size_t state_bytes,
+                         void* workspace, size_t workspace_bytes, float* loss, bool want_total, void* stream) {
   TCL_REQUIRE(n_tensors >= 2 && n_tensors <= TCL_MAX_TENSORS && n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG,
               "loss_fwd: %d tensors / %d pairs", n_tensors, n_pairs);
   TCL_REQUIRE(x && pair_row && pair_col && state && workspace && loss, TCL_ERR_BAD_ARG, "loss_fwd: null pointer");
@@ -68,6 +89,12 @@ extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dt
     z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
     inv[m] = reinterpret_cast<float*>(st8 + L.inv) + static_cast<size_t>(m) * batch;
   }
+  if (small_enabled(n_tensors, n_pairs, batch, dim, op_format) && workspace_bytes >= small_fwd_workspace_bytes(n_pairs, batch))
+    return launch_small_fwd(n_tensors, x, x_dtype, batch, dim, x_row_stride, n_pairs, pair_row, pair_col, op_format, inv_tau,
+                            alpha, eps, z, inv, reinterpret_cast<float*>(st8 + L.diag2),
+                            reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
+                            reinterpret_cast<float*>(st8 + L.parts), loss, want_total, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
   if (int e = tcl_l2norm_fwd(n_tensors, x, x_dtype, batch, dim, x_row_stride, z, 0, op_format, inv, eps, stream)) return e;
   const void* zrow[TCL_MAX_PAIRS];
   const void* zcol[TCL_MAX_PAIRS];
@@ -80,19 +107,43 @@ extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dt
   float* row_sum = reinterpret_cast<float*>(st8 + L.row_sum);
   float* col_sum = reinterpret_cast<float*>(st8 + L.col_sum);
   float* diag2 = reinterpret_cast<float*>(st8 + L.diag2);
-  return ntxent_fwd_finalize_fused(n_pairs, zrow, zcol, batch, dim, op_format, inv_tau, alpha, row_sum, col_sum, diag2,
-                                   reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
-                                   reinterpret_cast<float*>(st8 + L.parts), loss, workspace, workspace_bytes, stream);
+  if (int e = ntxent_fwd_finalize_fused(n_pairs, zrow, zcol, batch, dim, op_format, inv_tau, alpha, row_sum, col_sum, diag2,
+                                        reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
+                                        reinterpret_cast<float*>(st8 + L.parts), loss, workspace, workspace_bytes, stream))
+    return e;
+  if (want_total) {
+    LaunchCfg lc(dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream));
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, sum_losses_kernel, loss, n_pairs));
+  }
+  return TCL_OK;
 }
 
-extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
                                    int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
                                    const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
-                                   const void* state, const float* grad_losses, const uint8_t* need_grad,
-                                   void* const* dx, void* workspace, size_t workspace_bytes, void* stream) {
+                                   void* state, size_t state_bytes, void* workspace, size_t workspace_bytes,
+                                   float* loss, void* stream) {
+  return loss_fwd_impl(n_tensors, x, x_dtype, batch, dim, x_row_stride, n_pairs, pair_row, pair_col, op_format, inv_tau,
+                       alpha, eps, state, state_bytes, workspace, workspace_bytes, loss, false, stream);
+}
+extern "C" int tcl_ntxent_loss_fwd_total(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                                         int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
+                                         const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
+                                         void* state, size_t state_bytes, void* workspace, size_t workspace_bytes,
+                                         float* loss, void* stream) {
+  return loss_fwd_impl(n_tensors, x, x_dtype, batch, dim, x_row_stride, n_pairs, pair_row, pair_col, op_format, inv_tau,
+                       alpha, eps, state, state_bytes, workspace, workspace_bytes, loss, true, stream);
+}
+
+static int loss_bwd_impl(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                         int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                         int op_format, float inv_tau, float alpha, float eps, const void* state,
+                         const float* grad_losses, const float* grad_total, const uint8_t* need_grad, void* const* dx,
+                         void* workspace, size_t workspace_bytes, void* stream) {
   TCL_REQUIRE(n_tensors >= 2 && n_tensors <= TCL_MAX_TENSORS && n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG,
               "loss_bwd: %d tensors / %d pairs", n_tensors, n_pairs);
-  TCL_REQUIRE(x && pair_row && pair_col && state && workspace && grad_losses && need_grad && dx, TCL_ERR_BAD_ARG, "loss_bwd: null pointer");
+  TCL_REQUIRE(x && pair_row && pair_col && state && workspace && (grad_losses || grad_total) && need_grad && dx, TCL_ERR_BAD_ARG,
+              "loss_bwd: null pointer");
   TCL_REQUIRE(workspace_bytes >= tcl_ntxent_loss_workspace_bytes(n_tensors, n_pairs, batch, dim), TCL_ERR_WORKSPACE, "loss_bwd: workspace too small");
   TCL_REQUIRE(aligned_to(workspace, 256), TCL_ERR_BAD_ALIGN, "loss_bwd: workspace must be 256-byte aligned");
   const LossState L = loss_state_layout(n_tensors, n_pairs, batch, dim);
@@ -104,6 +155,19 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
   for (int m = 0; m < n_tensors; ++m) {
     z[m] = st8 + L.z + static_cast<size_t>(m) * batch * dim * 2;
     zt[m] = ws8 + static_cast<size_t>(m) * dim * ld_t * 2;
+  }
+  if (small_enabled(n_tensors, n_pairs, batch, dim, op_format) && workspace_bytes >= small_bwd_workspace_bytes(n_tensors, batch, dim))
+    return launch_small_bwd(n_tensors, x, x_dtype, batch, dim, x_row_stride, n_pairs, pair_row, pair_col, op_format, inv_tau,
+                            alpha, eps, z, reinterpret_cast<const float*>(st8 + L.inv),
+                            reinterpret_cast<const float*>(st8 + L.lse_row), reinterpret_cast<const float*>(st8 + L.lse_col),
+                            grad_losses, grad_total, need_grad, dx, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
+  if (grad_total != nullptr) {
+    // the multi-kernel forms read ONE array of upstream gradients: combine into the reserved tail of the workspace
+    float* comb = reinterpret_cast<float*>(ws8 + tcl_ntxent_loss_workspace_bytes(n_tensors, n_pairs, batch, dim) - 256);
+    LaunchCfg lc(dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream));
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, combine_grads_kernel, grad_losses, grad_total, n_pairs, comb));
+    grad_losses = comb;
   }
   const size_t zt_bytes = align_up(static_cast<size_t>(n_tensors) * dim * ld_t * 2, 256);
   const bool need_t = tcl_ntxent_bwd_needs_transpose(dim) != 0 && !bwd_sharedg_enabled(n_pairs, batch, dim);
@@ -165,4 +229,23 @@ extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dt
   if (n_jobs == 0) return TCL_OK;
   return tcl_ntxent_bwd(n_jobs, jobs, batch, batch, dim, 0, 0, ld_t, x_dtype, x_row_stride, op_format, inv_tau, eps,
                         ws8 + zt_bytes, workspace_bytes - zt_bytes, stream);
+}
+
+extern "C" int tcl_ntxent_loss_bwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                                   int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
+                                   const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
+                                   const void* state, const float* grad_losses, const uint8_t* need_grad,
+                                   void* const* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  TCL_REQUIRE(grad_losses != nullptr, TCL_ERR_BAD_ARG, "loss_bwd: null pointer");
+  return loss_bwd_impl(n_tensors, x, x_dtype, batch, dim, x_row_stride, n_pairs, pair_row, pair_col, op_format, inv_tau,
+                       alpha, eps, state, grad_losses, nullptr, need_grad, dx, workspace, workspace_bytes, stream);
+}
+extern "C" int tcl_ntxent_loss_bwd_total(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,
+                                         int64_t x_row_stride, int n_pairs, const int32_t* pair_row,
+                                         const int32_t* pair_col, int op_format, float inv_tau, float alpha, float eps,
+                                         const void* state, const float* grad_losses, const float* grad_total,
+                                         const uint8_t* need_grad, void* const* dx, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  return loss_bwd_impl(n_tensors, x, x_dtype, batch, dim, x_row_stride, n_pairs, pair_row, pair_col, op_format, inv_tau,
+                       alpha, eps, state, grad_losses, grad_total, need_grad, dx, workspace, workspace_bytes, stream);
 }

@@ -46,10 +46,13 @@ def _prep(feats):
 
 
 class _FusedNTXent(torch.autograd.Function):
-    """losses[p] for every pair (a, b), a < b, of the given feature matrices.
+    """(losses[p] for every pair (a, b), a < b, of the given feature matrices; their sum).
 
-    Two library calls per step: tcl_ntxent_loss_fwd (K1 -> K2 -> reduce -> finalise) and
-    tcl_ntxent_loss_bwd (transpose -> K3 -> normalise backward); see include/tricolo_b200.h."""
+    Two library calls per step: tcl_ntxent_loss_fwd_total (K1 -> K2 -> reduce -> finalise, or ONE cooperative kernel
+    at small batch) and tcl_ntxent_loss_bwd_total (G -> gradient GEMMs -> normalise backward, or ONE cooperative
+    kernel); see include/tricolo_b200.h.  The sum is an output of the forward and its upstream gradient an input of
+    the backward, so `total_loss.backward()` (tricolo_net.py:64, the training step) runs no framework kernels between
+    the two calls except autograd's own ones_like for the root gradient."""
 
     @staticmethod
     def forward(ctx, temperature: float, alpha: float, op_format: int, pairs, *feats: torch.Tensor):
@@ -64,32 +67,39 @@ class _FusedNTXent(torch.autograd.Function):
         ws_bytes = LIB.tcl_ntxent_loss_workspace_bytes(n, p, b, d)
         state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        loss = torch.empty((p,), dtype=torch.float32, device=dev)
+        loss = torch.empty((p + 1,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            L.check(LIB.tcl_ntxent_loss_fwd(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr, pc,
-                                            op_format, inv_tau, alpha, ops.EPS, state.data_ptr(), state_bytes,
-                                            ws.data_ptr(), ws_bytes, loss.data_ptr(), L.stream_ptr(dev)))
+            L.check(LIB.tcl_ntxent_loss_fwd_total(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr,
+                                                  pc, op_format, inv_tau, alpha, ops.EPS, state.data_ptr(), state_bytes,
+                                                  ws.data_ptr(), ws_bytes, loss.data_ptr(), L.stream_ptr(dev)))
         ctx.cfg = (inv_tau, float(alpha), op_format, pr, pc, ws_bytes)
         ctx.save_for_backward(state, *xs)
-        return loss
+        ctx.set_materialize_grads(False)  # an unused output arrives as None, not as a zeros kernel
+        return loss[:p], loss[p]
 
     @staticmethod
-    def backward(ctx, grad_losses: torch.Tensor):
+    def backward(ctx, grad_losses, grad_total):
         inv_tau, alpha, op_format, pr, pc, ws_bytes = ctx.cfg
         state, *xs = ctx.saved_tensors
         n, p = len(xs), len(pr)
         b, d = xs[0].shape
         dev = xs[0].device
-        if grad_losses.dtype != torch.float32 or not grad_losses.is_contiguous():
+        if grad_losses is None and grad_total is None:
+            return (None,) * (4 + n)
+        if grad_losses is not None and (grad_losses.dtype != torch.float32 or not grad_losses.is_contiguous()):
             grad_losses = grad_losses.to(torch.float32).contiguous()
+        if grad_total is not None and grad_total.dtype != torch.float32:
+            grad_total = grad_total.to(torch.float32)
         need = (C.c_uint8 * n)(*[1 if ctx.needs_input_grad[4 + m] else 0 for m in range(n)])
         dx_all = torch.empty((n, b, d), dtype=xs[0].dtype, device=dev)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         dxs = (C.c_void_p * n)(*[dx_all.data_ptr() + m * b * d * dx_all.element_size() for m in range(n)])
         with torch.cuda.device(dev):
-            L.check(LIB.tcl_ntxent_loss_bwd(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr, pc,
-                                            op_format, inv_tau, alpha, ops.EPS, state.data_ptr(), grad_losses.data_ptr(),
-                                            need, dxs, ws.data_ptr(), ws_bytes, L.stream_ptr(dev)))
+            L.check(LIB.tcl_ntxent_loss_bwd_total(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr,
+                                                  pc, op_format, inv_tau, alpha, ops.EPS, state.data_ptr(),
+                                                  None if grad_losses is None else grad_losses.data_ptr(),
+                                                  None if grad_total is None else grad_total.data_ptr(),
+                                                  need, dxs, ws.data_ptr(), ws_bytes, L.stream_ptr(dev)))
         grads = [dx_all[m] if need[m] else None for m in range(n)]
         return (None, None, None, None, *grads)
 
@@ -97,6 +107,13 @@ class _FusedNTXent(torch.autograd.Function):
 def trimodal_ntxent(feats: Sequence[torch.Tensor], temperature: float, alpha: float,
                     op_format: int = DEFAULT_OP_FORMAT) -> torch.Tensor:
     """Per-pair losses [n_pairs] (fp32) for all unordered pairs of `feats`, in combinations() order."""
+    return trimodal_ntxent_total(feats, temperature, alpha, op_format)[0]
+
+
+def trimodal_ntxent_total(feats: Sequence[torch.Tensor], temperature: float, alpha: float,
+                          op_format: int = DEFAULT_OP_FORMAT) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(per-pair losses [n_pairs], their sum as a 0-dim tensor), both fp32 and both differentiable; backpropagating
+    through the sum alone costs no framework kernels (see _FusedNTXent)."""
     feats = list(feats)
     if len(feats) < 2 or len(feats) > 3:
         raise ValueError("expected 2 or 3 feature matrices")
@@ -127,10 +144,14 @@ class NTXentLoss(torch.nn.Module):
             raise NotImplementedError(
                 "tricolo_b200.NTXentLoss supports norm=True only (the only mode TriCoLoNet uses, "
                 "tricolo_net.py:63); there is no fallback path")
-        return trimodal_ntxent([zis, zjs], self.temperature, self.alpha_weight, self.op_format)[0]
+        # one pair: the sum output IS the pair's loss (0 + l in fp32), and needs no select / select-backward kernels
+        return trimodal_ntxent_total([zis, zjs], self.temperature, self.alpha_weight, self.op_format)[1]
 
     def fused(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:
         return trimodal_ntxent(feats, self.temperature, self.alpha_weight, self.op_format)
+
+    def fused_total(self, feats: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        return trimodal_ntxent_total(feats, self.temperature, self.alpha_weight, self.op_format)
 
 
 def calculate_losses(output_dict: Dict[str, torch.Tensor], loss_prefix: str, loss_fn: NTXentLoss) -> Dict[str, torch.Tensor]:
@@ -140,9 +161,10 @@ def calculate_losses(output_dict: Dict[str, torch.Tensor], loss_prefix: str, los
     calculate_losses(out, prefix, self.loss_fn).
     """
     keys = list(output_dict.keys())
-    losses = loss_fn.fused([output_dict[k] for k in keys])
+    losses, total = loss_fn.fused_total([output_dict[k] for k in keys])
     loss_dict = {}
     for p, (a, b) in enumerate(combinations(keys, 2)):
         loss_dict[f"{loss_prefix}/{a[:-9]}_{b[:-9]}_loss"] = losses[p]
-    loss_dict[f"{loss_prefix}/total_loss"] = sum(loss_dict.values())
+    # sum(loss_dict.values()) of tricolo_net.py:64, formed by the forward itself (fp32, pair order)
+    loss_dict[f"{loss_prefix}/total_loss"] = total
     return loss_dict
