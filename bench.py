@@ -335,7 +335,11 @@ def run_ours(args, rank, world, local_rank):
         kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9,
                                    "frac_of_hbm_peak": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm_gbs"]})
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
-    bwd_kernel = "ntxent_ggemm_kernel" if bwd_mode == "sharedg" else "ntxent_bwd_pc_kernel"
+    # the CTA-pair kernel (cta_group::2) is the default gradient GEMM; TRICOLO_B200_GGEMM=1sm keeps the one-SM kernel
+    ggemm = "ntxent_ggemm_kernel" if os.environ.get("TRICOLO_B200_GGEMM") == "1sm" else "ntxent_ggemm2_kernel"
+    bwd_kernel = ggemm if bwd_mode == "sharedg" else "ntxent_bwd_pc_kernel"
+    if bwd_mode == "sharedg" and "ntxent_bwd" in kern:
+        kern["ntxent_bwd"]["kernel"] = ggemm
     traffic, traffic_src = None, None
     try:  # DRAM bytes per launch of the same kernel at the same shapes, from the newest committed ncu capture
         cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))

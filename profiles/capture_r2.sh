@@ -11,5 +11,7 @@ ncu --set full --clock-control none --import-source on -k regex:"sim_gemm_reside
     python profiles/prof_step.py retrieval > gpurun_out/${tag}_twokernel.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"topk_rank" -c 1 -o gpurun_out/${tag}_shard -f \
     python profiles/prof_step.py shard > gpurun_out/${tag}_shard.log 2>&1
-tail -2 gpurun_out/${tag}_loss.log gpurun_out/${tag}_fused.log gpurun_out/${tag}_twokernel.log gpurun_out/${tag}_shard.log
+ncu --set full --clock-control none --import-source on -k regex:"ntxent_small" -s 2 -c 2 -o gpurun_out/${tag}_small -f \
+    python profiles/prof_step.py loss 256 > gpurun_out/${tag}_small.log 2>&1
+tail -2 gpurun_out/${tag}_small.log gpurun_out/${tag}_loss.log gpurun_out/${tag}_fused.log gpurun_out/${tag}_twokernel.log gpurun_out/${tag}_shard.log
 ls -la gpurun_out/${tag}_*

@@ -169,7 +169,7 @@ struct FwdPartials {
 int ntxent_fwd_finalize_fused(int n_pairs, const void* const* zrow, const void* const* zcol, int64_t batch, int64_t dim,
                               int op_format, float inv_tau, float alpha, float* row_sumexp, float* col_sumexp,
                               float* diag2, float* lse2_row, float* lse2_col, float* loss_parts, float* loss,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              void* workspace, size_t workspace_bytes, void* stream, bool want_total = false);
 // sim_gemm_resident.cu: retrieval GEMM with the query block resident (dim % 64 == 0, dim <= 512)
 int launch_sim_gemm_resident(const void* q, const void* g, int64_t n_q, int64_t n_g, int64_t dim, int op_format,
                              float* s, int64_t ld_s, cudaStream_t st);

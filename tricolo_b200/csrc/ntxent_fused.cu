@@ -30,13 +30,6 @@ static LossState loss_state_layout(int n_tensors, int n_pairs, int64_t batch, in
   return L;
 }
 
-// loss[n] = loss[0] + ... + loss[n - 1] in fp32, pair order: sum(loss_dict.values()), tricolo_net.py:64
-__global__ void sum_losses_kernel(float* loss, int n) {
-  griddep_wait();
-  float t = 0.f;
-  for (int p = 0; p < n; ++p) t += loss[p];
-  loss[n] = t;
-}
 // out[p] = d/d loss[p] + d/d (sum of the losses); either input may be null
 __global__ void combine_grads_kernel(const float* grad_losses, const float* grad_total, int n, float* out) {
   griddep_wait();
@@ -107,15 +100,11 @@ static int loss_fwd_impl(int n_tensors, const void* const* x, int x_dtype, int64
   float* row_sum = reinterpret_cast<float*>(st8 + L.row_sum);
   float* col_sum = reinterpret_cast<float*>(st8 + L.col_sum);
   float* diag2 = reinterpret_cast<float*>(st8 + L.diag2);
-  if (int e = ntxent_fwd_finalize_fused(n_pairs, zrow, zcol, batch, dim, op_format, inv_tau, alpha, row_sum, col_sum, diag2,
-                                        reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
-                                        reinterpret_cast<float*>(st8 + L.parts), loss, workspace, workspace_bytes, stream))
-    return e;
-  if (want_total) {
-    LaunchCfg lc(dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream));
-    TCL_CHECK_CUDA(cudaLaunchKernelEx(&lc.cfg, sum_losses_kernel, loss, n_pairs));
-  }
-  return TCL_OK;
+  // the sum of the pair losses (want_total) is added by the last pair's finalise cluster
+  return ntxent_fwd_finalize_fused(n_pairs, zrow, zcol, batch, dim, op_format, inv_tau, alpha, row_sum, col_sum, diag2,
+                                   reinterpret_cast<float*>(st8 + L.lse_row), reinterpret_cast<float*>(st8 + L.lse_col),
+                                   reinterpret_cast<float*>(st8 + L.parts), loss, workspace, workspace_bytes, stream,
+                                   want_total);
 }
 
 extern "C" int tcl_ntxent_loss_fwd(int n_tensors, const void* const* x, int x_dtype, int64_t batch, int64_t dim,

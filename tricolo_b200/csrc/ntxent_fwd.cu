@@ -15,6 +15,7 @@
 //   sums of the tile are reduced over the 128 rows with a register butterfly
 //   (quad TMEM load layout) and written to a per-(i-block) partial buffer, so the
 //   final sums are formed in a fixed order (deterministic, no atomics).
+#include <atomic>
 #include "host_common.h"
 #include "../../include/tricolo_b200.h"
 
@@ -688,11 +689,15 @@ __global__ void fwd_reduce_kernel(const float* __restrict__ row_part, const floa
 // lse + loss; one cluster of FIN_CTAS blocks per pair, fixed-order trees (inside a block, then over the blocks in
 // rank order through distributed shared memory) so the result is reproducible and needs no global scratch
 static constexpr int FIN_CTAS = 8;
+static constexpr int FIN_LANES = 8;
+// pairs whose loss has been written, per launch lane (host counter): the last one adds the pair losses; self-resetting
+__device__ unsigned int g_fin_done[FIN_LANES];
 __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
     int n_rows, int n_cols, int row_offset, float c1, float alpha, float* __restrict__ row_sum,
     float* __restrict__ col_sum, const float* __restrict__ diag2, float* __restrict__ lse2_row,
     float* __restrict__ lse2_col, float* __restrict__ loss_parts, float* __restrict__ loss,
-    const float* __restrict__ row_part, const float* __restrict__ col_part, int n_row_slots, int n_iblocks) {
+    const float* __restrict__ row_part, const float* __restrict__ col_part, int n_row_slots, int n_iblocks,
+    int total_lane) {  // >= 0: loss[n_pairs] = sum of the pair losses (fp32, pair order), by the last pair to finish
   griddep_launch();
   griddep_wait();
   const int pair = blockIdx.y;
@@ -756,8 +761,20 @@ __global__ void __launch_bounds__(1024) fwd_finalize_kernel(
     const double pa = ta * ln2, pb = tb * ln2;
     loss_parts[pair * 2 + 0] = static_cast<float>(pa);
     loss_parts[pair * 2 + 1] = static_cast<float>(pb);
-    if (loss != nullptr)
-      loss[pair] = static_cast<float>((alpha * pa + (1.0 - alpha) * pb) / n_cols);
+    if (loss != nullptr) {
+      __stcg(loss + pair, static_cast<float>((alpha * pa + (1.0 - alpha) * pb) / n_cols));
+      if (total_lane >= 0) {
+        const int n_pairs = gridDim.y;
+        __threadfence();
+        if (atomicAdd(g_fin_done + total_lane, 1u) + 1u == static_cast<unsigned int>(n_pairs)) {
+          g_fin_done[total_lane] = 0u;
+          __threadfence();
+          float t = 0.f;
+          for (int p = 0; p < n_pairs; ++p) t += __ldcg(loss + p);  // sum(loss_dict.values()), tricolo_net.py:64
+          loss[n_pairs] = t;
+        }
+      }
+    }
   }
 }
 
@@ -1056,7 +1073,9 @@ extern "C" int tcl_ntxent_fwd(int n_pairs, const void* const* zrow, const void* 
 static int ntxent_finalize_impl(int n_pairs, int64_t n_rows, int64_t n_cols, int64_t row_offset,
                                 float inv_tau, float alpha, float* row_sumexp, float* col_sumexp,
                                 const float* diag2, float* lse2_row, float* lse2_col, float* loss_parts, float* loss,
-                                void* stream, const FwdPartials* parts) {
+                                void* stream, const FwdPartials* parts, bool want_total = false) {
+  static std::atomic<unsigned> next_lane{0};
+  const int total_lane = (want_total && loss) ? static_cast<int>(next_lane.fetch_add(1u) % FIN_LANES) : -1;
   TCL_REQUIRE(n_pairs >= 1 && n_pairs <= TCL_MAX_PAIRS, TCL_ERR_BAD_ARG, "finalize: n_pairs %d", n_pairs);
   TCL_REQUIRE(n_rows >= 1 && n_cols >= 1, TCL_ERR_BAD_SHAPE, "finalize: sizes");
   TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && lse2_row && lse2_col && loss_parts, TCL_ERR_BAD_ARG, "finalize: null pointer");
@@ -1072,7 +1091,7 @@ static int ntxent_finalize_impl(int n_pairs, int64_t n_rows, int64_t n_cols, int
     const float* cp = parts ? parts->col_part : nullptr;
     TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, fwd_finalize_kernel, (int)n_rows, (int)n_cols, (int)row_offset, c1, alpha,
                                       row_sumexp, col_sumexp, diag2, lse2_row, lse2_col, loss_parts, loss, rp, cp,
-                                      parts ? parts->n_row_slots : 0, parts ? parts->n_iblocks : 0));
+                                      parts ? parts->n_row_slots : 0, parts ? parts->n_iblocks : 0, total_lane));
   }
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
@@ -1092,7 +1111,7 @@ namespace tcl {
 int ntxent_fwd_finalize_fused(int n_pairs, const void* const* zrow, const void* const* zcol, int64_t batch, int64_t dim,
                               int op_format, float inv_tau, float alpha, float* row_sumexp, float* col_sumexp,
                               float* diag2, float* lse2_row, float* lse2_col, float* loss_parts, float* loss,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              void* workspace, size_t workspace_bytes, void* stream, bool want_total) {
   // Small batches are launch-bound: the finalise cluster reduces the partials itself (B = 256: 15 -> 9 us).  At
   // large batches the partials are megabytes and the wide reduce kernel in front of the finalise is faster.
   const bool fuse = batch <= 2048;
@@ -1101,7 +1120,7 @@ int ntxent_fwd_finalize_fused(int n_pairs, const void* const* zrow, const void* 
                               diag2, workspace, workspace_bytes, stream, fuse ? &parts : nullptr))
     return e;
   return ntxent_finalize_impl(n_pairs, batch, batch, 0, inv_tau, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col,
-                              loss_parts, loss, stream, fuse ? &parts : nullptr);
+                              loss_parts, loss, stream, fuse ? &parts : nullptr, want_total);
 }
 }  // namespace tcl
 
