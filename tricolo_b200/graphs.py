@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from .loss.nt_xent import DEFAULT_OP_FORMAT, trimodal_ntxent
+from .loss.nt_xent import DEFAULT_OP_FORMAT, trimodal_ntxent_total
 
 
 class GraphedTrimodalLoss:
@@ -27,25 +27,26 @@ class GraphedTrimodalLoss:
             from .distributed import global_trimodal_ntxent
 
             def fn(fs):
-                return global_trimodal_ntxent(fs, temperature, alpha, group, op_format=op_format)
+                losses = global_trimodal_ntxent(fs, temperature, alpha, group, op_format=op_format)
+                return losses, losses.sum()
         else:
-            def fn(fs):
-                return trimodal_ntxent(fs, temperature, alpha, op_format=op_format)
+            def fn(fs):  # the sum comes out of the forward call itself: no framework kernels inside the graph
+                return trimodal_ntxent_total(fs, temperature, alpha, op_format=op_format)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 for f in self.static_in:
                     f.grad = None
-                fn(self.static_in).sum().backward()
+                fn(self.static_in)[1].backward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         for f in self.static_in:
             f.grad = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.losses = fn(self.static_in)
-            self.losses.sum().backward()
+            self.losses, total = fn(self.static_in)
+            total.backward()
         self.grads: List[Optional[torch.Tensor]] = [f.grad for f in self.static_in]
 
     def replay(self):

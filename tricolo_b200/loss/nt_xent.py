@@ -11,6 +11,8 @@ implementation of the math in this package.
 """
 from __future__ import annotations
 
+import functools
+import os
 from itertools import combinations
 from typing import Dict, List, Sequence, Tuple
 
@@ -31,6 +33,32 @@ DEFAULT_OP_FORMAT = ops.F16
 
 def _pairs(n: int) -> List[Tuple[int, int]]:
     return list(combinations(range(n), 2))
+
+
+@functools.lru_cache(maxsize=64)
+def _plan(n: int, pairs: Tuple[Tuple[int, int], ...], b: int, d: int, env):
+    """Per-shape constants of the two library calls (the pair index arrays and the buffer sizes): a training loop
+    calls with one shape, and at small batch the host side of a step is longer than its device side.  `env`: the
+    switches the library reads per call and that change the workspace size."""
+    p = len(pairs)
+    pr = (C.c_int32 * p)(*[a for a, _ in pairs])
+    pc = (C.c_int32 * p)(*[c for _, c in pairs])
+    return pr, pc, LIB.tcl_ntxent_loss_state_bytes(n, p, b, d), LIB.tcl_ntxent_loss_workspace_bytes(n, p, b, d)
+
+
+class _OnDevice:
+    """`with torch.cuda.device(dev)` only when `dev` is not already current (the context manager costs ~10 us)."""
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
 
 
 def _prep(feats):
@@ -61,14 +89,12 @@ class _FusedNTXent(torch.autograd.Function):
         n, p = len(xs), len(pairs)
         b, d = xs[0].shape
         inv_tau = 1.0 / float(temperature)
-        pr = (C.c_int32 * p)(*[a for a, _ in pairs])
-        pc = (C.c_int32 * p)(*[c for _, c in pairs])
-        state_bytes = LIB.tcl_ntxent_loss_state_bytes(n, p, b, d)
-        ws_bytes = LIB.tcl_ntxent_loss_workspace_bytes(n, p, b, d)
+        env = os.environ.get
+        pr, pc, state_bytes, ws_bytes = _plan(n, tuple(pairs), b, d, (env("TRICOLO_B200_BWD"), env("TRICOLO_B200_SMALL")))
         state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         loss = torch.empty((p + 1,), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             L.check(LIB.tcl_ntxent_loss_fwd_total(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr,
                                                   pc, op_format, inv_tau, alpha, ops.EPS, state.data_ptr(), state_bytes,
                                                   ws.data_ptr(), ws_bytes, loss.data_ptr(), L.stream_ptr(dev)))
@@ -94,7 +120,7 @@ class _FusedNTXent(torch.autograd.Function):
         dx_all = torch.empty((n, b, d), dtype=xs[0].dtype, device=dev)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         dxs = (C.c_void_p * n)(*[dx_all.data_ptr() + m * b * d * dx_all.element_size() for m in range(n)])
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             L.check(LIB.tcl_ntxent_loss_bwd_total(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr,
                                                   pc, op_format, inv_tau, alpha, ops.EPS, state.data_ptr(),
                                                   None if grad_losses is None else grad_losses.data_ptr(),
