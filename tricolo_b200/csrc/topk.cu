@@ -19,6 +19,13 @@ __device__ __forceinline__ bool before(float a, int ia, float b, int ib) {
   return a > b || (a == b && ia < ib);
 }
 
+// warp-wide fp32 maximum in one instruction (sm_100a: redux.sync on f32 -> CREDUX.MAX.F32)
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 template <int K>
 struct TopList {
   float v[K];
@@ -78,23 +85,59 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(
   const float4* row4 = reinterpret_cast<const float4*>(row);
   int g4 = lane;
   // software-pipelined loads (the next 4 x 16 bytes per lane are requested before the current 16 values are consumed)
-  // and a warp-wide entry threshold: the largest k-th value of any lane's list.  That lane alone holds k earlier candidates
-  // that are >= thr, all with smaller column numbers than anything still to come (columns grow from iteration to
-  // iteration), so a value <= thr can no longer enter the row's top-k.  Without it every lane keeps inserting into its
-  // own list (the k-th best of 1/32 of the row is a weak bar): hundreds of divergent insertion passes per row, ~50 us
-  // of a warp's time, whatever the row length.
+  // and a warp-wide entry threshold (see refresh() below): a value <= thr can no longer enter the row's top-k, so the
+  // per-lane sorted lists are only touched by the few values that can.
   float thr = -FLT_MAX;
+  int cnt_eq = 0;
   auto consume = [&](const float4& a, const float4& b, const float4& c, const float4& d, int base4) {
     const float vals[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    // common case in ~3 instructions per value: one compare-and-add for the rank, one equality folded into a
+    // predicate, one max; ties with the ground truth and candidates above the threshold take the slow paths below
+    bool eq = false;
+    float m = vals[0];
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const int col = (base4 + (u >> 2) * 32) * 4 + (u & 3);
       const float x = vals[u];
-      cnt += (x > s_gt) || (x == s_gt && col < gt_cut);
-      if (x > thr) top.push(x, col);
+      cnt += x > s_gt;
+      eq |= x == s_gt;
+      m = fmaxf(m, x);
+    }
+    if (eq) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int col = (base4 + (u >> 2) * 32) * 4 + (u & 3);
+        cnt_eq += (vals[u] == s_gt) && (col < gt_cut);
+      }
+    }
+    if (m > thr) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int col = (base4 + (u >> 2) * 32) * 4 + (u & 3);
+        if (vals[u] > thr) top.push(vals[u], col);
+      }
     }
   };
-  // warp-uniform trip count (the threshold update shuffles over the full warp): whole 512-column chunks only
+  // EXACT k-th largest value of everything the warp has consumed so far, without touching the lists: k rounds of a
+  // warp-wide max over per-lane cursors into the (sorted) lane lists.  Called between chunks only, when every consumed
+  // column is smaller than every column still to come, so a later value <= thr loses against k earlier candidates
+  // (ties included) and can be skipped.  The max over lanes of the lanes' own k-th value used before is a far weaker
+  // bar (the k-th best of 1/32 of the row): ncu showed 28 warp instructions per value on 25k-column rows, i.e. the
+  // kernel was issue-bound by divergent insertions (sm 84 %, dram 54 %).
+  auto refresh = [&]() {
+    int p = 0;
+    float t = -FLT_MAX;
+    for (int r = 0; r < k; ++r) {
+      float c = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < K; ++j) c = (p == j) ? top.v[j] : c;
+      const float mx = warp_max_f32(c);
+      const unsigned who = __ballot_sync(0xffffffffu, c == mx);
+      if (lane == __ffs(who) - 1) ++p;
+      t = mx;
+    }
+    thr = t;
+  };
+  // warp-uniform trip count (the refresh shuffles over the full warp): whole 512-column chunks only
   const int n_full = n_vec >> 7;  // chunks of 128 float4 in which every lane has all four loads
   if (n_full > 0) {
     float4 a = __ldcs(row4 + g4), b = __ldcs(row4 + g4 + 32), c = __ldcs(row4 + g4 + 64), d = __ldcs(row4 + g4 + 96);
@@ -103,15 +146,13 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(
       if (ch + 1 < n_full) {
         na = __ldcs(row4 + g4 + 128); nb = __ldcs(row4 + g4 + 160); nc = __ldcs(row4 + g4 + 192); nd = __ldcs(row4 + g4 + 224);
       }
-      if ((ch & 3) == 0) {  // refresh the threshold every 2048 columns
-        float t = top.v[K - 1];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
-        thr = t;
-      }
+      // refresh after 1, 2, 4, 8 chunks, then every 8: the expected number of later values above the exact k-th of
+      // c chunks is k * (chunks until the next refresh) / c
+      if (ch != 0 && ((ch & (ch - 1)) == 0 || (ch & 7) == 0)) refresh();
       consume(a, b, c, d, g4);
       a = na; b = nb; c = nc; d = nd;
     }
+    refresh();
   }
   for (; g4 < n_vec; g4 += 32) {
     float4 a = __ldcs(row4 + g4);
@@ -135,6 +176,7 @@ __global__ void __launch_bounds__(256) topk_rank_kernel(
   }
 
   // rank: total count
+  cnt += cnt_eq;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
 
