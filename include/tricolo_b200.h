@@ -322,6 +322,28 @@ int tcl_ntxent_loss_bwd_total(int n_tensors, const void* const* x_host_ptrs, int
                               void* const* dx_host_ptrs, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * NTXentLoss.forward(zis, zjs, norm=False): nt_xent.py:55-74 with the F.normalize of :56-57 skipped, and its autograd.
+ * The logits x_i . x_j / tau are unbounded, so this path carries online (max, sum) statistics per row and column and
+ * computes in fp32 on the FMA pipe (16-bit operands cannot give rtol 1e-3 on logits of magnitude 1e2..1e3); the
+ * B x B logits never reach HBM here either.  TriCoLoNet itself only ever calls norm=True (tricolo_net.py:63).
+ *   x, pair_row/col, loss [n_pairs + 1], grad_losses / grad_total, need_grad_host, dx: as tcl_ntxent_loss_*_total
+ *   dim % 16 == 0; x_dtype f32 / f16 / bf16 (converted to fp32 on load; dx in x_dtype, [batch, dim] contiguous)
+ *   state      tcl_ntxent_raw_state_bytes(): natural-log LSEs of the logit rows and columns, forward -> backward
+ *   workspace  tcl_ntxent_raw_workspace_bytes(): forward scratch only
+ * ------------------------------------------------------------------------- */
+size_t tcl_ntxent_raw_state_bytes(int n_pairs, int64_t batch);
+size_t tcl_ntxent_raw_workspace_bytes(int n_pairs, int64_t batch);
+int tcl_ntxent_raw_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t batch, int64_t dim,
+                       int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                       float inv_tau, float alpha, void* state, size_t state_bytes, void* workspace,
+                       size_t workspace_bytes, float* loss, void* stream);
+int tcl_ntxent_raw_bwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t batch, int64_t dim,
+                       int64_t x_row_stride, int n_pairs, const int32_t* pair_row, const int32_t* pair_col,
+                       float inv_tau, float alpha, const void* state, const float* grad_losses,
+                       const float* grad_total, const uint8_t* need_grad_host, void* const* dx_host_ptrs,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------
  * K2' — similarity GEMM for retrieval.           replaces eval_retrieval.py:74 (np.dot)
  * S[q, g] = Q[q,:] · G[g,:] (raw dot product, no normalisation), 16-bit operands,
  * fp32 accumulate, fp32 output with leading dimension ld_s (ld_s % 4 == 0).
@@ -415,7 +437,9 @@ enum {
   TCL_K_RANK_METRICS = 16,
   TCL_K_NTXENT_SMALL_FWD = 17, /* small-batch whole-loss forward, one cooperative launch (csrc/ntxent_small.cu) */
   TCL_K_NTXENT_SMALL_BWD = 18, /* small-batch whole-loss backward, one cooperative launch */
-  TCL_K_COUNT = 19
+  TCL_K_NTXENT_RAW_FWD = 19,   /* norm=False forward tile kernel (csrc/ntxent_raw.cu); its finalise is TCL_K_FWD_FINALIZE */
+  TCL_K_NTXENT_RAW_BWD = 20,   /* norm=False backward */
+  TCL_K_COUNT = 21
 };
 int64_t tcl_launch_count(void);
 int tcl_profile_enable(int on);

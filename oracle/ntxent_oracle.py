@@ -37,8 +37,9 @@ def ntxent_forward(zis, zjs, temperature: float, alpha: float) -> float:
     return alpha * loss_a + (1.0 - alpha) * loss_b
 
 
-def ntxent_forward_backward(zis, zjs, temperature: float, alpha: float, grad_out: float = 1.0):
+def ntxent_forward_backward(zis, zjs, temperature: float, alpha: float, grad_out: float = 1.0, norm: bool = True):
     """Loss and d(loss)/d(zis), d(loss)/d(zjs) in fp64 (closed form of the autograd graph).
+    norm=False: nt_xent.py:55 skips the F.normalize of :56-57; the logits are the raw inner products / tau.
 
     dL/dZ = [alpha softmax_rows(Z) + (1-alpha) softmax_cols(Z) - I] / B
     dzi_hat = dL/dZ zj_hat / tau ; dzj_hat = dL/dZ^T zi_hat / tau
@@ -47,8 +48,11 @@ def ntxent_forward_backward(zis, zjs, temperature: float, alpha: float, grad_out
     xi = np.asarray(zis, dtype=np.float64)
     xj = np.asarray(zjs, dtype=np.float64)
     b = xi.shape[0]
-    zi, ni = _normalise(xi)
-    zj, nj = _normalise(xj)
+    if norm:
+        zi, ni = _normalise(xi)
+        zj, nj = _normalise(xj)
+    else:
+        zi, zj = xi, xj
     z = zi @ zj.T / temperature
     lr = _lse(z, 1)
     lc = _lse(z, 0)
@@ -58,6 +62,8 @@ def ntxent_forward_backward(zis, zjs, temperature: float, alpha: float, grad_out
     g *= grad_out
     gzi = g @ zj / temperature
     gzj = g.T @ zi / temperature
+    if not norm:
+        return loss, gzi, gzj
 
     def norm_bwd(gz, zh, n, x):
         clamped = (np.sqrt((x * x).sum(axis=1, keepdims=True)) < EPS)
@@ -73,7 +79,8 @@ def pair_order(keys):
     return list(combinations(list(keys), 2))
 
 
-def trimodal_forward_backward(features: dict, temperature: float, alpha: float, prefix: str = "train_loss"):
+def trimodal_forward_backward(features: dict, temperature: float, alpha: float, prefix: str = "train_loss",
+                              norm: bool = True):
     """tricolo_net.py:56-65: one bimodal loss per unordered key pair, summed.
 
     Returns (loss_dict with the reference's key names, grads dict keyed like `features`).
@@ -81,7 +88,7 @@ def trimodal_forward_backward(features: dict, temperature: float, alpha: float, 
     losses = {}
     grads = {k: np.zeros(np.asarray(v).shape, dtype=np.float64) for k, v in features.items()}
     for a, b in pair_order(features.keys()):
-        loss, ga, gb = ntxent_forward_backward(features[a], features[b], temperature, alpha)
+        loss, ga, gb = ntxent_forward_backward(features[a], features[b], temperature, alpha, norm=norm)
         losses[f"{prefix}/{a[:-9]}_{b[:-9]}_loss"] = loss  # key[:-9] strips "_features" (tricolo_net.py:62)
         grads[a] += ga
         grads[b] += gb

@@ -53,6 +53,18 @@ def test_argument_validation_without_gpu():
     assert rc == 1
     rc = L.tcl_ntxent_fwd(1, arr, arr, 128, 128, 128, 0, 0, 0, 1000.0, p, p, p, p, 1 << 20, None)  # tau too small
     assert rc == 4 and b"temperature" in L.tcl_last_error_string()
+    # norm=False entry points: dim % 16, dtype, pair indices
+    i3 = (ctypes.c_int32 * 1)(0)
+    i4 = (ctypes.c_int32 * 1)(1)
+    arr2 = (ctypes.c_void_p * 2)(p.value, p.value)
+    rc = L.tcl_ntxent_raw_fwd(2, arr2, 0, 64, 100, 100, 1, i3, i4, 10.0, 0.25, p, 1 << 20, p, 1 << 20, p, None)
+    assert rc == 1 and b"multiple of 16" in L.tcl_last_error_string()
+    rc = L.tcl_ntxent_raw_fwd(2, arr2, 3, 64, 128, 128, 1, i3, i4, 10.0, 0.25, p, 1 << 20, p, 1 << 20, p, None)  # f64
+    assert rc == 4
+    rc = L.tcl_ntxent_raw_fwd(2, arr2, 0, 64, 128, 128, 1, i3, i3, 10.0, 0.25, p, 1 << 20, p, 1 << 20, p, None)  # pair (0, 0)
+    assert rc == 4
+    assert L.tcl_ntxent_raw_state_bytes(3, 8192) == 3 * 8192 * 2 * 4
+    assert L.tcl_ntxent_raw_workspace_bytes(3, 8192) > 3 * 128 * 8192 * 8
     assert L.tcl_ntxent_fwd_workspace_bytes(3, 8192, 8192) > 0
     assert L.tcl_ntxent_bwd_workspace_bytes(3, 8192, 512) >= 3 * 8192 * 512 * 4
 

@@ -199,6 +199,63 @@ def test_bf16_operand_mode_runs_and_is_less_accurate(tb):
     assert errs[tb.ops.BF16] > errs[tb.ops.F16]
 
 
+@pytest.mark.parametrize("name", ["R1", "R2", "R3", "R4"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_unnormalised_loss_and_grads(tb, name, dtype):
+    """norm=False (nt_xent.py:55; csrc/ntxent_raw.cu) against the fp64 oracle AND the reference's own outputs
+    (tests/golden/raw_*.{json,npz}): logits of magnitude 1e1..1e3, online (max, sum) statistics, ragged tiles."""
+    import json
+
+    from tests.cases import raw_case
+
+    feats = raw_case(name)  # bf16-representable values: both input dtypes carry them exactly
+    ref_losses, ref_grads = NO.trimodal_forward_backward({k: v.numpy() for k, v in feats.items()}, TAU, ALPHA, prefix="x",
+                                                        norm=False)
+    with open(os.path.join(HERE, "golden", "raw_outputs.json")) as f:
+        gold = json.load(f)["cases"][name]
+    gz = np.load(os.path.join(HERE, "golden", "raw_grads.npz"))
+    dev = [v.to(dtype).cuda().requires_grad_(True) for v in feats.values()]
+    fn = tb.loss.NTXentLoss(TAU, ALPHA)
+    if len(dev) == 2:
+        total = fn(dev[0], dev[1], norm=False)  # the reference signature
+        losses = total.reshape(1)
+    else:
+        losses, total = fn.fused_total(dev, norm=False)
+    from itertools import combinations
+    names = [f"{a[:-9]}_{b[:-9]}_loss" for a, b in combinations(feats.keys(), 2)]  # pair order of tricolo_net.py:59-61
+    for got, k in zip(losses.tolist(), names):
+        assert got == pytest.approx(gold["losses"][k], rel=RTOL), k
+        assert got == pytest.approx(ref_losses[f"x/{k}"], rel=1e-5, abs=1e-6), k  # fp32 arithmetic: far inside rtol 1e-3
+    assert float(total.detach()) == pytest.approx(gold["total"], rel=RTOL)
+    total.backward()
+    # bf16 gradients are rounded on output: half an ulp = 2^-9 relative per entry
+    # fp32 logits of magnitude 1e3 (R3, R4) carry absolute errors of ~1e-4, in this library and in the fp32 reference
+    # alike: the softmax inherits them as relative errors
+    rt = (1e-5 if name in ("R1", "R2") else 5e-4) if dtype == torch.float32 else 4e-3
+    for x, k in zip(dev, feats.keys()):
+        got = x.grad.double().cpu().numpy()
+        assert x.grad.dtype == dtype
+        ref = ref_grads[k]
+        assert np.linalg.norm(got - ref) <= rt * np.linalg.norm(ref), k
+        assert np.linalg.norm(got[::4] - gz[f"{name}.{k}"]) <= max(rt, 2e-5) * np.linalg.norm(gz[f"{name}.{k}"]), k
+    # upstream scaling and a tensor that needs no gradient
+    dev2 = [v.to(dtype).cuda().requires_grad_(i != 0) for i, v in enumerate(feats.values())]
+    l2 = fn.fused(dev2, norm=False)
+    w = torch.arange(1, l2.numel() + 1, device="cuda", dtype=torch.float32)
+    (l2 * w).sum().backward()
+    assert dev2[0].grad is None
+    acc = np.zeros_like(ref_grads[list(feats)[1]])
+    keys = list(feats)
+    for p, (a, b) in enumerate(combinations(keys, 2)):
+        _, ga, gb = NO.ntxent_forward_backward(feats[a].numpy(), feats[b].numpy(), TAU, ALPHA, grad_out=float(p + 1), norm=False)
+        if a == keys[1]:
+            acc += ga
+        if b == keys[1]:
+            acc += gb
+    got = dev2[1].grad.double().cpu().numpy()
+    assert np.linalg.norm(got - acc) <= rt * np.linalg.norm(acc)
+
+
 def test_unsupported_inputs_raise(tb):
     a = torch.randn(64, 100).cuda()  # dim not a multiple of 64
     fn = tb.loss.NTXentLoss(TAU, ALPHA)

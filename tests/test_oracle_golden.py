@@ -138,3 +138,24 @@ def test_bf16_round_matches_torch():
 
     x = np.random.default_rng(0).standard_normal(10000).astype(np.float32)
     assert np.array_equal(RO.bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+# ---------------------------------------------------------------- norm=False (nt_xent.py:55)
+@pytest.mark.parametrize("name", ["R1", "R2", "R3", "R4"])
+def test_unnormalised_oracle_matches_reference(name):
+    """oracle(norm=False) against the reference's own forward/backward (tests/golden/make_golden_raw.py)."""
+    import json
+
+    from tests.cases import raw_case
+
+    with open(os.path.join(HERE, "golden", "raw_outputs.json")) as f:
+        ref = json.load(f)["cases"][name]
+    z = np.load(os.path.join(HERE, "golden", "raw_grads.npz"))
+    feats = {k: v.numpy() for k, v in raw_case(name).items()}
+    losses, grads = NO.trimodal_forward_backward(feats, TAU, ALPHA, prefix="x", norm=False)
+    for k, v in ref["losses"].items():
+        assert losses[f"x/{k}"] == pytest.approx(v, rel=5e-6, abs=1e-6), k  # fp32 reference vs fp64 oracle
+    assert losses["x/total_loss"] == pytest.approx(ref["total"], rel=5e-6, abs=1e-6)
+    for k, g in grads.items():
+        r = z[f"{name}.{k}"]
+        assert np.linalg.norm(g[::4] - r) <= 2e-5 * np.linalg.norm(r) + 1e-9, k

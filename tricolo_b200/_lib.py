@@ -19,7 +19,7 @@ TCL_DT_F32, TCL_DT_F16, TCL_DT_BF16, TCL_DT_F64 = 0, 1, 2, 3
 KERNEL_IDS = {
     "l2norm_fwd": 0, "cast16": 1, "transpose16": 2, "ntxent_fwd": 3, "fwd_reduce": 4, "fwd_finalize": 5,
     "ntxent_bwd": 6, "l2norm_bwd": 7, "sim_gemm": 8, "topk_rank": 9, "gather_gt": 10, "topk_merge": 11, "sim_topk_fused": 12, "gather_sum": 13, "peer_sum": 14, "ntxent_g": 15, "rank_metrics": 16,
-    "ntxent_small_fwd": 17, "ntxent_small_bwd": 18,
+    "ntxent_small_fwd": 17, "ntxent_small_bwd": 18, "ntxent_raw_fwd": 19, "ntxent_raw_bwd": 20,
 }
 
 _DTYPE_CODE = {
@@ -109,6 +109,12 @@ SIGNATURES = {
                                        _i, _f, _f, _f, _vp, _sz, _vp, _sz, _vp, _vp]),
     "tcl_ntxent_loss_bwd_total": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                        _i, _f, _f, _f, _vp, _vp, _vp, C.POINTER(C.c_uint8), _pp, _vp, _sz, _vp]),
+    "tcl_ntxent_raw_state_bytes": (_sz, [_i, _i64]),
+    "tcl_ntxent_raw_workspace_bytes": (_sz, [_i, _i64]),
+    "tcl_ntxent_raw_fwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                _f, _f, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "tcl_ntxent_raw_bwd": (_i, [_i, _pp, _i, _i64, _i64, _i64, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                _f, _f, _vp, _vp, _vp, C.POINTER(C.c_uint8), _pp, _vp]),
     "tcl_sim_gemm": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _i64, _vp]),
     "tcl_topk_rank": (_i, [_vp, _i64, _i64, _i64, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tcl_gather_gt_sim": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),

@@ -130,16 +130,68 @@ class _FusedNTXent(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _RawNTXent(torch.autograd.Function):
+    """The same outputs as _FusedNTXent for norm=False (nt_xent.py:55: the F.normalize of :56-57 is skipped):
+    tcl_ntxent_raw_fwd / _bwd (csrc/ntxent_raw.cu) - fp32 logit tiles with online (max, sum) statistics."""
+
+    @staticmethod
+    def forward(ctx, temperature: float, alpha: float, pairs, *feats: torch.Tensor):
+        dev = L.require_cuda(*feats)
+        xs = _prep([f.detach() for f in feats])
+        n, p = len(xs), len(pairs)
+        b, d = xs[0].shape
+        inv_tau = 1.0 / float(temperature)
+        pr = (C.c_int32 * p)(*[a for a, _ in pairs])
+        pc = (C.c_int32 * p)(*[c for _, c in pairs])
+        state_bytes, ws_bytes = LIB.tcl_ntxent_raw_state_bytes(p, b), LIB.tcl_ntxent_raw_workspace_bytes(p, b)
+        state = torch.empty((state_bytes,), dtype=torch.uint8, device=dev)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        loss = torch.empty((p + 1,), dtype=torch.float32, device=dev)
+        with _OnDevice(dev):
+            L.check(LIB.tcl_ntxent_raw_fwd(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr, pc,
+                                           inv_tau, alpha, state.data_ptr(), state_bytes, ws.data_ptr(), ws_bytes,
+                                           loss.data_ptr(), L.stream_ptr(dev)))
+        ctx.cfg = (inv_tau, float(alpha), pr, pc)
+        ctx.save_for_backward(state, *xs)
+        ctx.set_materialize_grads(False)
+        return loss[:p], loss[p]
+
+    @staticmethod
+    def backward(ctx, grad_losses, grad_total):
+        inv_tau, alpha, pr, pc = ctx.cfg
+        state, *xs = ctx.saved_tensors
+        n, p = len(xs), len(pr)
+        b, d = xs[0].shape
+        dev = xs[0].device
+        if grad_losses is None and grad_total is None:
+            return (None,) * (3 + n)
+        if grad_losses is not None and (grad_losses.dtype != torch.float32 or not grad_losses.is_contiguous()):
+            grad_losses = grad_losses.to(torch.float32).contiguous()
+        if grad_total is not None and grad_total.dtype != torch.float32:
+            grad_total = grad_total.to(torch.float32)
+        need = (C.c_uint8 * n)(*[1 if ctx.needs_input_grad[3 + m] else 0 for m in range(n)])
+        dx_all = torch.empty((n, b, d), dtype=xs[0].dtype, device=dev)
+        dxs = (C.c_void_p * n)(*[dx_all.data_ptr() + m * b * d * dx_all.element_size() for m in range(n)])
+        with _OnDevice(dev):
+            L.check(LIB.tcl_ntxent_raw_bwd(n, L.ptr_array(xs), L.dtype_code(xs[0]), b, d, xs[0].stride(0), p, pr, pc,
+                                           inv_tau, alpha, state.data_ptr(),
+                                           None if grad_losses is None else grad_losses.data_ptr(),
+                                           None if grad_total is None else grad_total.data_ptr(),
+                                           need, dxs, L.stream_ptr(dev)))
+        return (None, None, None, *[dx_all[m] if need[m] else None for m in range(n)])
+
+
 def trimodal_ntxent(feats: Sequence[torch.Tensor], temperature: float, alpha: float,
-                    op_format: int = DEFAULT_OP_FORMAT) -> torch.Tensor:
+                    op_format: int = DEFAULT_OP_FORMAT, norm: bool = True) -> torch.Tensor:
     """Per-pair losses [n_pairs] (fp32) for all unordered pairs of `feats`, in combinations() order."""
-    return trimodal_ntxent_total(feats, temperature, alpha, op_format)[0]
+    return trimodal_ntxent_total(feats, temperature, alpha, op_format, norm)[0]
 
 
 def trimodal_ntxent_total(feats: Sequence[torch.Tensor], temperature: float, alpha: float,
-                          op_format: int = DEFAULT_OP_FORMAT) -> Tuple[torch.Tensor, torch.Tensor]:
+                          op_format: int = DEFAULT_OP_FORMAT, norm: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """(per-pair losses [n_pairs], their sum as a 0-dim tensor), both fp32 and both differentiable; backpropagating
-    through the sum alone costs no framework kernels (see _FusedNTXent)."""
+    through the sum alone costs no framework kernels (see _FusedNTXent).  norm=False (nt_xent.py:55) takes the fp32
+    path of csrc/ntxent_raw.cu (`op_format` does not apply there)."""
     feats = list(feats)
     if len(feats) < 2 or len(feats) > 3:
         raise ValueError("expected 2 or 3 feature matrices")
@@ -149,6 +201,8 @@ def trimodal_ntxent_total(feats: Sequence[torch.Tensor], temperature: float, alp
             raise ValueError(f"feature matrices must share one [batch, dim] shape, got {tuple(f.shape)} vs {(b, d)}")
     dt = feats[0].dtype
     feats = [f if f.dtype == dt else f.to(dt) for f in feats]
+    if not norm:
+        return _RawNTXent.apply(float(temperature), float(alpha), _pairs(len(feats)), *feats)
     return _FusedNTXent.apply(float(temperature), float(alpha), op_format, _pairs(len(feats)), *feats)
 
 
@@ -165,19 +219,16 @@ class NTXentLoss(torch.nn.Module):
         self.op_format = op_format
 
     def forward(self, zis, zjs, norm=True):
-        if not norm:
-            # nt_xent.py:55 allows norm=False; the fused sum-exp relies on |cos| <= 1.
-            raise NotImplementedError(
-                "tricolo_b200.NTXentLoss supports norm=True only (the only mode TriCoLoNet uses, "
-                "tricolo_net.py:63); there is no fallback path")
-        # one pair: the sum output IS the pair's loss (0 + l in fp32), and needs no select / select-backward kernels
-        return trimodal_ntxent_total([zis, zjs], self.temperature, self.alpha_weight, self.op_format)[1]
+        # one pair: the sum output IS the pair's loss (0 + l in fp32), and needs no select / select-backward kernels.
+        # norm=False (nt_xent.py:55; never used by TriCoLoNet, tricolo_net.py:63) runs the fp32 kernels of
+        # csrc/ntxent_raw.cu: unbounded logits need online (max, sum) statistics and fp32 products.
+        return trimodal_ntxent_total([zis, zjs], self.temperature, self.alpha_weight, self.op_format, norm=bool(norm))[1]
 
-    def fused(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:
-        return trimodal_ntxent(feats, self.temperature, self.alpha_weight, self.op_format)
+    def fused(self, feats: Sequence[torch.Tensor], norm: bool = True) -> torch.Tensor:
+        return trimodal_ntxent(feats, self.temperature, self.alpha_weight, self.op_format, norm)
 
-    def fused_total(self, feats: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
-        return trimodal_ntxent_total(feats, self.temperature, self.alpha_weight, self.op_format)
+    def fused_total(self, feats: Sequence[torch.Tensor], norm: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        return trimodal_ntxent_total(feats, self.temperature, self.alpha_weight, self.op_format, norm)
 
 
 def calculate_losses(output_dict: Dict[str, torch.Tensor], loss_prefix: str, loss_fn: NTXentLoss) -> Dict[str, torch.Tensor]:
