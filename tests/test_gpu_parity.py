@@ -107,8 +107,9 @@ def test_bimodal_module_signature_and_order(tb, golden):
     assert ab == pytest.approx(golden["order"]["ab"], rel=RTOL)
     assert ba == pytest.approx(golden["order"]["ba"], rel=RTOL)
     assert ab != ba  # alpha != 0.5: argument order matters
-    with pytest.raises(NotImplementedError):
-        fn(a, b, norm=False)
+    # norm=False is a different function of the inputs (nt_xent.py:55), same signature
+    assert float(fn(a, b, norm=False)) == pytest.approx(NO.ntxent_forward_backward(a.cpu().numpy(), b.cpu().numpy(), TAU, ALPHA,
+                                                                               norm=False)[0], rel=1e-5)
     with pytest.raises(RuntimeError):
         fn(a.cpu(), b.cpu())  # no CPU path
 

@@ -23,7 +23,6 @@ namespace raw {
 constexpr int RT = 64;      // tile edge (rows of either tensor)
 constexpr int RK = 16;      // dims per operand slice
 constexpr int RP = RT + 4;  // padded row of a k-major slice (rows stay 16-byte aligned)
-constexpr int DC = 128;     // dims of the other tensor handled by one backward CTA
 
 template <typename T>
 __device__ __forceinline__ float4 ld4(const T* p);
@@ -265,10 +264,15 @@ struct BwdParams {
   float inv_tau;
 };
 
-constexpr int kBwdSmem = (2 * RK * RP + RT * (RT + 1) + RT * DC) * 4;
+// DC = dims of the other tensor handled by one backward CTA: the logit tile is re-formed once per DC-wide slice of the
+// gradient, so 256 halves the recompute of 128 at twice the accumulator registers (chosen by the host: 128 while the
+// grid would not fill the GPU otherwise)
+template <int DC>
+constexpr int bwd_smem() { return (2 * RK * RP + RT * (RT + 1) + RT * DC) * 4; }
 
-template <typename T>
+template <typename T, int DC>
 __global__ void __launch_bounds__(256) raw_bwd_kernel(const __grid_constant__ BwdParams P) {
+  constexpr int NH = DC / 64;  // float4 groups per thread and gradient row
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float (*Xs)[RP] = reinterpret_cast<float (*)[RP]>(smem_raw);
   float (*Ys)[RP] = reinterpret_cast<float (*)[RP]>(smem_raw + RK * RP * 4);
@@ -278,11 +282,11 @@ __global__ void __launch_bounds__(256) raw_bwd_kernel(const __grid_constant__ Bw
   const int m = blockIdx.z, i0 = blockIdx.x * RT, dc0 = blockIdx.y * DC, n = P.n;
   if (P.dx[m] == nullptr) return;  // no gradient wanted for this tensor
   const T* X = static_cast<const T*>(P.x[m]);
-  float out[4][8];
+  float out[4][4 * NH];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) out[r][c] = 0.f;
+    for (int c = 0; c < 4 * NH; ++c) out[r][c] = 0.f;
   for (int jb = 0; jb < P.n_job[m]; ++jb) {
     const BwdJob J = P.job[m][jb];
     const T* Y = static_cast<const T*>(P.x[J.other]);
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(256) raw_bwd_kernel(const __grid_constant__ Bw
           Gs[ty * 4 + r][tx * 4 + c] = (i < n && j < n) ? coef * gv : 0.f;
         }
       }
-      // the partner's rows j0.., dims dc0..dc0+127
+      // the partner's rows j0.., dims dc0..dc0+DC-1
 #pragma unroll
       for (int q = 0; q < (RT * DC / 4) / 256; ++q) {
         const int idx = q * 256 + t, row = idx / (DC / 4), c4 = (idx % (DC / 4)) * 4;
@@ -326,16 +330,19 @@ __global__ void __launch_bounds__(256) raw_bwd_kernel(const __grid_constant__ Bw
         *reinterpret_cast<float4*>(&Yc[row][c4]) = v;
       }
       __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
       for (int k = 0; k < RT; ++k) {
-        const float4 y0 = *reinterpret_cast<const float4*>(&Yc[k][tx * 4]);
-        const float4 y1 = *reinterpret_cast<const float4*>(&Yc[k][64 + tx * 4]);
-        const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+        float gk[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float gk = Gs[ty * 4 + r][k];
+        for (int r = 0; r < 4; ++r) gk[r] = Gs[ty * 4 + r][k];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) out[r][c] = fmaf(gk, yv[c], out[r][c]);
+        for (int h = 0; h < NH; ++h) {
+          const float4 y = *reinterpret_cast<const float4*>(&Yc[k][h * 64 + tx * 4]);
+          const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[r][h * 4 + c] = fmaf(gk[r], yv[c], out[r][h * 4 + c]);
         }
       }
       __syncthreads();
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(256) raw_bwd_kernel(const __grid_constant__ Bw
     const int i = i0 + ty * 4 + r;
     if (i >= n) continue;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NH; ++h) {
       const int c = dc0 + h * 64 + tx * 4;
       if (c < P.dim) {
         const float v[4] = {out[r][h * 4 + 0], out[r][h * 4 + 1], out[r][h * 4 + 2], out[r][h * 4 + 3]};
@@ -508,22 +515,20 @@ extern "C" int tcl_ntxent_raw_bwd(int n_tensors, const void* const* x, int x_dty
   B.n = static_cast<int>(batch); B.dim = static_cast<int>(dim); B.n_rt = static_cast<int>((batch + RT - 1) / RT);
   B.stride = x_row_stride; B.inv_tau = inv_tau;
   // grid z = tensor; the CTAs of a tensor that needs no gradient leave at once
-  const dim3 grid(B.n_rt, static_cast<unsigned>((dim + DC - 1) / DC), n_tensors);
+  const bool wide = dim > 128 && static_cast<int64_t>(B.n_rt) * ((dim + 255) / 256) * n_tensors >= 2 * kNumSMsB200;
   ProfScope prof(TCL_K_NTXENT_RAW_BWD, st);
+#define TCL_RAW_BWD(T, DCV)                                                                                   \
+  do {                                                                                                        \
+    if (int e = ensure_dyn_smem(raw_bwd_kernel<T, DCV>, bwd_smem<DCV>())) return e;                           \
+    raw_bwd_kernel<T, DCV><<<dim3(B.n_rt, static_cast<unsigned>((dim + DCV - 1) / DCV), n_tensors), 256,     \
+                             bwd_smem<DCV>(), st>>>(B);                                                       \
+  } while (0)
   switch (x_dtype) {
-    case TCL_DT_F32:
-      if (int e = ensure_dyn_smem(raw_bwd_kernel<float>, kBwdSmem)) return e;
-      raw_bwd_kernel<float><<<grid, 256, kBwdSmem, st>>>(B);
-      break;
-    case TCL_DT_F16:
-      if (int e = ensure_dyn_smem(raw_bwd_kernel<__half>, kBwdSmem)) return e;
-      raw_bwd_kernel<__half><<<grid, 256, kBwdSmem, st>>>(B);
-      break;
-    default:
-      if (int e = ensure_dyn_smem(raw_bwd_kernel<__nv_bfloat16>, kBwdSmem)) return e;
-      raw_bwd_kernel<__nv_bfloat16><<<grid, 256, kBwdSmem, st>>>(B);
-      break;
+    case TCL_DT_F32: if (wide) TCL_RAW_BWD(float, 256); else TCL_RAW_BWD(float, 128); break;
+    case TCL_DT_F16: if (wide) TCL_RAW_BWD(__half, 256); else TCL_RAW_BWD(__half, 128); break;
+    default: if (wide) TCL_RAW_BWD(__nv_bfloat16, 256); else TCL_RAW_BWD(__nv_bfloat16, 128); break;
   }
+#undef TCL_RAW_BWD
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
