@@ -525,7 +525,7 @@ int launch_l2norm_bwd(const NormBwdParams& pr, int n_jobs, int x_dtype, int64_t 
 // NormShParams), then the same projection as above.  Fixed summation order: row-side slots, then source ranks
 // 0..W-1 with their slots.
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, int WMAX>
 __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_constant__ NormShParams pr, int64_t rows,
                                                                  int dim, int64_t x_stride, float eps) {
   griddep_launch();
@@ -566,6 +566,59 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
   float g[kMaxIter][4], z[kMaxIter][4];
   float dot = 0.f;
   const int64_t col_slot_stride = rows * static_cast<int64_t>(dim);
+  // common case (fp16 column partials, at most two pieces per unit): fixed trip counts, so every load of a 128-column
+  // step - x, the row-side slots and W x slots column-side partials - is issued before anything is consumed, and the
+  // four steps overlap; with the piece counts as loop bounds the row cost ~12 dependent round trips to memory
+  // (45 us per launch at 4096 rows per rank).  Same summation order as the general path below (absent entries add 0).
+  constexpr int KR = 6;  // row-side pieces held in registers (a 64-tile row unit spans up to 5 tile ranges at 1024 rows per rank)
+  const bool fast = pr.col16 && pr.world <= WMAX && np_row[0] <= KR && np_row[1] <= KR && np_col[0] <= 2 && np_col[1] <= 2;
+  if (fast) {
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < dim) {
+        const int dh = (pr.n_dsplit == 2 && c >= 256) ? 1 : 0;
+        const int64_t off = row * dim + c;
+        float xv[4];
+        load4<T>(x + c, xv);
+        float4 rp[KR];
+        uint2 h[2][WMAX];
+#pragma unroll
+        for (int k = 0; k < KR; ++k)
+          rp[k] = k < np_row[dh] ? __ldcs(reinterpret_cast<const float4*>(jb.row_part + k * pr.row_slot_stride + off))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int r = 0; r < WMAX; ++r)
+            h[k][r] = (k < np_col[dh] && r < pr.world)
+                          ? __ldcv(reinterpret_cast<const uint2*>(static_cast<const __half*>(jb.col_part) +
+                                                                  (static_cast<int64_t>(r) * pr.n_slots_col + k) * col_slot_stride + off))
+                          : make_uint2(0u, 0u);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          acc[0] += sc_own * rp[k].x; acc[1] += sc_own * rp[k].y; acc[2] += sc_own * rp[k].z; acc[3] += sc_own * rp[k].w;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int r = 0; r < WMAX; ++r) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h[k][r].x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h[k][r].y));
+            acc[0] += sc[r] * a.x; acc[1] += sc[r] * a.y; acc[2] += sc[r] * b.x; acc[3] += sc[r] * b.y;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          g[it][e] = acc[e];
+          z[it][e] = xv[e] * inv;
+          dot += g[it][e] * z[it][e];
+        }
+      }
+    }
+  } else {
 #pragma unroll
   for (int it = 0; it < kMaxIter; ++it) {
     const int c = it * 128 + lane * 4;
@@ -614,6 +667,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_sharded_kernel(const __grid_co
       }
     }
   }
+  }
   dot = warp_sum(dot);
   if (clamped) dot = 0.f;
 #pragma unroll
@@ -634,13 +688,21 @@ int launch_l2norm_bwd_sharded(const NormShParams& pr, int n_jobs, int x_dtype, i
   dim3 grid(static_cast<unsigned>((rows + 7) / 8), n_jobs);
   ProfScope prof(TCL_K_L2NORM_BWD, st);
   LaunchCfg L(grid, dim3(256), 0, st);
+  // the fast path holds 2 x WMAX column-side loads per step in registers: instantiate for the world sizes of one node
+#define TCL_NBS(T)                                                                                                    \
+  do {                                                                                                                \
+    if (pr.world <= 2) TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<T, 2>, pr, rows, dim, x_stride, eps)); \
+    else if (pr.world <= 4) TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<T, 4>, pr, rows, dim, x_stride, eps)); \
+    else TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<T, TCL_MAX_PEERS>, pr, rows, dim, x_stride, eps)); \
+  } while (0)
   switch (x_dtype) {
-    case TCL_DT_F32: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<float>, pr, rows, dim, x_stride, eps)); break;
-    case TCL_DT_F64: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<double>, pr, rows, dim, x_stride, eps)); break;
-    case TCL_DT_F16: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<__half>, pr, rows, dim, x_stride, eps)); break;
-    case TCL_DT_BF16: TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, l2norm_bwd_sharded_kernel<__nv_bfloat16>, pr, rows, dim, x_stride, eps)); break;
+    case TCL_DT_F32: TCL_NBS(float); break;
+    case TCL_DT_F64: TCL_NBS(double); break;
+    case TCL_DT_F16: TCL_NBS(__half); break;
+    case TCL_DT_BF16: TCL_NBS(__nv_bfloat16); break;
     default: return set_error(TCL_ERR_BAD_ARG, "unknown x_dtype %d", x_dtype);
   }
+#undef TCL_NBS
   TCL_CHECK_CUDA(cudaGetLastError());
   return TCL_OK;
 }
