@@ -362,8 +362,13 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- NVLink traffic of the fused compute+transfer kernels (N > 1): algorithmic bytes per rank and step
     nvlink = None
     if world > 1:
-        gather_in = 3 * (batch - b_loc) * DIM * 2
+        # modalities whose rows cross NVLink: all three for the directional backward, the two column-side ones (image,
+        # voxel) for the sharded shared-G backward (tricolo_b200/distributed.py)
+        gathered_mods = 2 if (bwd_mode == "sharedg" and os.environ.get("TRICOLO_B200_GATHER_ALL", "0") != "1"
+                              and os.environ.get("TRICOLO_B200_MULTICAST", "0") != "1") else 3
+        gather_in = gathered_mods * (batch - b_loc) * DIM * 2
         nvlink = {"gather": {"kernel": "l2norm_fwd_push_kernel (K1 storing into every rank's gathered buffer)",
+                             "modalities_gathered": gathered_mods,
                              "bytes_in_per_rank": gather_in, "bytes_out_per_rank": gather_in,
                              "gbs_per_direction": gather_in / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9 if "l2norm_fwd" in kern else None},
                   "statistics": {"kernel": "fwd_finalize_sharded_kernel (pulls every rank's slot)",

@@ -72,7 +72,9 @@ int tcl_l2norm_fwd(int n_tensors, const void* const* x_host_ptrs, int x_dtype, i
  * operand buffer (peer-mapped device memory, e.g. a torch symmetric-memory allocation: plain st.global over NVLink).
  *   z_dst_host_ptrs[r * n_tensors + m] = address of THIS rank's first row of modality m inside rank r's buffer.
  * No synchronisation: the caller brackets the call with cross-device barriers (nobody still reads the buffers before,
- * every rank's rows have landed after).  n_dst <= TCL_MAX_PEERS. */
+ * every rank's rows have landed after).  n_dst <= TCL_MAX_PEERS.  Destination 0 is mandatory for every tensor; a NULL
+ * address at r > 0 skips that (destination, tensor): a modality whose remote rows nobody reads (the text modality
+ * under the sharded shared-G backward, or in a forward without gradients) then costs no NVLink traffic. */
 #define TCL_MAX_PEERS 8
 int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x_host_ptrs, int x_dtype, int64_t rows, int64_t dim,
                          int64_t x_row_stride, int n_dst, void* const* z_dst_host_ptrs, int64_t z_row_stride,

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_push_kernel(const __grid_const
         if (lane == 0) flag_wait_ge(sy + ShardSync::kReady + p, e);
         __syncwarp();
       }
+      if (pk.out[p][tensor] == nullptr) continue;  // this destination does not take this tensor (bcast form only)
       TOut* z = static_cast<TOut*>(pk.out[p][tensor]) + row * z_stride;
 #pragma unroll
       for (int it = 0; it < 2; ++it) {
@@ -778,7 +779,9 @@ extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_d
     pk.aux[i] = inv_norm[i];
     for (int d = 0; d < n_dst; ++d) {
       void* p = z_dst[d * n_tensors + i];
-      TCL_REQUIRE(p && aligned_to(p, 16), TCL_ERR_BAD_ALIGN, "l2norm_bcast: destination %d of tensor %d", d, i);
+      // destination 0 (the own buffer) is mandatory; a NULL further destination means "this peer never reads this
+      // tensor's rows" (e.g. the text modality under the sharded shared-G backward) and is skipped
+      TCL_REQUIRE((p || d > 0) && aligned_to(p, 16), TCL_ERR_BAD_ALIGN, "l2norm_bcast: destination %d of tensor %d", d, i);
       pk.out[d][i] = p;
     }
   }

@@ -233,8 +233,18 @@ class _GlobalNTXent(torch.autograd.Function):
         if ws is not None:
             # peer-memory transport: K1 stores every row into all ranks' buffers; barriers before (nobody still reads
             # the previous step's operands) and after (every rank's rows have landed everywhere)
+            # modalities whose remote rows anyone reads: the column side of a pair (forward, G recompute, row-side
+            # gradient GEMM); only the directional backward also reads the row side of every pair from all ranks.
+            # Under the sharded shared-G backward (or without gradients) the other modalities (text) stay local: a
+            # third less NVLink traffic in the gather
+            use_sg = _sharded_g_enabled(b_loc) and ops.ShardedBwdPlan.supported(b_loc, dim, world)
+            ctx.use_sg = use_sg
+            dsts = ws.dsts
+            if (use_sg or not needs_grad) and not ws.multicast and os.environ.get("TRICOLO_B200_GATHER_ALL", "0") != "1":
+                cols = {b for _, b in pairs}
+                dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
             ws.hz.barrier(channel=0)
-            invs, xs = ops.l2norm_fwd_bcast(feats, ws.dsts, ws.z_row_stride, op_format)
+            invs, xs = ops.l2norm_fwd_bcast(feats, dsts, ws.z_row_stride, op_format)
             ws.hz.barrier(channel=0)
             z_glob3 = ws.z.view(b_glob, n, dim)
             z_all = [z_glob3[:, m] for m in range(n)]
