@@ -127,6 +127,13 @@ int tcl_ntxent_finalize_sharded(int n_pairs, int64_t b_loc, int64_t b_glob, int 
  * bit-identical sums).  16-byte aligned pointers; any n. */
 int tcl_peer_sum_f32(int n_src, const float* const* src_host_ptrs, int64_t n, float* out, void* stream);
 
+/* Copy-engine transfer of `rows` rows of `width_bytes` between two pitched device buffers (cudaMemcpy2DAsync, device to
+ * device; either side may be peer-mapped memory of another GPU).  The sharded loss uses it to send the rows of a modality
+ * that only the BACKWARD reads remotely (text under the directional backward) to the peers on a side stream while the
+ * forward tile kernel runs: no SM time, NVLink busy during the MMAs (tricolo_b200/distributed.py). */
+int tcl_copy_rows(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                  int64_t rows, void* stream);
+
 /* 16-bit cast without normalisation (retrieval uses the raw dot product,
  * eval_retrieval.py:74).  Accepts f32/f64/f16/bf16 input. */
 int tcl_cast_16bit(const void* x, int x_dtype, int64_t rows, int64_t dim, int64_t x_row_stride,

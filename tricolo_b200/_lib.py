@@ -79,6 +79,7 @@ SIGNATURES = {
     "tcl_ntxent_fwd_sharded": (_i, [_i, _pp, _pp, _i64, _i64, _i64, _i64, _i, _i, _i, _f, _vp, _vp, _sz, _pp, _pp, _pp, _i,
                                     C.POINTER(C.c_int64), _vp]),
     "tcl_ntxent_finalize_sharded": (_i, [_i, _i64, _i64, _i, _i, _f, _f, _pp, _vp, _vp, _vp, _vp, _vp]),
+    "tcl_copy_rows": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "tcl_cast_16bit": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp]),
     "tcl_triplet_workspace_bytes": (_sz, [_i64]),
     "tcl_triplet_fwd": (_i, [_vp, _vp, _i, _i64, _i64, _i64, _f, _vp, _vp, _vp, _sz, _vp]),

@@ -75,3 +75,16 @@ extern "C" int tcl_profile_read(int kernel_id, double* total_ms, int64_t* launch
   *launches = static_cast<int64_t>(g_used[kernel_id]);
   return TCL_OK;
 }
+
+extern "C" int tcl_copy_rows(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                             int64_t width_bytes, int64_t rows, void* stream) {
+  TCL_REQUIRE(dst && src, TCL_ERR_BAD_ARG, "copy_rows: null pointer");
+  TCL_REQUIRE(rows >= 0 && width_bytes >= 1 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+              TCL_ERR_BAD_SHAPE, "copy_rows: rows %lld, width %lld, pitches %lld / %lld", (long long)rows,
+              (long long)width_bytes, (long long)dst_pitch_bytes, (long long)src_pitch_bytes);
+  if (rows == 0) return TCL_OK;
+  TCL_CHECK_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(dst_pitch_bytes), src, static_cast<size_t>(src_pitch_bytes),
+                                   static_cast<size_t>(width_bytes), static_cast<size_t>(rows), cudaMemcpyDeviceToDevice,
+                                   static_cast<cudaStream_t>(stream)));
+  return TCL_OK;
+}

@@ -78,6 +78,7 @@ class _SymmWorkspace:
         self.dsts = [[base + (lo * n * dim + m * dim) * esz for m in range(n)] for base in bases]
         if not mc:  # own buffer first, then the peers in a rank-staggered order (no all-to-one bursts)
             self.dsts = self.dsts[rank:] + self.dsts[:rank]
+        self.side = torch.cuda.Stream(device=dev)  # copy-engine transfers that overlap the forward tile kernel
         self.busy = False  # a forward with autograd holds the gathered operands until its backward
         self.group, self.world, self.rank, self.b_loc, self.n, self.dim = group, world, rank, b_loc, n, dim
         self._bwd = {}
@@ -169,13 +170,14 @@ def _fused_push_enabled() -> bool:
 
 def _sharded_g_enabled(b_loc: int = 1 << 30) -> bool:
     """Backward form of a sharded step: TRICOLO_B200_SHARDED_BWD=sharedg|pc forces one.  Default: the sharded shared-G
-    form (6 b B D, in-kernel reduce-scatter) from 4096 rows per rank on, the directional kernel (8 b B D, no exchange)
-    below - measured at B=8192: N=2 0.439 vs 0.470 ms per step, N=4 0.305 vs 0.28, N=8 0.246 vs 0.217 (with few rows per rank the
-    29 MB of fp32 partials per rank and the per-kernel fixed costs outweigh the saved recompute)."""
+    form (6 b B D, in-kernel reduce-scatter, two modalities gathered) from 2048 rows per rank on, the directional
+    kernel (8 b B D, no exchange, three modalities gathered) below - measured at B=8192 (profiles/r2m_*, r2n_*):
+    N=2 0.407 vs 0.470 ms per step, N=4 0.279 vs 0.287, N=8 0.214 vs 0.207 (with 1024 rows per rank kernel A, kernel B
+    and the summing normalise backward each carry ~10 us of fixed cost that the saved recompute no longer covers)."""
     e = os.environ.get("TRICOLO_B200_SHARDED_BWD", "")
     if e in ("sharedg", "pc"):
         return e == "sharedg"
-    return b_loc >= 4096
+    return b_loc >= 2048
 
 
 def _world(group=None):
@@ -239,12 +241,33 @@ class _GlobalNTXent(torch.autograd.Function):
             # third less NVLink traffic in the gather
             use_sg = _sharded_g_enabled(b_loc) and ops.ShardedBwdPlan.supported(b_loc, dim, world)
             ctx.use_sg = use_sg
+            # The directional backward does read those rows from all ranks - but only the BACKWARD: they are sent by
+            # the copy engines on a side stream while the forward tile kernel runs (no SM time, NVLink busy during the
+            # MMAs) and are complete before the statistics barrier below (TRICOLO_B200_GATHER_ALL=1: K1 sends everything)
             dsts = ws.dsts
-            if (use_sg or not needs_grad) and not ws.multicast and os.environ.get("TRICOLO_B200_GATHER_ALL", "0") != "1":
+            deferred = []
+            if not ws.multicast and os.environ.get("TRICOLO_B200_GATHER_ALL", "0") != "1":
                 cols = {b for _, b in pairs}
+                deferred = [m for m in range(n) if m not in cols]
                 dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
+                if use_sg or not needs_grad:
+                    deferred = []
             ws.hz.barrier(channel=0)
             invs, xs = ops.l2norm_fwd_bcast(feats, dsts, ws.z_row_stride, op_format)
+            ev_sent = None
+            if deferred:
+                cur = torch.cuda.current_stream(dev)
+                ev_k1 = torch.cuda.Event()
+                ev_k1.record(cur)
+                esz = ws.z.element_size()
+                pitch = ws.z_row_stride * esz
+                with torch.cuda.stream(ws.side):
+                    ws.side.wait_event(ev_k1)
+                    for d in ws.dsts[1:]:  # peers in the rank-staggered order; ws.dsts[0] is the own buffer
+                        for m in deferred:
+                            ops.copy_rows(d[m], pitch, ws.dsts[0][m], pitch, dim * esz, b_loc, ws.side.cuda_stream)
+                    ev_sent = torch.cuda.Event()
+                    ev_sent.record(ws.side)
             ws.hz.barrier(channel=0)
             z_glob3 = ws.z.view(b_glob, n, dim)
             z_all = [z_glob3[:, m] for m in range(n)]
@@ -255,6 +278,8 @@ class _GlobalNTXent(torch.autograd.Function):
             # ranks are needed by the backward
             ops.ntxent_fwd_sharded([z_own[a] for a, _ in pairs], [z_all[b] for _, b in pairs], rank, world, inv_tau,
                                    ws.stats_addrs, None, op_format)
+            if ev_sent is not None:  # this rank's deferred rows have left before it enters the barrier: after the barrier
+                torch.cuda.current_stream(dev).wait_event(ev_sent)  # every rank's have landed everywhere
             ws.hstats.barrier(channel=0)
             lse2_row_all, lse2_col, loss = ops.ntxent_finalize_sharded(p, b_loc, rank, world, inv_tau, alpha, ws.stats_addrs,
                                                                        0, dev)

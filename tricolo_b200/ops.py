@@ -93,6 +93,12 @@ def l2norm_fwd_bcast(xs: Sequence[torch.Tensor], dsts: Sequence[Sequence], z_row
     return invs, xs
 
 
+def copy_rows(dst_addr: int, dst_pitch: int, src_addr: int, src_pitch: int, width: int, rows: int, stream: int) -> None:
+    """Copy-engine (cudaMemcpy2DAsync) transfer of `rows` x `width` bytes between pitched device buffers; `stream` is a
+    raw cudaStream_t."""
+    L.check(LIB.tcl_copy_rows(int(dst_addr), dst_pitch, int(src_addr), src_pitch, width, rows, int(stream)))
+
+
 def shard_sync_bytes() -> int:
     return int(LIB.tcl_shard_sync_bytes())
 
