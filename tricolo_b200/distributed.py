@@ -241,17 +241,21 @@ class _GlobalNTXent(torch.autograd.Function):
             # third less NVLink traffic in the gather
             use_sg = _sharded_g_enabled(b_loc) and ops.ShardedBwdPlan.supported(b_loc, dim, world)
             ctx.use_sg = use_sg
-            # The directional backward does read those rows from all ranks - but only the BACKWARD: they are sent by
-            # the copy engines on a side stream while the forward tile kernel runs (no SM time, NVLink busy during the
-            # MMAs) and are complete before the statistics barrier below (TRICOLO_B200_GATHER_ALL=1: K1 sends everything)
+            # The directional backward does read those rows from all ranks - but only the BACKWARD.  Opt-in experiment
+            # (TRICOLO_B200_DEFER_GATHER=1): they are sent by the copy engines on a side stream while the forward tile
+            # kernel runs and are complete before the statistics barrier below.  Correct (multi-rank parity), K1 + gather
+            # 42 -> 32 us on 8 B200, but the step got SLOWER (0.207 -> 0.212 ms; pipelined e2e 0.37 -> 0.46 ms): 1 KB rows
+            # at a 3 KB pitch are a poor copy-engine pattern, the statistics barrier ends up waiting for them.  Default:
+            # K1 stores every modality itself when the directional backward follows.
             dsts = ws.dsts
             deferred = []
             if not ws.multicast and os.environ.get("TRICOLO_B200_GATHER_ALL", "0") != "1":
                 cols = {b for _, b in pairs}
-                deferred = [m for m in range(n) if m not in cols]
-                dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
                 if use_sg or not needs_grad:
-                    deferred = []
+                    dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
+                elif os.environ.get("TRICOLO_B200_DEFER_GATHER", "0") == "1":
+                    deferred = [m for m in range(n) if m not in cols]
+                    dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
             ws.hz.barrier(channel=0)
             invs, xs = ops.l2norm_fwd_bcast(feats, dsts, ws.z_row_stride, op_format)
             ev_sent = None
