@@ -65,6 +65,13 @@ def test_argument_validation_without_gpu():
     assert rc == 4
     assert L.tcl_ntxent_raw_state_bytes(3, 8192) == 3 * 8192 * 2 * 4
     assert L.tcl_ntxent_raw_workspace_bytes(3, 8192) > 3 * 128 * 8192 * 8
+    # gather with per-(destination, tensor) addresses: destination 0 is mandatory, NULL further destinations are skipped
+    inv = (ctypes.c_void_p * 1)(p.value)
+    dst = (ctypes.c_void_p * 2)(None, p.value)
+    rc = L.tcl_l2norm_fwd_bcast(1, arr, 0, 8, 64, 64, 2, dst, 64, 0, inv, 1e-12, None)
+    assert rc == 2 and b"destination 0" in L.tcl_last_error_string()
+    rc = L.tcl_copy_rows(p, 64, p, 32, 64, 4, None)  # source pitch below the row width
+    assert rc == 1
     assert L.tcl_ntxent_fwd_workspace_bytes(3, 8192, 8192) > 0
     assert L.tcl_ntxent_bwd_workspace_bytes(3, 8192, 512) >= 3 * 8192 * 512 * 4
 

@@ -766,8 +766,6 @@ extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_d
               "l2norm_bcast: dim must be a multiple of 8 in [8, 512] (got %lld)", (long long)dim);
   TCL_REQUIRE(x_row_stride >= dim && (x_row_stride * dtype_size(x_dtype)) % 16 == 0, TCL_ERR_BAD_ALIGN, "l2norm_bcast: row stride");
   TCL_REQUIRE(op_format == TCL_OP_F16 || op_format == TCL_OP_BF16, TCL_ERR_BAD_ARG, "op_format %d", op_format);
-  if (int e = require_sm100()) return e;
-  if (rows == 0) return TCL_OK;
   PushPack pk{};
   pk.rank = 0;
   pk.world = n_dst;
@@ -785,6 +783,8 @@ extern "C" int tcl_l2norm_fwd_bcast(int n_tensors, const void* const* x, int x_d
       pk.out[d][i] = p;
     }
   }
+  if (int e = require_sm100()) return e;
+  if (rows == 0) return TCL_OK;
   return launch_push(pk, n_tensors, x_dtype, rows, (int)dim, x_row_stride, z_row_stride, op_format, eps,
                      static_cast<cudaStream_t>(stream));
 }
