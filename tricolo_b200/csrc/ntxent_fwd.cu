@@ -908,6 +908,126 @@ __global__ void __launch_bounds__(1024) fwd_finalize_sharded_kernel(
   }
 }
 
+// Large batches on one GPU: the wide reduction of the tile kernel's partials AND the finalise in ONE launch (the
+// reduce -> finalise pair cost 10 + 12 us at B = 8192 for ~7 MB of partials).  Fixed-order sums of the partials (the
+// column partials as four quarter sums, combined pairwise), lse2 = log2(sum) + c1, block sums of (lse2_row - diag, lse2_col - diag) in fp64; the
+// block that finishes last for a pair adds the block sums in block order and writes the pair's loss, the last pair
+// adds the pair losses in pair order.  Requires n_rows == n_cols, row_offset == 0 (the whole-loss entry).  Counters
+// and block sums live in per-launch-lane device arrays (self-resetting), so concurrent streams do not collide.
+static constexpr int RF_MAX_BLOCKS = 1024;  // 64 indices per block: batch <= 65536
+__device__ unsigned int g_rf_done[FIN_LANES][TCL_MAX_PAIRS + 1];
+__device__ double g_rf_part[FIN_LANES][TCL_MAX_PAIRS][RF_MAX_BLOCKS][2];
+__global__ void __launch_bounds__(256) fwd_reduce_finalize_kernel(
+    int n, float c1, float alpha, float* __restrict__ row_sum, float* __restrict__ col_sum,
+    const float* __restrict__ diag2, float* __restrict__ lse2_row, float* __restrict__ lse2_col,
+    float* __restrict__ loss_parts, float* __restrict__ loss, const float* __restrict__ row_part,
+    const float* __restrict__ col_part, int n_row_slots, int n_iblocks, int lane_id, int want_total) {
+  griddep_launch();
+  griddep_wait();
+  __shared__ float cpart[4][64];
+  __shared__ double sa[64], sb[64];
+  __shared__ bool last;
+  const int pair = blockIdx.y;
+  // 64 indices per block, four quarter-sums of the column partials per index (a warp reads 32 consecutive floats
+  // of one partial row per load; 16 loads in flight per thread at 64 row blocks); quarter 0 also adds the row slots
+  const int q = threadIdx.x >> 6, li = threadIdx.x & 63;
+  const int i = blockIdx.x * 64 + li;
+  float r = 0.f;
+  {
+    const int per = (n_iblocks + 3) >> 2;
+    const int b0 = q * per, b1 = (b0 + per < n_iblocks) ? b0 + per : n_iblocks;
+    float c = 0.f;
+    if (i < n) {
+      const float* cp = col_part + static_cast<int64_t>(pair) * n_iblocks * n + i;
+      int bk = b0;
+      for (; bk + 16 <= b1; bk += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcs(cp + static_cast<int64_t>(bk + u) * n);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) c += v[u];
+      }
+      for (; bk < b1; ++bk) c += __ldcs(cp + static_cast<int64_t>(bk) * n);
+      if (q == 0)
+        for (int s = 0; s < n_row_slots; ++s) r += row_part[(static_cast<int64_t>(pair) * n_row_slots + s) * n + i];
+    }
+    cpart[q][li] = c;
+  }
+  __syncthreads();
+  double a = 0.0, b = 0.0;
+  if (q == 0 && i < n) {
+    const float c = (cpart[0][li] + cpart[1][li]) + (cpart[2][li] + cpart[3][li]);  // fixed order
+    const int64_t o = static_cast<int64_t>(pair) * n + i;
+    row_sum[o] = r;
+    col_sum[o] = c;
+    const float lr = log2f(r) + c1, lc = log2f(c) + c1, dg = diag2[o];
+    lse2_row[o] = lr;
+    lse2_col[o] = lc;
+    a = static_cast<double>(lr - dg);
+    b = static_cast<double>(lc - dg);
+  }
+  if (q == 0) {
+    sa[li] = a;
+    sb[li] = b;
+  }
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sb[threadIdx.x] += sb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    g_rf_part[lane_id][pair][blockIdx.x][0] = sa[0];
+    g_rf_part[lane_id][pair][blockIdx.x][1] = sb[0];
+    __threadfence();
+    last = atomicAdd(&g_rf_done[lane_id][pair], 1u) + 1u == gridDim.x;
+  }
+  __syncthreads();
+  if (!last) return;
+  // the pair's last block: block sums in block order (a fixed tree over 64 threads, then thread 0)
+  __threadfence();
+  double ta = 0.0, tb = 0.0;
+  if (threadIdx.x < 64) {
+    for (unsigned blk = threadIdx.x; blk < gridDim.x; blk += 64) {
+      ta += __ldcg(&g_rf_part[lane_id][pair][blk][0]);
+      tb += __ldcg(&g_rf_part[lane_id][pair][blk][1]);
+    }
+    sa[threadIdx.x] = ta;
+    sb[threadIdx.x] = tb;
+  }
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sb[threadIdx.x] += sb[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    g_rf_done[lane_id][pair] = 0u;
+    const double ln2 = 0.69314718055994530942;
+    const double pa = sa[0] * ln2, pb = sb[0] * ln2;
+    loss_parts[pair * 2 + 0] = static_cast<float>(pa);
+    loss_parts[pair * 2 + 1] = static_cast<float>(pb);
+    if (loss != nullptr) {
+      __stcg(loss + pair, static_cast<float>((alpha * pa + (1.0 - alpha) * pb) / n));
+      if (want_total) {
+        const int n_pairs = gridDim.y;
+        __threadfence();
+        if (atomicAdd(&g_rf_done[lane_id][TCL_MAX_PAIRS], 1u) + 1u == static_cast<unsigned int>(n_pairs)) {
+          g_rf_done[lane_id][TCL_MAX_PAIRS] = 0u;
+          __threadfence();
+          float t = 0.f;
+          for (int p = 0; p < n_pairs; ++p) t += __ldcg(loss + p);  // sum(loss_dict.values()), tricolo_net.py:64
+          loss[n_pairs] = t;
+        }
+      }
+    }
+  }
+}
+
 static int fwd_split(int n_pairs, int n_iblocks, int n_jtiles) {
   // One CTA per SM.  Cost model of a split s of the column sweep: waves(s) x (prologue + tiles per CTA), the
   // prologue (row block into shared memory / TMEM, pipeline fill) being worth about two tiles.  Small problems end up
@@ -1115,10 +1235,27 @@ int ntxent_fwd_finalize_fused(int n_pairs, const void* const* zrow, const void* 
   // Small batches are launch-bound: the finalise cluster reduces the partials itself (B = 256: 15 -> 9 us).  At
   // large batches the partials are megabytes and the wide reduce kernel in front of the finalise is faster.
   const bool fuse = batch <= 2048;
+  // ... and from there on ONE wide kernel reduces and finalises (TRICOLO_B200_FINALIZE=split keeps the two kernels)
+  static const bool wide_ok = [] { const char* e = getenv("TRICOLO_B200_FINALIZE"); return !(e && strcmp(e, "split") == 0); }();
+  const bool wide = !fuse && wide_ok && (batch + 63) / 64 <= RF_MAX_BLOCKS;
   FwdPartials parts;
   if (int e = ntxent_fwd_impl(n_pairs, zrow, zcol, batch, batch, dim, 0, 0, op_format, inv_tau, row_sumexp, col_sumexp,
-                              diag2, workspace, workspace_bytes, stream, fuse ? &parts : nullptr))
+                              diag2, workspace, workspace_bytes, stream, (fuse || wide) ? &parts : nullptr))
     return e;
+  if (wide) {
+    static std::atomic<unsigned> next_lane{0};
+    const int lane_id = static_cast<int>(next_lane.fetch_add(1u) % FIN_LANES);
+    TCL_REQUIRE(row_sumexp && col_sumexp && diag2 && lse2_row && lse2_col && loss_parts, TCL_ERR_BAD_ARG, "finalize: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ProfScope prof(TCL_K_FWD_FINALIZE, st);
+    LaunchCfg L(dim3(static_cast<unsigned>((batch + 63) / 64), n_pairs), dim3(256), 0, st);
+    TCL_CHECK_CUDA(cudaLaunchKernelEx(&L.cfg, fwd_reduce_finalize_kernel, (int)batch, inv_tau * 1.4426950408889634f, alpha,
+                                      row_sumexp, col_sumexp, (const float*)diag2, lse2_row, lse2_col, loss_parts, loss,
+                                      parts.row_part, parts.col_part, parts.n_row_slots, parts.n_iblocks, lane_id,
+                                      (want_total && loss) ? 1 : 0));
+    TCL_CHECK_CUDA(cudaGetLastError());
+    return TCL_OK;
+  }
   return ntxent_finalize_impl(n_pairs, batch, batch, 0, inv_tau, alpha, row_sumexp, col_sumexp, diag2, lse2_row, lse2_col,
                               loss_parts, loss, stream, fuse ? &parts : nullptr, want_total);
 }
