@@ -334,6 +334,38 @@ def run_ours(args, rank, world, local_rank):
     if "l2norm_fwd" in kern:
         kern["l2norm_fwd"].update({"bound": "hbm", "gbs": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9,
                                    "frac_of_hbm_peak": bytes_l2n / (kern["l2norm_fwd"]["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm_gbs"]})
+        if world == 1:
+            # an event pair around ONE 15 us kernel adds ~5 us of launch / record latency to it; the same kernel timed as 12
+            # back-to-back launches over three rotating input sets (150 MB > L2, so no launch finds its input cached)
+            try:
+                sets = [[f.detach().clone() for f in feats] for _ in range(3)]
+                outs = [[torch.empty((b_loc, DIM), dtype=torch.float16 if op == ops.F16 else torch.bfloat16, device=dev)
+                         for _ in feats] for _ in range(3)]
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for k in range(3):
+                        ops.l2norm_fwd(sets[k], op, out=outs[k])
+                torch.cuda.current_stream().wait_stream(side)
+                g12 = torch.cuda.CUDAGraph()  # the host cannot issue 15 us kernels back to back: replay a captured sequence
+                with torch.cuda.graph(g12):
+                    for k in range(12):
+                        ops.l2norm_fwd(sets[k % 3], op, out=outs[k % 3])
+                g12.replay()
+                flush.zero_()
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g12.replay()
+                b.record()
+                torch.cuda.synchronize(dev)
+                ms = a.elapsed_time(b) / 12
+                kern["l2norm_fwd"]["back_to_back"] = {"ms_per_launch": ms, "gbs": bytes_l2n / (ms * 1e-3) / 1e9,
+                                                      "frac_of_hbm_peak": bytes_l2n / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                      "note": "12 graph-replayed launches inside one event pair, inputs rotate over 3 sets (150 MB)"}
+                del sets, outs, g12
+            except Exception as ex:  # report, never hide
+                kern["l2norm_fwd"]["back_to_back"] = {"error": repr(ex)[:200]}
     ach = kern.get("ntxent_bwd", {}).get("algorithmic_tflops")
     # the CTA-pair kernel (cta_group::2) is the default gradient GEMM; TRICOLO_B200_GGEMM=1sm keeps the one-SM kernel
     ggemm = "ntxent_ggemm_kernel" if os.environ.get("TRICOLO_B200_GGEMM") == "1sm" else "ntxent_ggemm2_kernel"
