@@ -27,7 +27,9 @@ def main():
     def run_loss(loc, transport, bwd, sync="barrier"):
         os.environ["TRICOLO_B200_SYMM"] = transport
         os.environ["TRICOLO_B200_SHARDED_BWD"] = bwd
-        os.environ["TRICOLO_B200_SHARD_SYNC"] = sync
+        # sync "defer": barrier form with the text rows sent by the copy engines during the forward (opt-in experiment)
+        os.environ["TRICOLO_B200_SHARD_SYNC"] = "barrier" if sync == "defer" else sync
+        os.environ["TRICOLO_B200_DEFER_GATHER"] = "1" if sync == "defer" else "0"
         for x in loc:
             x.grad = None
         out = global_calculate_losses(dict(zip(keys, loc)), "train_loss", TAU, ALPHA)
@@ -54,7 +56,7 @@ def main():
         # push warps, flag-signalled reduce-scatter); nccl: NCCL collectives
         for name, transport, bwd, sync in (("symm/sharedg", "1", "sharedg", "barrier"), ("symm/sharedg/flags", "1", "sharedg", "flags"),
                                            ("symm/pc", "1", "pc", "barrier"), ("symm/pc/flags", "1", "pc", "flags"),
-                                           ("nccl/pc", "0", "pc", "barrier")):
+                                           ("symm/pc/defer", "1", "pc", "defer"), ("nccl/pc", "0", "pc", "barrier")):
             losses, grads = run_loss(loc, transport, bwd, sync)
             lerr = max(abs(losses[k] - v) / abs(v) for k, v in ref_l.items())
             errs = [np.linalg.norm(grads[m].double().cpu().numpy() - ref_g[k][rank * bl:(rank + 1) * bl]) /
