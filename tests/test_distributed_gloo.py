@@ -104,3 +104,28 @@ def test_sharded_retrieval_world2():
         assert np.array_equal(i, ref["_indices"])
         assert np.array_equal(r, ref["_rank"])
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_gather_plan_follows_the_backward_form(monkeypatch):
+    """Which modalities cross NVLink in K1's gather (tricolo_b200/distributed.py:_gather_plan): the column side of the
+    pairs always; the row-only modality (text) only for the directional backward."""
+    from tricolo_b200.distributed import _gather_plan
+
+    monkeypatch.delenv("TRICOLO_B200_GATHER_ALL", raising=False)
+    monkeypatch.delenv("TRICOLO_B200_DEFER_GATHER", raising=False)
+    pairs = [(0, 1), (0, 2), (1, 2)]  # (text, image), (text, voxel), (image, voxel): tricolo_net.py:59-61
+    dsts = [[100 + 10 * r + m for m in range(3)] for r in range(4)]  # own buffer first
+    sg, d = _gather_plan(dsts, pairs, 3, True, True, False)
+    assert sg[0] == dsts[0] and d == []
+    assert all(row[0] == 0 and row[1:] == ref[1:] for row, ref in zip(sg[1:], dsts[1:]))  # text stays local
+    assert _gather_plan(dsts, pairs, 3, False, False, False)[0] == sg  # forward without gradients: the same
+    assert _gather_plan(dsts, pairs, 3, False, True, False) == (dsts, [])  # directional backward: everything
+    monkeypatch.setenv("TRICOLO_B200_DEFER_GATHER", "1")
+    assert _gather_plan(dsts, pairs, 3, False, True, False) == (sg, [0])  # text by the copy engines
+    assert _gather_plan(dsts, pairs, 3, True, True, False) == (sg, [])
+    monkeypatch.setenv("TRICOLO_B200_GATHER_ALL", "1")
+    assert _gather_plan(dsts, pairs, 3, True, True, False) == (dsts, [])
+    monkeypatch.delenv("TRICOLO_B200_GATHER_ALL")
+    assert _gather_plan(dsts, pairs, 3, True, True, True) == (dsts, [])  # one multicast mapping: nothing to skip
+    # bimodal (text, voxel): voxel is the column side
+    assert _gather_plan([[1, 2], [3, 4]], [(0, 1)], 2, True, True, False)[0] == [[1, 2], [0, 4]]

@@ -180,6 +180,26 @@ def _sharded_g_enabled(b_loc: int = 1 << 30) -> bool:
     return b_loc >= 2048
 
 
+def _gather_plan(dsts, pairs, n, use_sg: bool, needs_grad: bool, multicast: bool):
+    """(destination addresses for K1's stores, modalities sent later by the copy engines).
+
+    `dsts[r][m]`: address of this rank's rows of modality m in destination r, the own buffer first.  Only the COLUMN side of
+    a pair is read from other ranks by the forward, the G recompute and the row-side gradient GEMM; the directional
+    backward alone also reads the row side (text) of every rank.  So under the sharded shared-G backward, or without
+    gradients, the row-only modalities get address 0 (= skipped by tcl_l2norm_fwd_bcast) at every remote destination.
+    For the directional backward K1 sends everything, unless TRICOLO_B200_DEFER_GATHER=1 hands those rows to the copy
+    engines.  TRICOLO_B200_GATHER_ALL=1 or the multicast mapping: K1 sends everything."""
+    if multicast or os.environ.get("TRICOLO_B200_GATHER_ALL", "0") == "1":
+        return dsts, []
+    cols = {b for _, b in pairs}
+    local_only = [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
+    if use_sg or not needs_grad:
+        return [dsts[0]] + local_only, []
+    if os.environ.get("TRICOLO_B200_DEFER_GATHER", "0") == "1":
+        return [dsts[0]] + local_only, [m for m in range(n) if m not in cols]
+    return dsts, []
+
+
 def _world(group=None):
     return dist.get_world_size(group), dist.get_rank(group)
 
@@ -233,29 +253,15 @@ class _GlobalNTXent(torch.autograd.Function):
             ctx.save_for_backward(lse2_row_all, lse2_col, ws.z, *xs, *invs)
             return loss
         if ws is not None:
-            # peer-memory transport: K1 stores every row into all ranks' buffers; barriers before (nobody still reads
-            # the previous step's operands) and after (every rank's rows have landed everywhere)
-            # modalities whose remote rows anyone reads: the column side of a pair (forward, G recompute, row-side
-            # gradient GEMM); only the directional backward also reads the row side of every pair from all ranks.
-            # Under the sharded shared-G backward (or without gradients) the other modalities (text) stay local: a
-            # third less NVLink traffic in the gather
+            # peer-memory transport: K1 stores its rows into the ranks' buffers; barriers before (nobody still reads
+            # the previous step's operands) and after (every rank's rows have landed everywhere).  Which modalities
+            # cross NVLink follows the backward form (_gather_plan): a third less traffic under the sharded shared-G
+            # backward.  The copy-engine variant (TRICOLO_B200_DEFER_GATHER=1) is correct (multi-rank parity) and cut
+            # K1 + gather 42 -> 32 us on 8 B200, but the step got SLOWER (0.207 -> 0.212 ms; pipelined e2e 0.37 -> 0.46 ms):
+            # 1 KB rows at a 3 KB pitch are a poor copy-engine pattern and the statistics barrier ends up waiting for them.
             use_sg = _sharded_g_enabled(b_loc) and ops.ShardedBwdPlan.supported(b_loc, dim, world)
             ctx.use_sg = use_sg
-            # The directional backward does read those rows from all ranks - but only the BACKWARD.  Opt-in experiment
-            # (TRICOLO_B200_DEFER_GATHER=1): they are sent by the copy engines on a side stream while the forward tile
-            # kernel runs and are complete before the statistics barrier below.  Correct (multi-rank parity), K1 + gather
-            # 42 -> 32 us on 8 B200, but the step got SLOWER (0.207 -> 0.212 ms; pipelined e2e 0.37 -> 0.46 ms): 1 KB rows
-            # at a 3 KB pitch are a poor copy-engine pattern, the statistics barrier ends up waiting for them.  Default:
-            # K1 stores every modality itself when the directional backward follows.
-            dsts = ws.dsts
-            deferred = []
-            if not ws.multicast and os.environ.get("TRICOLO_B200_GATHER_ALL", "0") != "1":
-                cols = {b for _, b in pairs}
-                if use_sg or not needs_grad:
-                    dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
-                elif os.environ.get("TRICOLO_B200_DEFER_GATHER", "0") == "1":
-                    deferred = [m for m in range(n) if m not in cols]
-                    dsts = [dsts[0]] + [[a if m in cols else 0 for m, a in enumerate(d)] for d in dsts[1:]]
+            dsts, deferred = _gather_plan(ws.dsts, pairs, n, use_sg, needs_grad, ws.multicast)
             ws.hz.barrier(channel=0)
             invs, xs = ops.l2norm_fwd_bcast(feats, dsts, ws.z_row_stride, op_format)
             ev_sent = None
