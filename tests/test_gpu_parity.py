@@ -749,6 +749,26 @@ def test_bcast_normalise_and_peer_sum_single_gpu(tb):
             assert torch.equal(v[lo:lo + 300, m], zs[m])
             assert torch.equal(invs2[m], invs[m])
         assert float(v[:lo].abs().max()) == 0 and float(v[lo + 300:].abs().max()) == 0
+    # a NULL address at a further destination skips that (destination, tensor): the modality nobody reads remotely
+    # (text under the sharded shared-G backward) costs no NVLink traffic
+    bufs2 = [torch.zeros((700, 3 * 512), dtype=torch.float16, device="cuda") for _ in range(3)]
+    dsts2 = [[b.data_ptr() + (lo * 3 * 512 + m * 512) * 2 for m in range(3)] for b in bufs2]
+    dsts2 = [dsts2[0]] + [[0] + list(d[1:]) for d in dsts2[1:]]
+    ops.l2norm_fwd_bcast(xs, dsts2, 3 * 512, 0)
+    for r, b in enumerate(bufs2):
+        v = b.view(700, 3, 512)
+        for m in range(3):
+            if r > 0 and m == 0:
+                assert float(v[:, m].abs().max()) == 0
+            else:
+                assert torch.equal(v[lo:lo + 300, m], zs[m])
+    # tcl_copy_rows: copy-engine transfer between pitched buffers (columns 8..15 of 24 int16 per row)
+    src = torch.arange(8 * 24, dtype=torch.int16, device="cuda").view(8, 24) + 1
+    dst = torch.zeros_like(src)
+    ops.copy_rows(dst.data_ptr() + 16, 48, src.data_ptr() + 16, 48, 16, 8, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, 8:16], src[:, 8:16])
+    assert int(dst[:, :8].abs().sum()) == 0 and int(dst[:, 16:].abs().sum()) == 0
     parts = [torch.randn(3, 3, 1000, generator=g).cuda() for _ in range(5)]
     want = parts[0].clone()
     for p in parts[1:]:
